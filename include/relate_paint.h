@@ -1,0 +1,137 @@
+/*
+ * relate_paint.h — C ABI of the B200-native replacement for Relate's chromosome-painting
+ * hot path (`Relate --mode Paint`).
+ *
+ * The reference has no plugin/FFI interface: the path sits behind one in-process C++ call
+ * and a set of files.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference checkout, include/...):
+ *
+ *   rp_paint_chunk      <- int Paint(cxxopts::Options&, int chunk_index)      pipeline/Paint.cpp:17-108
+ *   rp_chunk_load       <- Data::Data(6 files) + --painting handling          src/data.cpp:86-97, pipeline/Paint.cpp:21-61
+ *   rp_chunk_create     <- the in-memory Data the painter is handed            src/data.hpp (sequence, r, theta)
+ *   rp_paint_targets    <- for(hap) FastPainting::PaintSteppingStones(...)     pipeline/Paint.cpp:81-87, src/fast_painting.cpp:18-618
+ *   rp_rle_encode       <- CollapsedMatrix<float>::DumpToFile (stepping stone) src/collapsed_matrix.hpp:228-265
+ *   rp_fast_log_device  <- fast_log                                            src/fast_log.hpp:6-22
+ *
+ * Conventions: every function returns 0 on success and a negative RP_E* code on failure and
+ * never calls exit()/abort(); rp_last_error() gives the message of the calling thread's last
+ * failure.  All pointers are plain host pointers unless the name says `dev`.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with RP_ENODEVICE.
+ */
+#ifndef RELATE_PAINT_H
+#define RELATE_PAINT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RP_OK 0
+#define RP_EINVAL (-1)    /* bad argument / inconsistent input            */
+#define RP_EIO (-2)       /* file missing, short read, cannot create       */
+#define RP_ECUDA (-3)     /* CUDA runtime error (message has the details)  */
+#define RP_ENODEVICE (-4) /* no usable CUDA device                         */
+#define RP_ENOMEM (-5)
+#define RP_EUNSUPPORTED (-6) /* e.g. N beyond what one CTA can own        */
+
+/* flags */
+#define RP_FP64 1u /* verification mode: fp64 state and sums (default fp32 state, as north_star) */
+
+typedef struct rp_chunk rp_chunk; /* opaque: a chunk resident in one GPU's HBM */
+
+typedef struct rp_info {
+    int N, L, W;           /* haplotypes, SNPs, windows                                */
+    int device;
+    int words_per_snp;     /* row stride of the SNP-major bit matrix, in 32-bit words  */
+    long long hbm_bytes;   /* bytes of HBM held by the chunk (bit matrices, r, plan)   */
+} rp_info;
+
+typedef struct rp_stats {
+    double ms_h2d;       /* host->device copies issued by the call                       */
+    double ms_prep;      /* bit-pack / transpose / site tables (CUDA events)              */
+    double ms_paint;     /* the forward/backward kernel (CUDA events, launching stream)   */
+    double ms_d2h;       /* device->host copies                                           */
+    double ms_encode;    /* host RLE + file writes (wall)                                 */
+    double ms_total;     /* wall time of the call                                         */
+    long long sites;     /* U = sum_k D_k over the painted targets (visited sites)        */
+    long long cells;     /* painted cells: (#targets) * N * L                             */
+    long long h2d_bytes, d2h_bytes;
+    int launches;        /* kernel launches issued by the call                            */
+    int n_targets;
+    int team_threads;    /* threads cooperating on one (target,direction) job             */
+    int words_per_thread;
+    int ctas;            /* grid size of the paint kernel                                 */
+    int reserved;
+} rp_stats;
+
+typedef struct rp_tune { /* all zero = automatic */
+    int words_per_thread; /* 1 or 2: 32-bit genotype words (32 haplotypes each) per thread  */
+    int ctas_per_sm;      /* persistent CTAs per SM                                          */
+    int reserved[6];
+} rp_tune;
+
+const char *rp_last_error(void);
+int rp_device_count(void);
+const char *rp_version(void);
+
+/* Pinned host memory for callers that want full-speed PCIe copies (cudaMallocHost / cudaFreeHost). */
+int rp_host_alloc(size_t bytes, void **out);
+void rp_host_free(void *p);
+
+/* ---- chunk lifetime ---------------------------------------------------------------- */
+/* hap: L*N chars '0'/'1', SNP-major (Data::sequence); r: L doubles, already multiplied by rho;
+ * wb: n_wb = W+1 window boundaries (wb[0]=0, wb[W]=L); theta as Data::theta.
+ * The chars are copied to the device, bit-packed there (SNP-major and haplotype-major). */
+int rp_chunk_create(int device, int N, int L, const char *hap, const double *r, const int *wb, int n_wb,
+                    double theta, unsigned flags, rp_chunk **out);
+/* Reads <out_dir>/parameters_c<c>.bin and chunk_<c>.{hap,r} (and checks .bp,.dist,.rpos,.state exist, as
+ * the reference loader opens them); painting = the --painting string "theta,rho" or NULL. */
+int rp_chunk_load(int device, const char *out_dir, int chunk_index, const char *painting, unsigned flags,
+                  rp_chunk **out);
+int rp_chunk_info(const rp_chunk *c, rp_info *info);
+void rp_chunk_free(rp_chunk *c);
+int rp_chunk_set_tune(rp_chunk *c, const rp_tune *t);
+
+/* ---- painting ---------------------------------------------------------------------- */
+/* Paint targets k in [k_begin, k_end).  Host outputs (pre-RLE), T = k_end-k_begin:
+ *   alpha, beta        float [T][W][N]   forward / backward stepping-stone vectors
+ *   ls_alpha, ls_beta  float [T][W]      their log-scales
+ *   site_begin/end     int   [T][W]      boundary SNPs (boundarySNP_begin / boundarySNP_end)
+ * Any output pointer may be NULL to skip its copy. */
+int rp_paint_targets(rp_chunk *c, int k_begin, int k_end, float *alpha, float *beta, float *ls_alpha,
+                     float *ls_beta, int *site_begin, int *site_end, rp_stats *stats);
+/* Same computation, results left in HBM (buffers owned by the chunk, valid until the next paint call on
+ * it or rp_chunk_free).  Used by bench.py's device-resident leg and by consumers that stay on the GPU. */
+int rp_paint_targets_device(rp_chunk *c, int k_begin, int k_end, const float **dev_alpha,
+                            const float **dev_beta, const float **dev_ls_alpha, const float **dev_ls_beta,
+                            const int **dev_site_begin, const int **dev_site_end, rp_stats *stats);
+
+/* One call from a host-resident Data to host-resident stepping stones: chunk_create + paint_targets + free.
+ * This is the call bench.py times for its end-to-end ("e2e") number: hap/r go host->device and the
+ * stepping stones come device->host inside it.  tune may be NULL. */
+int rp_paint_from_host(int device, int N, int L, const char *hap, const double *r, const int *wb, int n_wb,
+                       double theta, unsigned flags, const rp_tune *tune, int k_begin, int k_end, float *alpha,
+                       float *beta, float *ls_alpha, float *ls_beta, int *site_begin, int *site_end,
+                       rp_stats *stats);
+
+/* The whole stage: load chunk files, paint every target on the given devices (targets sharded over
+ * devices by visited-site count, no collective), RLE-encode and write
+ * <out_dir>/chunk_<c>/paint/relate_<w>.bin in target order.  devices==NULL: device 0 only. */
+int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
+                   int n_devices, unsigned flags, rp_stats *stats);
+
+/* ---- small pieces exposed for the parity tests -------------------------------------- */
+/* Host encoder used by rp_paint_chunk; returns the number of runs K (vals/lens sized n). */
+int rp_rle_encode(const float *v, int n, float *vals, int *lens);
+/* Evaluates the kernel's device fast_log on n floats (host in/out). */
+int rp_fast_log_device(int device, const float *in, float *out, int n);
+/* Bit-packs on the device and returns the SNP-major and haplotype-major bit matrices (host out). */
+int rp_debug_pack(int device, int N, int L, const char *hap, uint32_t *snp_major, int *words_per_snp,
+                  uint32_t *hap_major, int *words_per_hap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RELATE_PAINT_H */

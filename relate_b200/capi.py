@@ -1,0 +1,257 @@
+"""ctypes binding of ``include/relate_paint.h`` (``librelate_paint.so``).
+
+This is the only way Python code in this repo reaches the painting path: there is no
+Python/numpy/torch implementation of it and no CPU fallback.  If the library is missing or
+no CUDA device is present, calls raise :class:`PaintError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librelate_paint.so")
+
+RP_FP64 = 1
+
+ERRORS = {-1: "EINVAL", -2: "EIO", -3: "ECUDA", -4: "ENODEVICE", -5: "ENOMEM", -6: "EUNSUPPORTED"}
+
+
+class PaintError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"relate_paint: {ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class RpInfo(C.Structure):
+    _fields_ = [("N", C.c_int), ("L", C.c_int), ("W", C.c_int), ("device", C.c_int),
+                ("words_per_snp", C.c_int), ("hbm_bytes", C.c_longlong)]
+
+
+class RpStats(C.Structure):
+    _fields_ = [("ms_h2d", C.c_double), ("ms_prep", C.c_double), ("ms_paint", C.c_double),
+                ("ms_d2h", C.c_double), ("ms_encode", C.c_double), ("ms_total", C.c_double),
+                ("sites", C.c_longlong), ("cells", C.c_longlong), ("h2d_bytes", C.c_longlong),
+                ("d2h_bytes", C.c_longlong), ("launches", C.c_int), ("n_targets", C.c_int),
+                ("team_threads", C.c_int), ("words_per_thread", C.c_int), ("ctas", C.c_int),
+                ("reserved", C.c_int)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+class RpTune(C.Structure):
+    _fields_ = [("words_per_thread", C.c_int), ("ctas_per_sm", C.c_int), ("reserved", C.c_int * 6)]
+
+
+# every symbol include/relate_paint.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "rp_last_error": (C.c_char_p, []),
+    "rp_device_count": (C.c_int, []),
+    "rp_version": (C.c_char_p, []),
+    "rp_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "rp_host_free": (None, [_P]),
+    "rp_chunk_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_double, C.c_uint, C.POINTER(_P)]),
+    "rp_chunk_load": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_uint, C.POINTER(_P)]),
+    "rp_chunk_info": (C.c_int, [_P, C.POINTER(RpInfo)]),
+    "rp_chunk_free": (None, [_P]),
+    "rp_chunk_set_tune": (C.c_int, [_P, C.POINTER(RpTune)]),
+    "rp_paint_targets": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(RpStats)]),
+    "rp_paint_targets_device": (C.c_int, [_P, C.c_int, C.c_int] + [C.POINTER(_P)] * 6 + [C.POINTER(RpStats)]),
+    "rp_paint_from_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_double, C.c_uint,
+                                     C.POINTER(RpTune), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(RpStats)]),
+    "rp_paint_chunk": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, _P, C.c_int, C.c_uint, C.POINTER(RpStats)]),
+    "rp_rle_encode": (C.c_int, [_P, C.c_int, _P, _P]),
+    "rp_fast_log_device": (C.c_int, [C.c_int, _P, _P, C.c_int]),
+    "rp_debug_pack": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int), _P, C.POINTER(C.c_int)]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PaintError(-4, f"{LIB_PATH} not built (run __graft_entry__.build()); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise PaintError(rc, lib().rp_last_error().decode(errors="replace"))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class SteppingStones:
+    """Pre-RLE output of painting targets [k_begin, k_end)."""
+    k_begin: int
+    alpha: np.ndarray       # float32 [T, W, N]
+    beta: np.ndarray        # float32 [T, W, N]
+    ls_alpha: np.ndarray    # float32 [T, W]
+    ls_beta: np.ndarray     # float32 [T, W]
+    site_begin: np.ndarray  # int32 [T, W]
+    site_end: np.ndarray    # int32 [T, W]
+    stats: dict
+
+
+class DeviceChunk:
+    """A chunk resident in one GPU's HBM (``rp_chunk``)."""
+
+    def __init__(self, handle, keep=()):
+        self._h = handle
+        self._keep = keep
+        info = RpInfo()
+        check(lib().rp_chunk_info(self._h, C.byref(info)))
+        self.N, self.L, self.W, self.device = info.N, info.L, info.W, info.device
+        self.words_per_snp, self.hbm_bytes = info.words_per_snp, info.hbm_bytes
+
+    @classmethod
+    def from_arrays(cls, hap: np.ndarray, r: np.ndarray, wb: np.ndarray, theta: float = 0.001,
+                    device: int = 0, fp64: bool = False) -> "DeviceChunk":
+        hap = np.ascontiguousarray(hap, dtype=np.uint8)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        wb = np.ascontiguousarray(wb, dtype=np.int32)
+        L, N = hap.shape
+        h = C.c_void_p()
+        check(lib().rp_chunk_create(device, N, L, _ptr(hap), _ptr(r), _ptr(wb), len(wb), theta,
+                                    RP_FP64 if fp64 else 0, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def load(cls, out_dir: str, chunk_index: int, painting: str | None = None, device: int = 0,
+             fp64: bool = False) -> "DeviceChunk":
+        h = C.c_void_p()
+        check(lib().rp_chunk_load(device, out_dir.encode(), chunk_index,
+                                  painting.encode() if painting is not None else None,
+                                  RP_FP64 if fp64 else 0, C.byref(h)))
+        return cls(h)
+
+    def set_tune(self, words_per_thread: int = 0, ctas_per_sm: int = 0) -> None:
+        t = RpTune(words_per_thread, ctas_per_sm)
+        check(lib().rp_chunk_set_tune(self._h, C.byref(t)))
+
+    def paint_targets(self, k_begin: int = 0, k_end: int | None = None, vectors: bool = True) -> SteppingStones:
+        k_end = self.N if k_end is None else k_end
+        T = k_end - k_begin
+        alpha = np.empty((T, self.W, self.N), np.float32) if vectors else None
+        beta = np.empty((T, self.W, self.N), np.float32) if vectors else None
+        lsa = np.empty((T, self.W), np.float32)
+        lsb = np.empty((T, self.W), np.float32)
+        sb = np.empty((T, self.W), np.int32)
+        se = np.empty((T, self.W), np.int32)
+        st = RpStats()
+        check(lib().rp_paint_targets(self._h, k_begin, k_end, _ptr(alpha), _ptr(beta), _ptr(lsa), _ptr(lsb),
+                                     _ptr(sb), _ptr(se), C.byref(st)))
+        return SteppingStones(k_begin, alpha, beta, lsa, lsb, sb, se, st.as_dict())
+
+    def paint_targets_device(self, k_begin: int = 0, k_end: int | None = None) -> dict:
+        """Paint with results left in HBM; returns the stats (device pointers stay inside the library)."""
+        k_end = self.N if k_end is None else k_end
+        ptrs = [C.c_void_p() for _ in range(6)]
+        st = RpStats()
+        check(lib().rp_paint_targets_device(self._h, k_begin, k_end, *[C.byref(p) for p in ptrs], C.byref(st)))
+        d = st.as_dict()
+        d["dev_ptrs"] = [p.value for p in ptrs]
+        return d
+
+    def close(self) -> None:
+        if self._h:
+            lib().rp_chunk_free(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def paint_from_host(hap, r, wb, theta=0.001, device=0, fp64=False, k_begin=0, k_end=None, out=None,
+                    words_per_thread=0, ctas_per_sm=0) -> SteppingStones:
+    """chunk_create + paint + copy back + free in one C call (the end-to-end call bench.py times).
+
+    ``out`` may carry preallocated (e.g. pinned) arrays: dict with alpha,beta,ls_alpha,ls_beta,site_begin,site_end.
+    """
+    L, N = hap.shape
+    W = len(wb) - 1
+    k_end = N if k_end is None else k_end
+    T = k_end - k_begin
+    if out is None:
+        out = dict(alpha=np.empty((T, W, N), np.float32), beta=np.empty((T, W, N), np.float32),
+                   ls_alpha=np.empty((T, W), np.float32), ls_beta=np.empty((T, W), np.float32),
+                   site_begin=np.empty((T, W), np.int32), site_end=np.empty((T, W), np.int32))
+    st = RpStats()
+    tune = RpTune(words_per_thread, ctas_per_sm)
+    check(lib().rp_paint_from_host(device, N, L, _ptr(hap), _ptr(r), _ptr(wb), len(wb), theta,
+                                   RP_FP64 if fp64 else 0, C.byref(tune), k_begin, k_end, _ptr(out["alpha"]),
+                                   _ptr(out["beta"]), _ptr(out["ls_alpha"]), _ptr(out["ls_beta"]),
+                                   _ptr(out["site_begin"]), _ptr(out["site_end"]), C.byref(st)))
+    return SteppingStones(k_begin, out["alpha"], out["beta"], out["ls_alpha"], out["ls_beta"],
+                          out["site_begin"], out["site_end"], st.as_dict())
+
+
+def paint_chunk(out_dir: str, chunk_index: int, painting: str | None = None, devices=None, fp64: bool = False) -> dict:
+    """The Paint stage (``Relate --mode Paint``): writes ``<out_dir>/chunk_<c>/paint/relate_<w>.bin``."""
+    st = RpStats()
+    dev = None
+    n = 0
+    if devices is not None:
+        dev = np.asarray(list(devices), dtype=np.int32)
+        n = len(dev)
+    check(lib().rp_paint_chunk(out_dir.encode(), chunk_index, painting.encode() if painting is not None else None,
+                               _ptr(dev), n, RP_FP64 if fp64 else 0, C.byref(st)))
+    return st.as_dict()
+
+
+def rle_encode(v: np.ndarray):
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    vals = np.empty(len(v), np.float32)
+    lens = np.empty(len(v), np.int32)
+    k = lib().rp_rle_encode(_ptr(v), len(v), _ptr(vals), _ptr(lens))
+    if k < 0:
+        check(k)
+    return vals[:k].copy(), lens[:k].copy()
+
+
+def fast_log_device(x: np.ndarray, device: int = 0) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    check(lib().rp_fast_log_device(device, _ptr(x), _ptr(out), x.size))
+    return out
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by cudaMallocHost memory (freed when the array's owner is collected)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib().rp_host_alloc(max(n, 1), C.byref(p)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED.append((p, buf))
+    return arr
+
+
+_PINNED: list = []

@@ -1,0 +1,138 @@
+// host_io.hpp — host-side file formats at the Paint boundary.
+//
+//  * chunk loader: what Data::Data(6 files) + Paint() read
+//    (/root/reference/include/src/data.cpp:86-97,531-540; data.hpp:91-101;
+//     collapsed_matrix.hpp:215-225; pipeline/Paint.cpp:21-61)
+//  * stepping-stone record encoder: CollapsedMatrix<float>::DumpToFile
+//    (/root/reference/include/src/collapsed_matrix.hpp:228-265)
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+namespace rp {
+
+struct HostChunk {
+    int N = 0, L = 0;
+    std::vector<int> wb;      // W+1 window boundaries
+    std::vector<char> hap;    // L*N chars, SNP-major
+    std::vector<double> r;    // L, multiplied by rho
+    double theta = 0.001;     // data.cpp:95
+};
+
+inline bool file_exists(const std::string &p)
+{
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+
+// returns "" on success, else the error text
+inline std::string load_chunk_files(const std::string &dir, int chunk, const char *painting, HostChunk &hc)
+{
+    const std::string base = dir + "/chunk_" + std::to_string(chunk);
+    {
+        const std::string p = dir + "/parameters_c" + std::to_string(chunk) + ".bin";
+        FILE *fp = fopen(p.c_str(), "rb");
+        if (!fp) return "cannot open " + p;
+        int nb = 0;
+        bool ok = fread(&hc.N, 4, 1, fp) == 1 && fread(&hc.L, 4, 1, fp) == 1 && fread(&nb, 4, 1, fp) == 1 && nb >= 2;
+        if (ok) {
+            hc.wb.resize(nb);
+            ok = fread(hc.wb.data(), 4, nb, fp) == (size_t)nb;
+        }
+        fclose(fp);
+        if (!ok) return "short read in " + p;
+    }
+    for (const char *ext : {".bp", ".dist", ".rpos", ".state"}) // the reference loader opens all six
+        if (!file_exists(base + ext)) return "missing " + base + ext;
+    {
+        const std::string p = base + ".hap";
+        FILE *fp = fopen(p.c_str(), "rb");
+        if (!fp) return "cannot open " + p;
+        uint64_t uL = 0, uN = 0;
+        bool ok = fread(&uL, 8, 1, fp) == 1 && fread(&uN, 8, 1, fp) == 1;
+        if (ok && ((int)uL != hc.L || (int)uN != hc.N)) {
+            fclose(fp);
+            return p + ": dimensions disagree with parameters file";
+        }
+        if (ok) {
+            hc.hap.resize((size_t)uL * uN);
+            ok = fread(hc.hap.data(), 1, hc.hap.size(), fp) == hc.hap.size();
+        }
+        fclose(fp);
+        if (!ok) return "short read in " + p;
+    }
+    {
+        const std::string p = base + ".r";
+        FILE *fp = fopen(p.c_str(), "rb");
+        if (!fp) return "cannot open " + p;
+        unsigned n = 0;
+        bool ok = fread(&n, 4, 1, fp) == 1 && (int)n == hc.L;
+        if (ok) {
+            hc.r.resize(n);
+            ok = fread(hc.r.data(), 8, n, fp) == n;
+        }
+        fclose(fp);
+        if (!ok) return "short read in " + p;
+    }
+    hc.theta = 0.001;
+    if (painting) { // both numbers are parsed as float (std::stof), Paint.cpp:47,56
+        char *end = nullptr;
+        hc.theta = (double)strtof(painting, &end);
+        double rho = 1.0;
+        if (end && *end == ',') rho = (double)strtof(end + 1, nullptr);
+        for (auto &x : hc.r) x *= rho;
+    }
+    if (hc.wb.back() != hc.L || hc.wb.front() != 0) return "window boundaries do not span the chunk";
+    return "";
+}
+
+// Run-length rule of the stepping-stone codec: v joins the run when
+// fabs(head - v) < 1e-3 * min(head, v)   (float difference, double comparison).
+inline int rle_encode(const float *v, int n, float *vals, int *lens)
+{
+    float head = v[0];
+    int k = 0;
+    vals[0] = head;
+    lens[0] = 1;
+    for (int j = 1; j < n; j++) {
+        const float x = v[j];
+        const float mn = std::min(head, x);
+        if ((double)std::fabs(head - x) < 1e-3 * (double)mn) {
+            lens[k]++;
+        } else {
+            head = x;
+            vals[++k] = x;
+            lens[k] = 1;
+        }
+    }
+    return k + 1;
+}
+
+// appends one record to `out`:  size_t 1; size_t N; int site; float logscale; int K; float val[K]; int len[K]
+inline void append_record(std::vector<char> &out, const float *v, int n, int site, float logscale,
+                          std::vector<float> &vals, std::vector<int> &lens)
+{
+    vals.resize(n);
+    lens.resize(n);
+    const int k = rle_encode(v, n, vals.data(), lens.data());
+    const uint64_t one = 1, sub = (uint64_t)n;
+    const size_t at = out.size();
+    out.resize(at + 28 + (size_t)8 * k);
+    char *p = out.data() + at;
+    memcpy(p, &one, 8);
+    memcpy(p + 8, &sub, 8);
+    memcpy(p + 16, &site, 4);
+    memcpy(p + 20, &logscale, 4);
+    memcpy(p + 24, &k, 4);
+    memcpy(p + 28, vals.data(), (size_t)4 * k);
+    memcpy(p + 28 + (size_t)4 * k, lens.data(), (size_t)4 * k);
+}
+
+} // namespace rp

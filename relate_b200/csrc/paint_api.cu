@@ -1,0 +1,781 @@
+// paint_api.cu — C ABI (include/relate_paint.h) over the kernels in paint_kernels.cuh.
+//
+// Host side of the B200-native `Relate --mode Paint`: what pipeline/Paint.cpp:17-108 and the
+// loop around FastPainting::PaintSteppingStones do in the reference, restructured as
+//   chunk files -> HBM-resident bit matrices -> per-target site tables -> persistent paint kernel
+//   -> stepping stones (device or host) -> RLE records -> chunk_<c>/paint/relate_<w>.bin.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/relate_paint.h"
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "host_io.hpp"
+#include "paint_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define RP_CUDA(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RP_ENODEVICE        \
+                                                                                        : RP_ECUDA,       \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                               \
+    } while (0)
+
+#define RP_TRY(expr)                \
+    do {                            \
+        int rc_ = (expr);           \
+        if (rc_ != RP_OK) return rc_; \
+    } while (0)
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return RP_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return fail(RP_ENOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+        }
+        cap = want;
+        return RP_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+} // namespace
+
+struct rp_chunk {
+    int device = 0;
+    int N = 0, L = 0, W = 0;
+    int wps = 0, lw = 0, nfw = 0, tailn = 0;
+    unsigned flags = 0;
+    double theta = 0.001;
+    int sm_count = 148;
+    std::vector<int> wb;
+    rp_tune tune{};
+    // resident
+    DevBuf G, GT, r, Phi, Plo, wbdev;
+    // per-paint work buffers (grown on demand, reused)
+    DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch;
+    long long *h_total = nullptr; // pinned
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+struct LaunchPlan {
+    int wpt = 1;
+    bool multi = false;
+    int threads = 32;
+};
+
+int plan_launch(const rp_chunk *c, LaunchPlan &lp)
+{
+    const int nfw = c->nfw;
+    const bool fp64 = (c->flags & RP_FP64) != 0;
+    int wpt = c->tune.words_per_thread;
+    if (wpt != 0 && wpt != 1 && wpt != 2) return fail(RP_EINVAL, "words_per_thread must be 0, 1 or 2");
+    if (fp64) wpt = 1;
+    if (wpt == 0) wpt = (nfw <= 32) ? 1 : 2;
+    const int need = std::max(1, (nfw + wpt - 1) / wpt);
+    lp.wpt = wpt;
+    lp.multi = need > 32;
+    lp.threads = ((need + 31) / 32) * 32;
+    const int maxt = (fp64 || wpt == 2) ? 512 : 1024;
+    if (lp.threads > maxt)
+        return fail(RP_EUNSUPPORTED, "N=" + std::to_string(c->N) + " needs " + std::to_string(lp.threads) +
+                                         " threads per team; one CTA owns at most " + std::to_string(maxt * wpt * 32) +
+                                         " haplotypes in this mode (cluster/DSMEM variant not built yet)");
+    return RP_OK;
+}
+
+template <typename T, int WPT, bool MULTI>
+int launch_paint_t(const rp_chunk *c, const rp::PaintParams &P, int threads, int &ctas)
+{
+    auto kern = rp::paint_kernel<T, WPT, MULTI>;
+    int occ = 0;
+    RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
+    if (occ < 1) return fail(RP_ECUDA, "paint kernel does not fit on an SM");
+    if (c->tune.ctas_per_sm > 0) occ = std::min(occ, c->tune.ctas_per_sm);
+    ctas = std::min(P.njobs, occ * c->sm_count);
+    kern<<<ctas, threads, 0, c->stream>>>(P);
+    RP_CUDA(cudaGetLastError());
+    return RP_OK;
+}
+
+// grid size is needed before the launch to size the fp64 scratch; compute it the same way
+template <typename T, int WPT, bool MULTI> int grid_for(const rp_chunk *c, int njobs, int threads, int &ctas)
+{
+    auto kern = rp::paint_kernel<T, WPT, MULTI>;
+    int occ = 0;
+    RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
+    if (occ < 1) return fail(RP_ECUDA, "paint kernel does not fit on an SM");
+    if (c->tune.ctas_per_sm > 0) occ = std::min(occ, c->tune.ctas_per_sm);
+    ctas = std::min(njobs, occ * c->sm_count);
+    return RP_OK;
+}
+
+int launch_paint(const rp_chunk *c, rp::PaintParams &P, const LaunchPlan &lp, DevBuf &scratch, int &ctas)
+{
+    const bool fp64 = (c->flags & RP_FP64) != 0;
+    if (fp64) {
+        if (lp.multi) RP_TRY((grid_for<double, 1, true>(c, P.njobs, lp.threads, ctas)));
+        else RP_TRY((grid_for<double, 1, false>(c, P.njobs, lp.threads, ctas)));
+        RP_TRY(scratch.ensure((size_t)ctas * c->N * sizeof(double)));
+        P.scratch = scratch.as<double>();
+        return lp.multi ? launch_paint_t<double, 1, true>(c, P, lp.threads, ctas)
+                        : launch_paint_t<double, 1, false>(c, P, lp.threads, ctas);
+    }
+    P.scratch = nullptr;
+    if (lp.wpt == 1)
+        return lp.multi ? launch_paint_t<float, 1, true>(c, P, lp.threads, ctas)
+                        : launch_paint_t<float, 1, false>(c, P, lp.threads, ctas);
+    return lp.multi ? launch_paint_t<float, 2, true>(c, P, lp.threads, ctas)
+                    : launch_paint_t<float, 2, false>(c, P, lp.threads, ctas);
+}
+
+// double-double prefix of r: P[s] = sum_{j<s} r[j] as hi+lo
+void dd_prefix(const double *r, int L, std::vector<double> &hi, std::vector<double> &lo)
+{
+    hi.assign((size_t)L + 1, 0.0);
+    lo.assign((size_t)L + 1, 0.0);
+    double h = 0.0, l = 0.0;
+    for (int s = 0; s < L; s++) {
+        const double a = h, b = r[s];
+        const double sum = a + b;
+        const double bb = sum - a;
+        const double err = (a - (sum - bb)) + (b - bb); // TwoSum
+        l += err;
+        const double nh = sum + l; // renormalise (FastTwoSum)
+        l = l - (nh - sum);
+        h = nh;
+        hi[s + 1] = h;
+        lo[s + 1] = l;
+    }
+}
+
+int chunk_from_host(int device, int N, int L, const char *hap, const double *r, const int *wb, int n_wb,
+                    double theta, unsigned flags, rp_chunk **out, rp_stats *st)
+{
+    if (!out || !hap || !r || !wb) return fail(RP_EINVAL, "null argument");
+    if (N < 2 || L < 2 || n_wb < 2) return fail(RP_EINVAL, "need N>=2, L>=2 and at least one window");
+    if (wb[0] != 0 || wb[n_wb - 1] != L) return fail(RP_EINVAL, "window boundaries must start at 0 and end at L");
+    for (int i = 1; i < n_wb; i++)
+        if (wb[i] <= wb[i - 1]) return fail(RP_EINVAL, "window boundaries must be strictly increasing");
+    if (!(theta > 0.0 && theta < 1.0)) return fail(RP_EINVAL, "theta must be in (0,1)");
+    int ndev = 0;
+    RP_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(RP_ENODEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(RP_EINVAL, "device index out of range");
+    RP_CUDA(cudaSetDevice(device));
+
+    rp_chunk *c = new rp_chunk();
+    auto bail = [&](int rc) {
+        std::string keep = g_err;
+        rp_chunk_free(c);
+        g_err = keep;
+        return rc;
+    };
+#define RP_TRYB(expr)                      \
+    do {                                   \
+        int rc_ = (expr);                  \
+        if (rc_ != RP_OK) return bail(rc_); \
+    } while (0)
+#define RP_CUDAB(call)                                                                               \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) return bail(fail(RP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
+    } while (0)
+
+    c->device = device;
+    c->N = N;
+    c->L = L;
+    c->W = n_wb - 1;
+    c->flags = flags;
+    c->theta = theta;
+    c->wb.assign(wb, wb + n_wb);
+    c->nfw = N / 32;
+    c->tailn = N % 32;
+    c->wps = (((N + 31) / 32) + 3) / 4 * 4; // rows padded to 16 bytes
+    c->lw = (L + 31) / 32;
+    cudaDeviceProp prop;
+    RP_CUDAB(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) return bail(fail(RP_ENODEVICE, "device is not sm_100-class; this library ships sm_100a code only"));
+    RP_CUDAB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) RP_CUDAB(cudaEventCreate(&e));
+    RP_CUDAB(cudaMallocHost(&c->h_total, sizeof(long long)));
+    LaunchPlan lp;
+    RP_TRYB(plan_launch(c, lp));
+
+    const double t0 = now_ms();
+    DevBuf chars;
+    const size_t nchar = (size_t)L * N;
+    RP_TRYB(chars.ensure(nchar));
+    RP_TRYB(c->G.ensure((size_t)L * c->wps * 4));
+    RP_TRYB(c->GT.ensure((size_t)N * c->lw * 4));
+    RP_TRYB(c->r.ensure((size_t)L * 8));
+    RP_TRYB(c->Phi.ensure((size_t)(L + 1) * 8));
+    RP_TRYB(c->Plo.ensure((size_t)(L + 1) * 8));
+    RP_TRYB(c->wbdev.ensure((size_t)n_wb * 4));
+    RP_CUDAB(cudaEventRecord(c->ev[0], c->stream));
+    RP_CUDAB(cudaMemcpyAsync(chars.p, hap, nchar, cudaMemcpyHostToDevice, c->stream));
+    std::vector<double> hi, lo;
+    dd_prefix(r, L, hi, lo);
+    RP_CUDAB(cudaMemcpyAsync(c->r.p, r, (size_t)L * 8, cudaMemcpyHostToDevice, c->stream));
+    RP_CUDAB(cudaMemcpyAsync(c->Phi.p, hi.data(), (size_t)(L + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    RP_CUDAB(cudaMemcpyAsync(c->Plo.p, lo.data(), (size_t)(L + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    RP_CUDAB(cudaMemcpyAsync(c->wbdev.p, wb, (size_t)n_wb * 4, cudaMemcpyHostToDevice, c->stream));
+    RP_CUDAB(cudaEventRecord(c->ev[1], c->stream));
+    {
+        const long long total = (long long)L * c->wps;
+        const int th = 256;
+        rp::pack_snp_major_kernel<<<(unsigned)((total + th - 1) / th), th, 0, c->stream>>>(
+            chars.as<unsigned char>(), N, L, c->G.as<uint32_t>(), c->wps);
+        RP_CUDAB(cudaGetLastError());
+        dim3 grid((N + 31) / 32, (c->lw + 31) / 32), block(32, 32);
+        rp::transpose_bits_kernel<<<grid, block, 0, c->stream>>>(c->G.as<uint32_t>(), c->wps, N, L,
+                                                                 c->GT.as<uint32_t>(), c->lw);
+        RP_CUDAB(cudaGetLastError());
+    }
+    RP_CUDAB(cudaEventRecord(c->ev[2], c->stream));
+    RP_CUDAB(cudaStreamSynchronize(c->stream));
+    chars.release();
+    if (st) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+        st->ms_h2d += a;
+        st->ms_prep += b;
+        st->h2d_bytes += (long long)nchar + (long long)L * 8 + (long long)(L + 1) * 16 + (long long)n_wb * 4;
+        st->launches += 2;
+        st->ms_total += now_ms() - t0;
+    }
+    *out = c;
+    return RP_OK;
+#undef RP_TRYB
+#undef RP_CUDAB
+}
+
+// Runs prep + paint for targets [k0,k1) on the chunk's stream; results stay in c->alpha etc.
+int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
+{
+    if (!c) return fail(RP_EINVAL, "null chunk");
+    if (k0 < 0 || k1 > c->N || k0 >= k1) return fail(RP_EINVAL, "bad target range");
+    RP_CUDA(cudaSetDevice(c->device));
+    const bool fp64 = (c->flags & RP_FP64) != 0;
+    const int nt = k1 - k0, W = c->W, N = c->N;
+    LaunchPlan lp;
+    RP_TRY(plan_launch(c, lp));
+    const size_t nw = (size_t)nt * W;
+    RP_TRY(c->counts.ensure((size_t)nt * 4));
+    RP_TRY(c->off.ensure((size_t)(nt + 1) * 8));
+    RP_TRY(c->ia.ensure(nw * 4));
+    RP_TRY(c->ib.ensure(nw * 4));
+    RP_TRY(c->lsA.ensure(nw * 8));
+    RP_TRY(c->lsB.ensure(nw * 8));
+    RP_TRY(c->sb.ensure(nw * 4));
+    RP_TRY(c->se.ensure(nw * 4));
+    RP_TRY(c->lsa.ensure(nw * 4));
+    RP_TRY(c->lsb.ensure(nw * 4));
+    RP_TRY(c->alpha.ensure(nw * N * 4));
+    RP_TRY(c->beta.ensure(nw * N * 4));
+    RP_TRY(c->queue.ensure(4));
+
+    cudaStream_t s = c->stream;
+    int launches = 0;
+    RP_CUDA(cudaEventRecord(c->ev[0], s));
+    const int th = 256, wpb = th / 32;
+    const unsigned gw = (unsigned)((nt + wpb - 1) / wpb);
+    rp::count_sites_kernel<<<gw, th, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->counts.as<int>());
+    RP_CUDA(cudaGetLastError());
+    rp::scan_counts_kernel<<<1, 1024, 0, s>>>(c->counts.as<int>(), nt, c->off.as<long long>());
+    RP_CUDA(cudaGetLastError());
+    launches += 2;
+    RP_CUDA(cudaMemcpyAsync(c->h_total, c->off.as<long long>() + nt, 8, cudaMemcpyDeviceToHost, s));
+    RP_CUDA(cudaStreamSynchronize(s));
+    const long long U = *c->h_total;
+    const size_t entsz = fp64 ? sizeof(rp::EntD) : sizeof(rp::EntF);
+    RP_TRY(c->ent.ensure((size_t)U * entsz));
+
+    rp::TableConsts tc;
+    const double ntheta = 1.0 - c->theta;
+    tc.log_ntheta = log(ntheta);
+    tc.log_small = log(0.01);
+    tc.Nm1 = N - 1.0;
+    const unsigned gb = (unsigned)((nw + th - 1) / th);
+    if (fp64) {
+        auto *e = c->ent.as<rp::EntD>();
+        rp::fill_sites_kernel<<<gw, th, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->off.as<long long>(), e);
+        rp::boundaries_kernel<<<gb, th, 0, s>>>(e, c->off.as<long long>(), nt, W, c->wbdev.as<int>(), c->ia.as<int>(),
+                                                c->ib.as<int>(), c->sb.as<int>(), c->se.as<int>());
+        rp::tables_kernel<<<gw, th, 0, s>>>(e, c->off.as<long long>(), nt, c->L, W, c->r.as<double>(),
+                                            c->Phi.as<double>(), c->Plo.as<double>(), tc, c->ia.as<int>(),
+                                            c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>());
+    } else {
+        auto *e = c->ent.as<rp::EntF>();
+        rp::fill_sites_kernel<<<gw, th, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->off.as<long long>(), e);
+        rp::boundaries_kernel<<<gb, th, 0, s>>>(e, c->off.as<long long>(), nt, W, c->wbdev.as<int>(), c->ia.as<int>(),
+                                                c->ib.as<int>(), c->sb.as<int>(), c->se.as<int>());
+        rp::tables_kernel<<<gw, th, 0, s>>>(e, c->off.as<long long>(), nt, c->L, W, c->r.as<double>(),
+                                            c->Phi.as<double>(), c->Plo.as<double>(), tc, c->ia.as<int>(),
+                                            c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>());
+    }
+    RP_CUDA(cudaGetLastError());
+    launches += 3;
+    RP_CUDA(cudaMemsetAsync(c->queue.p, 0, 4, s));
+    RP_CUDA(cudaEventRecord(c->ev[1], s));
+
+    rp::PaintParams P{};
+    P.G = c->G.as<uint32_t>();
+    P.wps = c->wps;
+    P.N = N;
+    P.L = c->L;
+    P.W = W;
+    P.nfw = c->nfw;
+    P.tailn = c->tailn;
+    P.k0 = k0;
+    P.nt = nt;
+    P.njobs = 2 * nt;
+    P.ent = c->ent.p;
+    P.off = c->off.as<long long>();
+    P.ia = c->ia.as<int>();
+    P.ib = c->ib.as<int>();
+    P.lsA = c->lsA.as<double>();
+    P.lsB = c->lsB.as<double>();
+    P.alpha = c->alpha.as<float>();
+    P.beta = c->beta.as<float>();
+    P.ls_alpha = c->lsa.as<float>();
+    P.ls_beta = c->lsb.as<float>();
+    P.queue = c->queue.as<int>();
+    // fast_painting.hpp:26-39, evaluated in fp64 exactly as written there
+    const double theta_ratio = c->theta / (1.0 - c->theta) - 1.0;
+    P.tau_mul = 1.0 * theta_ratio + 1.0;
+    P.prior_n = ntheta / (N - 1.0);
+    P.ntheta = ntheta;
+    P.inv_ntheta = 1.0 / ntheta;
+    P.lower = 1e-10;
+    P.upper = 1.0 / P.lower;
+    int ctas = 0;
+    RP_TRY(launch_paint(c, P, lp, c->scratch, ctas));
+    launches += 1;
+    RP_CUDA(cudaEventRecord(c->ev[2], s));
+    RP_CUDA(cudaStreamSynchronize(s));
+    if (st) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+        st->ms_prep += a;
+        st->ms_paint += b;
+        st->sites += U;
+        st->cells += (long long)nt * N * c->L;
+        st->launches += launches;
+        st->n_targets += nt;
+        st->team_threads = lp.threads;
+        st->words_per_thread = lp.wpt;
+        st->ctas = ctas;
+        st->d2h_bytes += 8;
+    }
+    return RP_OK;
+}
+
+int copy_out(rp_chunk *c, int nt, float *alpha, float *beta, float *ls_alpha, float *ls_beta, int *site_begin,
+             int *site_end, rp_stats *st)
+{
+    cudaStream_t s = c->stream;
+    const size_t nw = (size_t)nt * c->W;
+    long long bytes = 0;
+    RP_CUDA(cudaEventRecord(c->ev[0], s));
+    if (alpha) { RP_CUDA(cudaMemcpyAsync(alpha, c->alpha.p, nw * c->N * 4, cudaMemcpyDeviceToHost, s)); bytes += nw * c->N * 4; }
+    if (beta) { RP_CUDA(cudaMemcpyAsync(beta, c->beta.p, nw * c->N * 4, cudaMemcpyDeviceToHost, s)); bytes += nw * c->N * 4; }
+    if (ls_alpha) { RP_CUDA(cudaMemcpyAsync(ls_alpha, c->lsa.p, nw * 4, cudaMemcpyDeviceToHost, s)); bytes += nw * 4; }
+    if (ls_beta) { RP_CUDA(cudaMemcpyAsync(ls_beta, c->lsb.p, nw * 4, cudaMemcpyDeviceToHost, s)); bytes += nw * 4; }
+    if (site_begin) { RP_CUDA(cudaMemcpyAsync(site_begin, c->sb.p, nw * 4, cudaMemcpyDeviceToHost, s)); bytes += nw * 4; }
+    if (site_end) { RP_CUDA(cudaMemcpyAsync(site_end, c->se.p, nw * 4, cudaMemcpyDeviceToHost, s)); bytes += nw * 4; }
+    RP_CUDA(cudaEventRecord(c->ev[1], s));
+    RP_CUDA(cudaStreamSynchronize(s));
+    if (st) {
+        float a = 0;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+        st->ms_d2h += a;
+        st->d2h_bytes += bytes;
+    }
+    return RP_OK;
+}
+
+} // namespace
+
+// =========================================================================================
+extern "C" {
+
+const char *rp_last_error(void) { return g_err.c_str(); }
+
+const char *rp_version(void) { return "relate_b200 paint 0.1 (sm_100a)"; }
+
+int rp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rp_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(RP_EINVAL, "null argument");
+    RP_CUDA(cudaMallocHost(out, bytes));
+    return RP_OK;
+}
+
+void rp_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int rp_chunk_create(int device, int N, int L, const char *hap, const double *r, const int *wb, int n_wb,
+                    double theta, unsigned flags, rp_chunk **out)
+{
+    return chunk_from_host(device, N, L, hap, r, wb, n_wb, theta, flags, out, nullptr);
+}
+
+int rp_chunk_load(int device, const char *out_dir, int chunk_index, const char *painting, unsigned flags,
+                  rp_chunk **out)
+{
+    if (!out_dir || !out) return fail(RP_EINVAL, "null argument");
+    rp::HostChunk hc;
+    std::string err = rp::load_chunk_files(out_dir, chunk_index, painting, hc);
+    if (!err.empty()) return fail(RP_EIO, err);
+    return chunk_from_host(device, hc.N, hc.L, hc.hap.data(), hc.r.data(), hc.wb.data(), (int)hc.wb.size(),
+                           hc.theta, flags, out, nullptr);
+}
+
+int rp_chunk_info(const rp_chunk *c, rp_info *info)
+{
+    if (!c || !info) return fail(RP_EINVAL, "null argument");
+    info->N = c->N;
+    info->L = c->L;
+    info->W = c->W;
+    info->device = c->device;
+    info->words_per_snp = c->wps;
+    info->hbm_bytes = (long long)(c->G.cap + c->GT.cap + c->r.cap + c->Phi.cap + c->Plo.cap + c->wbdev.cap);
+    return RP_OK;
+}
+
+int rp_chunk_set_tune(rp_chunk *c, const rp_tune *t)
+{
+    if (!c) return fail(RP_EINVAL, "null chunk");
+    rp_tune old = c->tune;
+    c->tune = t ? *t : rp_tune{};
+    LaunchPlan lp;
+    int rc = plan_launch(c, lp);
+    if (rc != RP_OK) c->tune = old;
+    return rc;
+}
+
+void rp_chunk_free(rp_chunk *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
+                      &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch})
+        b->release();
+    if (c->h_total) cudaFreeHost(c->h_total);
+    for (auto &e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int rp_paint_targets_device(rp_chunk *c, int k_begin, int k_end, const float **dev_alpha, const float **dev_beta,
+                            const float **dev_ls_alpha, const float **dev_ls_beta, const int **dev_site_begin,
+                            const int **dev_site_end, rp_stats *stats)
+{
+    const double t0 = now_ms();
+    RP_TRY(paint_device(c, k_begin, k_end, stats));
+    if (dev_alpha) *dev_alpha = c->alpha.as<float>();
+    if (dev_beta) *dev_beta = c->beta.as<float>();
+    if (dev_ls_alpha) *dev_ls_alpha = c->lsa.as<float>();
+    if (dev_ls_beta) *dev_ls_beta = c->lsb.as<float>();
+    if (dev_site_begin) *dev_site_begin = c->sb.as<int>();
+    if (dev_site_end) *dev_site_end = c->se.as<int>();
+    if (stats) stats->ms_total += now_ms() - t0;
+    return RP_OK;
+}
+
+int rp_paint_targets(rp_chunk *c, int k_begin, int k_end, float *alpha, float *beta, float *ls_alpha,
+                     float *ls_beta, int *site_begin, int *site_end, rp_stats *stats)
+{
+    const double t0 = now_ms();
+    RP_TRY(paint_device(c, k_begin, k_end, stats));
+    RP_TRY(copy_out(c, k_end - k_begin, alpha, beta, ls_alpha, ls_beta, site_begin, site_end, stats));
+    if (stats) stats->ms_total += now_ms() - t0;
+    return RP_OK;
+}
+
+int rp_paint_from_host(int device, int N, int L, const char *hap, const double *r, const int *wb, int n_wb,
+                       double theta, unsigned flags, const rp_tune *tune, int k_begin, int k_end, float *alpha,
+                       float *beta, float *ls_alpha, float *ls_beta, int *site_begin, int *site_end,
+                       rp_stats *stats)
+{
+    const double t0 = now_ms();
+    rp_chunk *c = nullptr;
+    RP_TRY(chunk_from_host(device, N, L, hap, r, wb, n_wb, theta, flags, &c, stats));
+    int rc = RP_OK;
+    if (tune) rc = rp_chunk_set_tune(c, tune);
+    if (rc == RP_OK) rc = paint_device(c, k_begin, k_end, stats);
+    if (rc == RP_OK) rc = copy_out(c, k_end - k_begin, alpha, beta, ls_alpha, ls_beta, site_begin, site_end, stats);
+    std::string keep = g_err;
+    rp_chunk_free(c);
+    g_err = keep;
+    if (stats) stats->ms_total = now_ms() - t0;
+    return rc;
+}
+
+int rp_rle_encode(const float *v, int n, float *vals, int *lens)
+{
+    if (!v || !vals || !lens || n < 1) return fail(RP_EINVAL, "bad argument");
+    return rp::rle_encode(v, n, vals, lens);
+}
+
+int rp_fast_log_device(int device, const float *in, float *out, int n)
+{
+    if (!in || !out || n < 1) return fail(RP_EINVAL, "bad argument");
+    RP_CUDA(cudaSetDevice(device));
+    float *d = nullptr;
+    RP_CUDA(cudaMalloc(&d, (size_t)n * 8));
+    cudaError_t e = cudaMemcpy(d, in, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rp::fast_log_kernel<<<(n + 255) / 256, 256>>>(d, d + n, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d + n, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(RP_ECUDA, cudaGetErrorString(e));
+    return RP_OK;
+}
+
+int rp_debug_pack(int device, int N, int L, const char *hap, uint32_t *snp_major, int *words_per_snp,
+                  uint32_t *hap_major, int *words_per_hap)
+{
+    std::vector<double> r((size_t)L, 1e-4);
+    int wb[2] = {0, L};
+    rp_chunk *c = nullptr;
+    RP_TRY(chunk_from_host(device, N, L, hap, r.data(), wb, 2, 0.001, 0, &c, nullptr));
+    cudaError_t e = cudaSuccess;
+    if (snp_major) e = cudaMemcpy(snp_major, c->G.p, (size_t)L * c->wps * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && hap_major) e = cudaMemcpy(hap_major, c->GT.p, (size_t)N * c->lw * 4, cudaMemcpyDeviceToHost);
+    if (words_per_snp) *words_per_snp = c->wps;
+    if (words_per_hap) *words_per_hap = c->lw;
+    rp_chunk_free(c);
+    if (e != cudaSuccess) return fail(RP_ECUDA, cudaGetErrorString(e));
+    return RP_OK;
+}
+
+// ---- the whole stage (pipeline/Paint.cpp:17-108) ----------------------------------------
+// Targets are cut into batches; device threads pull batch indices from one counter (dynamic
+// balance over GPUs, no collective), paint + copy back, RLE-encode their batch per window on
+// host threads, and append to the W files strictly in batch order.
+int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices, int n_devices,
+                   unsigned flags, rp_stats *stats)
+{
+    if (!out_dir) return fail(RP_EINVAL, "null out_dir");
+    const double t0 = now_ms();
+    rp::HostChunk hc;
+    {
+        std::string err = rp::load_chunk_files(out_dir, chunk_index, painting, hc);
+        if (!err.empty()) return fail(RP_EIO, err);
+    }
+    int ndev = rp_device_count();
+    if (ndev < 1) return fail(RP_ENODEVICE, "no CUDA device (there is no CPU fallback)");
+    std::vector<int> devs;
+    if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+    else devs.push_back(0);
+    for (int d : devs)
+        if (d < 0 || d >= ndev) return fail(RP_EINVAL, "device index out of range");
+
+    const int N = hc.N, W = (int)hc.wb.size() - 1;
+    const std::string cdir = std::string(out_dir) + "/chunk_" + std::to_string(chunk_index);
+    const std::string pdir = cdir + "/paint";
+    // filesys::MakeDir semantics (src/filesystem.cpp:4-24): create if absent, mode 0700
+    for (const std::string &d : {cdir, pdir}) {
+        struct stat sb;
+        if (stat(d.c_str(), &sb) != 0 && mkdir(d.c_str(), 0700) != 0) return fail(RP_EIO, "could not create directory " + d);
+    }
+    std::vector<FILE *> files(W, nullptr);
+    auto close_all = [&]() {
+        for (FILE *f : files)
+            if (f) fclose(f);
+    };
+    for (int w = 0; w < W; w++) {
+        const std::string p = pdir + "/relate_" + std::to_string(w) + ".bin";
+        files[w] = fopen(p.c_str(), "wb");
+        if (!files[w]) {
+            close_all();
+            return fail(RP_EIO, "cannot create " + p);
+        }
+    }
+
+    // batch size: bound the pinned staging per device (~1.5 GB), keep the GPU full
+    const size_t per_target = (size_t)2 * W * N * 4;
+    long long bsz = (long long)((1536ull << 20) / per_target);
+    bsz = std::max<long long>(bsz, 64);
+    bsz = std::min<long long>(bsz, N);
+    if ((int)devs.size() > 1) bsz = std::min<long long>(bsz, std::max<long long>(64, (N + 2 * (long long)devs.size() - 1) / (2 * (long long)devs.size())));
+    const int B = (int)bsz;
+    const int nbatch = (N + B - 1) / B;
+
+    std::atomic<int> next_batch{0};
+    std::mutex mu;
+    std::condition_variable cv;
+    int next_write = 0;
+    int first_rc = RP_OK;
+    std::string first_err;
+    std::vector<rp_stats> dstats(devs.size());
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int enc_threads = (int)std::max<unsigned>(1, std::min<unsigned>(hw / (unsigned)devs.size(), 32));
+
+    auto worker = [&](int di) {
+        rp_stats &st = dstats[di];
+        memset(&st, 0, sizeof st);
+        rp_chunk *c = nullptr;
+        int rc = chunk_from_host(devs[di], hc.N, hc.L, hc.hap.data(), hc.r.data(), hc.wb.data(), (int)hc.wb.size(),
+                                 hc.theta, flags, &c, &st);
+        float *ha = nullptr, *hb = nullptr;
+        std::vector<float> lsa, lsb;
+        std::vector<int> sb, se;
+        if (rc == RP_OK) {
+            const size_t vb = (size_t)B * W * N * 4;
+            if (cudaMallocHost(&ha, vb) != cudaSuccess || cudaMallocHost(&hb, vb) != cudaSuccess)
+                rc = fail(RP_ENOMEM, "cudaMallocHost for the staging buffers failed");
+            lsa.resize((size_t)B * W);
+            lsb.resize((size_t)B * W);
+            sb.resize((size_t)B * W);
+            se.resize((size_t)B * W);
+        }
+        std::vector<std::vector<char>> blobs(W);
+        while (rc == RP_OK) {
+            const int b = next_batch.fetch_add(1);
+            if (b >= nbatch) break;
+            const int k0 = b * B, k1 = std::min(N, k0 + B), nt = k1 - k0;
+            rc = rp_paint_targets(c, k0, k1, ha, hb, lsa.data(), lsb.data(), sb.data(), se.data(), &st);
+            if (rc != RP_OK) break;
+            const double te = now_ms();
+            std::vector<std::thread> pool;
+            for (int ti = 0; ti < enc_threads; ti++) {
+                pool.emplace_back([&, ti]() {
+                    std::vector<float> vals;
+                    std::vector<int> lens;
+                    for (int w = ti; w < W; w += enc_threads) {
+                        std::vector<char> &out = blobs[w];
+                        out.clear();
+                        const int a0 = hc.wb[w], b0 = hc.wb[w + 1] - 1;
+                        for (int kk = 0; kk < nt; kk++) { // fast_painting.cpp:589-601
+                            const size_t at = out.size();
+                            out.resize(at + 8);
+                            memcpy(out.data() + at, &a0, 4);
+                            memcpy(out.data() + at + 4, &b0, 4);
+                            const size_t row = ((size_t)kk * W + w);
+                            rp::append_record(out, ha + row * N, N, sb[row], lsa[row], vals, lens);
+                            rp::append_record(out, hb + row * N, N, se[row], lsb[row], vals, lens);
+                        }
+                    }
+                });
+            }
+            for (auto &t : pool) t.join();
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return next_write == b || first_rc != RP_OK; });
+                if (first_rc == RP_OK) {
+                    for (int w = 0; w < W && rc == RP_OK; w++)
+                        if (fwrite(blobs[w].data(), 1, blobs[w].size(), files[w]) != blobs[w].size())
+                            rc = fail(RP_EIO, "short write to relate_" + std::to_string(w) + ".bin");
+                    next_write = b + 1;
+                }
+                cv.notify_all();
+            }
+            st.ms_encode += now_ms() - te;
+        }
+        if (rc != RP_OK) {
+            std::unique_lock<std::mutex> lk(mu);
+            if (first_rc == RP_OK) {
+                first_rc = rc;
+                first_err = g_err;
+            }
+            cv.notify_all();
+        }
+        if (ha) cudaFreeHost(ha);
+        if (hb) cudaFreeHost(hb);
+        if (c) rp_chunk_free(c);
+    };
+    std::vector<std::thread> threads;
+    for (int di = 0; di < (int)devs.size(); di++) threads.emplace_back(worker, di);
+    for (auto &t : threads) t.join();
+    close_all();
+    if (first_rc != RP_OK) return fail(first_rc, first_err);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (const rp_stats &s : dstats) {
+            stats->ms_h2d = std::max(stats->ms_h2d, s.ms_h2d);
+            stats->ms_prep = std::max(stats->ms_prep, s.ms_prep);
+            stats->ms_paint = std::max(stats->ms_paint, s.ms_paint);
+            stats->ms_d2h = std::max(stats->ms_d2h, s.ms_d2h);
+            stats->ms_encode = std::max(stats->ms_encode, s.ms_encode);
+            stats->sites += s.sites;
+            stats->cells += s.cells;
+            stats->h2d_bytes += s.h2d_bytes;
+            stats->d2h_bytes += s.d2h_bytes;
+            stats->launches += s.launches;
+            stats->n_targets += s.n_targets;
+            stats->team_threads = s.team_threads;
+            stats->words_per_thread = s.words_per_thread;
+            stats->ctas = s.ctas;
+        }
+        stats->ms_total = now_ms() - t0;
+    }
+    return RP_OK;
+}
+
+} // extern "C"
