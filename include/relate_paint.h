@@ -93,6 +93,9 @@ int rp_chunk_load(int device, const char *out_dir, int chunk_index, const char *
 int rp_chunk_info(const rp_chunk *c, rp_info *info);
 void rp_chunk_free(rp_chunk *c);
 int rp_chunk_set_tune(rp_chunk *c, const rp_tune *t);
+/* Issue this chunk's copies and kernels on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores
+ * the chunk's own stream).  Lets a caller bracket the work with events of its own. */
+int rp_chunk_set_stream(rp_chunk *c, void *cuda_stream);
 
 /* ---- painting ---------------------------------------------------------------------- */
 /* Paint targets k in [k_begin, k_end).  Host outputs (pre-RLE), T = k_end-k_begin:
@@ -127,6 +130,10 @@ int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, c
 int rp_rle_encode(const float *v, int n, float *vals, int *lens);
 /* Evaluates the kernel's device fast_log on n floats (host in/out). */
 int rp_fast_log_device(int device, const float *in, float *out, int n);
+/* Measures the FP32 lane-operation rate of the device with the paint step's instruction mix (packed add, scalar
+ * multiply, packed add; no memory): the measured denominator of the roofline bench.py reports.  `mix` uses
+ * add.f32x2 as the kernel does, `scalar` the same arithmetic with scalar adds. */
+int rp_peak_fp32(int device, double *lane_ops_per_s_mix, double *lane_ops_per_s_scalar);
 /* Bit-packs on the device and returns the SNP-major and haplotype-major bit matrices (host out). */
 int rp_debug_pack(int device, int N, int L, const char *hap, uint32_t *snp_major, int *words_per_snp,
                   uint32_t *hap_major, int *words_per_hap);

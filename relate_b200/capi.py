@@ -60,6 +60,8 @@ SYMBOLS = {
     "rp_chunk_info": (C.c_int, [_P, C.POINTER(RpInfo)]),
     "rp_chunk_free": (None, [_P]),
     "rp_chunk_set_tune": (C.c_int, [_P, C.POINTER(RpTune)]),
+    "rp_chunk_set_stream": (C.c_int, [_P, _P]),
+    "rp_peak_fp32": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rp_paint_targets": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(RpStats)]),
     "rp_paint_targets_device": (C.c_int, [_P, C.c_int, C.c_int] + [C.POINTER(_P)] * 6 + [C.POINTER(RpStats)]),
     "rp_paint_from_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_double, C.c_uint,
@@ -145,6 +147,10 @@ class DeviceChunk:
     def set_tune(self, words_per_thread: int = 0, ctas_per_sm: int = 0) -> None:
         t = RpTune(words_per_thread, ctas_per_sm)
         check(lib().rp_chunk_set_tune(self._h, C.byref(t)))
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        """Issue the chunk's work on an external CUDA stream (e.g. torch.cuda.Stream().cuda_stream)."""
+        check(lib().rp_chunk_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
     def paint_targets(self, k_begin: int = 0, k_end: int | None = None, vectors: bool = True) -> SteppingStones:
         k_end = self.N if k_end is None else k_end
@@ -240,6 +246,13 @@ def fast_log_device(x: np.ndarray, device: int = 0) -> np.ndarray:
     out = np.empty_like(x)
     check(lib().rp_fast_log_device(device, _ptr(x), _ptr(out), x.size))
     return out
+
+
+def peak_fp32(device: int = 0):
+    """-> (lane-ops/s with the kernel's packed mix, lane-ops/s with scalar adds), measured on the device."""
+    a, b = C.c_double(), C.c_double()
+    check(lib().rp_peak_fp32(device, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def pinned_empty(shape, dtype):

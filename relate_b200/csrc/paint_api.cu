@@ -98,7 +98,8 @@ struct rp_chunk {
     // per-paint work buffers (grown on demand, reused)
     DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch;
     long long *h_total = nullptr; // pinned
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // the stream every copy and kernel of this chunk is issued on
+    cudaStream_t own_stream = nullptr;   // created by the library; `stream` may be replaced by a caller's
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -243,7 +244,8 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
     RP_CUDAB(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     if (prop.major < 10) return bail(fail(RP_ENODEVICE, "device is not sm_100-class; this library ships sm_100a code only"));
-    RP_CUDAB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RP_CUDAB(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     for (auto &e : c->ev) RP_CUDAB(cudaEventCreate(&e));
     RP_CUDAB(cudaMallocHost(&c->h_total, sizeof(long long)));
     LaunchPlan lp;
@@ -515,6 +517,15 @@ int rp_chunk_set_tune(rp_chunk *c, const rp_tune *t)
     return rc;
 }
 
+int rp_chunk_set_stream(rp_chunk *c, void *cuda_stream)
+{
+    if (!c) return fail(RP_EINVAL, "null chunk");
+    RP_CUDA(cudaSetDevice(c->device));
+    RP_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return RP_OK;
+}
+
 void rp_chunk_free(rp_chunk *c)
 {
     if (!c) return;
@@ -525,7 +536,7 @@ void rp_chunk_free(rp_chunk *c)
     if (c->h_total) cudaFreeHost(c->h_total);
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -594,6 +605,43 @@ int rp_fast_log_device(int device, const float *in, float *out, int n)
     if (e == cudaSuccess) e = cudaMemcpy(out, d + n, (size_t)n * 4, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail(RP_ECUDA, cudaGetErrorString(e));
+    return RP_OK;
+}
+
+// FP32 issue-rate microbenchmark: the same instruction mix as the paint step (packed adds + scalar multiplies,
+// no memory), to give the roofline a measured denominator on the box it runs on.
+int rp_peak_fp32(int device, double *lane_ops_per_s_mix, double *lane_ops_per_s_scalar)
+{
+    RP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RP_CUDA(cudaGetDeviceProperties(&prop, device));
+    float *d = nullptr;
+    RP_CUDA(cudaMalloc(&d, 4096 * sizeof(float)));
+    cudaEvent_t e0, e1;
+    RP_CUDA(cudaEventCreate(&e0));
+    RP_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, threads = 256, blocks = prop.multiProcessorCount * 8;
+    double res[2] = {0, 0};
+    for (int mode = 0; mode < 2; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            RP_CUDA(cudaEventRecord(e0));
+            if (mode == 0) rp::peak_fp32_kernel<true><<<blocks, threads>>>(d, iters, 0.999f, 1e-3f);
+            else rp::peak_fp32_kernel<false><<<blocks, threads>>>(d, iters, 0.999f, 1e-3f);
+            RP_CUDA(cudaEventRecord(e1));
+            RP_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            RP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        // per thread and iteration: 16 pairs x (add, mul, add) = 96 lane-ops
+        res[mode] = (double)blocks * threads * iters * 96.0 / (best * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (lane_ops_per_s_mix) *lane_ops_per_s_mix = res[0];
+    if (lane_ops_per_s_scalar) *lane_ops_per_s_scalar = res[1];
     return RP_OK;
 }
 

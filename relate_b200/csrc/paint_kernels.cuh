@@ -47,6 +47,36 @@ __global__ void fast_log_kernel(const float *in, float *out, int n)
     if (i < n) out[i] = fast_log_dev(in[i]);
 }
 
+// FP32 issue-rate microbenchmark with the paint step's instruction mix and no memory traffic:
+// per pair  x = x + R (packed), x.lo *= m, x.hi *= m (scalar), S = S + x (packed)  -> 6 lane-ops, 4 (PACKED) or
+// 6 issue slots.  Used only to measure the roofline denominator.
+template <bool PACKED>
+__global__ void __launch_bounds__(256) peak_fp32_kernel(float *out, int iters, float m, float r)
+{
+    float2 a[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) a[j] = make_float2(1.0f + j + threadIdx.x, 2.0f + j);
+    float2 S0 = make_float2(0.f, 0.f), S1 = make_float2(0.f, 0.f);
+    const float2 R2 = make_float2(r, r);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            float2 v;
+            if (PACKED) v = __fadd2_rn(a[j], R2);
+            else v = make_float2(__fadd_rn(a[j].x, r), __fadd_rn(a[j].y, r));
+            v.x = __fmul_rn(v.x, m);
+            v.y = __fmul_rn(v.y, m);
+            a[j] = v;
+            if (PACKED) { if (j & 1) S1 = __fadd2_rn(S1, v); else S0 = __fadd2_rn(S0, v); }
+            else { if (j & 1) { S1.x = __fadd_rn(S1.x, v.x); S1.y = __fadd_rn(S1.y, v.y); } else { S0.x = __fadd_rn(S0.x, v.x); S0.y = __fadd_rn(S0.y, v.y); } }
+        }
+    }
+    float acc = S0.x + S0.y + S1.x + S1.y;
+#pragma unroll
+    for (int j = 0; j < 16; j++) acc += a[j].x + a[j].y;
+    if (acc == 123.456f) out[threadIdx.x] = acc; // keep the work alive
+}
+
 // ---------------------------------------------------------------------------------------
 // Bit packing.  hap: L*N chars; G: L rows of `wps` words, bit (n&31) of word n>>5 = hap[s][n]=='1'.
 // One thread per output word; a warp reads 1 KiB of consecutive chars.

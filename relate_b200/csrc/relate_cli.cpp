@@ -1,0 +1,325 @@
+// relate_cli.cpp — `relate`: drop-in for the reference's `Relate` binary on the Paint path.
+//
+// Mirrors the CLI surface of /root/reference/include/pipeline/Relate.cpp:15-328:
+//   * the same flag set (Relate.cpp:19-45) is accepted; unknown flags are an error, as with cxxopts;
+//   * `--mode Paint` (Relate.cpp:64-79 -> pipeline/Paint.cpp:17-108) runs natively on the GPUs through
+//     the C ABI in include/relate_paint.h;
+//   * `--mode All` (Relate.cpp:190-296) keeps the reference's stage order, with Paint native and every
+//     other stage delegated to the reference binary;
+//   * every other mode is handed to the reference binary unchanged (exec).
+// The reference binary is found via $RELATE_REFERENCE_BIN, else "<dir of this exe>/Relate.ref".
+// Extra flags of this build (stripped before delegating): --gpus a,b,c   --fp64
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <sys/resource.h>
+#include <sys/time.h>
+#include <sys/wait.h>
+#include <unistd.h>
+#include <vector>
+
+#include "../../include/relate_paint.h"
+
+namespace {
+
+struct Flag {
+    const char *name;
+    char shortname; // 0 if none
+    bool has_value;
+    const char *help;
+};
+
+// Relate.cpp:19-45, in the reference's order
+const Flag kFlags[] = {
+    {"help", 0, false, "Print help."},
+    {"mode", 0, true, "Choose which part of the algorithm to run."},
+    {"haps", 0, true, "Filename of haps file (Output file format of Shapeit)."},
+    {"sample", 0, true, "Filename of sample file (Output file format of Shapeit)."},
+    {"map", 0, true, "Genetic map."},
+    {"mutation_rate", 'm', true, "Mutation rate."},
+    {"effectiveN", 'N', true, "Effective population size."},
+    {"output", 'o', true, "Filename of output without file extension."},
+    {"dist", 0, true, "Optional but recommended. Distance in BP between SNPs."},
+    {"annot", 0, true, "Optional. Filename of file containing additional annotation of snps."},
+    {"memory", 0, true, "Optional. Approximate memory allowance in GB for storing distance matrices. Default is 5GB."},
+    {"sample_ages", 0, true, "Optional. Filename of file containing sample ages (one per line)."},
+    {"chunk_index", 0, true, "Optional. Index of chunk."},
+    {"first_section", 0, true, "Optional. Index of first section to infer."},
+    {"last_section", 0, true, "Optional. Index of last section to infer."},
+    {"coal", 0, true, "Optional. Filename of file containing coalescent rates."},
+    {"fb", 0, true, "Optional. Force build a new tree every x bases."},
+    {"no_consistency", 0, false, "Optional. Disable consistency option."},
+    {"transversion", 0, false, "Only use transversion for bl estimation."},
+    {"postprocess", 0, false, "(beta option) Postprocess topology."},
+    {"randomise", 0, false, "(beta option) Randomise topology in post processing step."},
+    {"input", 'i', true, "Filename of input."},
+    {"painting", 0, true, "Optional. Copying and transition parameters in chromosome painting algorithm. Format: theta,rho. Default: 0.001,1."},
+    {"seed", 0, true, "Optional. Seed for MCMC in branch lengths estimation."},
+    // this build only
+    {"gpus", 0, true, "(relate_b200) Comma-separated CUDA device indices for --mode Paint. Default: all visible."},
+    {"fp64", 0, false, "(relate_b200) fp64 state in the painting kernel (verification mode)."},
+};
+
+void print_help()
+{
+    std::cout << "Usage:\n  Relate [OPTION...]\n\n";
+    for (const Flag &f : kFlags) {
+        std::string lhs = "  ";
+        if (f.shortname) lhs += std::string("-") + f.shortname + ", ";
+        else lhs += "    ";
+        lhs += std::string("--") + f.name;
+        if (f.has_value) lhs += " arg";
+        std::cout << std::left << std::setw(30) << lhs << f.help << "\n";
+    }
+    std::cout << std::endl;
+}
+
+struct Args {
+    std::map<std::string, std::string> val;
+    std::set<std::string> present;
+    std::vector<std::string> passthrough; // argv for the reference binary (our own flags removed)
+    bool count(const char *k) const { return present.count(k) != 0; }
+    const std::string &get(const char *k) const { return val.at(k); }
+};
+
+const Flag *find_long(const std::string &n)
+{
+    for (const Flag &f : kFlags)
+        if (n == f.name) return &f;
+    return nullptr;
+}
+const Flag *find_short(char c)
+{
+    for (const Flag &f : kFlags)
+        if (f.shortname && f.shortname == c) return &f;
+    return nullptr;
+}
+
+bool parse(int argc, char **argv, Args &a, std::string &err)
+{
+    for (int i = 1; i < argc; i++) {
+        std::string tok = argv[i];
+        const Flag *f = nullptr;
+        std::string value;
+        bool inline_value = false;
+        if (tok.rfind("--", 0) == 0) {
+            std::string name = tok.substr(2);
+            size_t eq = name.find('=');
+            if (eq != std::string::npos) {
+                value = name.substr(eq + 1);
+                name = name.substr(0, eq);
+                inline_value = true;
+            }
+            f = find_long(name);
+            if (!f) { err = "Option '" + name + "' does not exist"; return false; }
+        } else if (tok.size() == 2 && tok[0] == '-') {
+            f = find_short(tok[1]);
+            if (!f) { err = std::string("Option '") + tok[1] + "' does not exist"; return false; }
+        } else {
+            err = "unexpected argument '" + tok + "'";
+            return false;
+        }
+        if (f->has_value && !inline_value) {
+            if (i + 1 >= argc) { err = std::string("Option '") + f->name + "' is missing an argument"; return false; }
+            value = argv[++i];
+        }
+        a.present.insert(f->name);
+        a.val[f->name] = value;
+        const bool ours = !strcmp(f->name, "gpus") || !strcmp(f->name, "fp64");
+        if (!ours) {
+            a.passthrough.push_back(std::string("--") + f->name);
+            if (f->has_value) a.passthrough.push_back(value);
+        }
+    }
+    return true;
+}
+
+std::string reference_binary(const char *argv0)
+{
+    if (const char *e = getenv("RELATE_REFERENCE_BIN")) return e;
+    char buf[4096];
+    ssize_t n = readlink("/proc/self/exe", buf, sizeof buf - 1);
+    std::string self = n > 0 ? std::string(buf, (size_t)n) : std::string(argv0);
+    size_t slash = self.rfind('/');
+    std::string dir = slash == std::string::npos ? "." : self.substr(0, slash);
+    return dir + "/Relate.ref";
+}
+
+// run the reference binary with `args`; returns its exit status (or 127)
+int run_reference(const std::string &bin, const std::vector<std::string> &args)
+{
+    if (access(bin.c_str(), X_OK) != 0) {
+        std::cerr << "relate: this build implements --mode Paint only; set RELATE_REFERENCE_BIN (or place the reference binary at "
+                  << bin << ") to run the other stages." << std::endl;
+        return 127;
+    }
+    std::vector<char *> av;
+    av.push_back(const_cast<char *>(bin.c_str()));
+    for (const std::string &s : args) av.push_back(const_cast<char *>(s.c_str()));
+    av.push_back(nullptr);
+    pid_t pid = fork();
+    if (pid == 0) {
+        execv(bin.c_str(), av.data());
+        _exit(127);
+    }
+    int status = 0;
+    waitpid(pid, &status, 0);
+    if (WIFEXITED(status)) return WEXITSTATUS(status);
+    return 128 + (WIFSIGNALED(status) ? WTERMSIG(status) : 0);
+}
+
+std::vector<std::string> with_mode(const Args &a, const std::string &mode, const std::vector<std::string> &extra = {})
+{
+    std::vector<std::string> out;
+    const std::set<std::string> replaced = {"--mode", "--chunk_index", "--first_section", "--last_section"};
+    for (size_t i = 0; i < a.passthrough.size(); i++) {
+        const std::string &t = a.passthrough[i];
+        if (replaced.count(t)) { i++; continue; }
+        out.push_back(t);
+    }
+    out.push_back("--mode");
+    out.push_back(mode);
+    for (const std::string &e : extra) out.push_back(e);
+    return out;
+}
+
+// pipeline/Paint.cpp:17-108 behind the C ABI
+int paint(const Args &a, int chunk_index)
+{
+    std::vector<int> devs;
+    if (a.count("gpus")) {
+        std::stringstream ss(a.get("gpus"));
+        std::string t;
+        while (std::getline(ss, t, ','))
+            if (!t.empty()) devs.push_back(atoi(t.c_str()));
+    } else {
+        int n = rp_device_count();
+        for (int i = 0; i < n; i++) devs.push_back(i);
+    }
+    if (devs.empty()) {
+        std::cerr << "relate: no CUDA device visible; --mode Paint has no CPU path in this build." << std::endl;
+        return 1;
+    }
+    std::cerr << "---------------------------------------------------------" << std::endl;
+    std::cerr << "Painting sequences..." << std::endl;
+    rp_stats st;
+    memset(&st, 0, sizeof st);
+    const char *painting = a.count("painting") ? a.get("painting").c_str() : nullptr;
+    int rc = rp_paint_chunk(a.get("output").c_str(), chunk_index, painting, devs.data(), (int)devs.size(),
+                            a.count("fp64") ? RP_FP64 : 0u, &st);
+    if (rc != RP_OK) {
+        std::cerr << "relate: Paint failed: " << rp_last_error() << std::endl;
+        return 1;
+    }
+    rusage usage;
+    getrusage(RUSAGE_SELF, &usage);
+    std::cerr << "GPU Paint: " << devs.size() << " device(s), " << st.n_targets << " targets, kernel " << std::fixed
+              << std::setprecision(3) << st.ms_paint << " ms, prep " << st.ms_prep << " ms, encode+write " << st.ms_encode
+              << " ms, total " << st.ms_total << " ms." << std::endl;
+    std::cerr << "CPU Time spent: " << usage.ru_utime.tv_sec << "." << std::setfill('0') << std::setw(6) << usage.ru_utime.tv_usec
+              << "s; Max Memory usage: " << std::setprecision(6) << usage.ru_maxrss / 1000.0 << "Mb." << std::endl;
+    std::cerr << "---------------------------------------------------------" << std::endl << std::endl;
+    return 0;
+}
+
+bool read_ints(const std::string &path, int *dst, int n)
+{
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    bool ok = fread(dst, 4, n, fp) == (size_t)n;
+    fclose(fp);
+    return ok;
+}
+
+} // namespace
+
+int main(int argc, char **argv)
+{
+    Args a;
+    std::string err;
+    if (!parse(argc, argv, a, err)) {
+        std::cerr << "relate: " << err << std::endl;
+        return 1;
+    }
+    const std::string mode = a.count("mode") ? a.get("mode") : "";
+    if (a.count("output")) { // Relate.cpp:50-58
+        if (a.get("output").find('/') != std::string::npos) {
+            std::cerr << "Output needs to be in working directory." << std::endl;
+            return 1;
+        }
+    }
+    const std::string ref = reference_binary(argv[0]);
+
+    if (mode == "Paint") {
+        bool help = false;
+        if (!a.count("chunk_index") || !a.count("output")) { // Relate.cpp:66-76
+            std::cout << "Not enough arguments supplied." << std::endl;
+            std::cout << "Needed: chunk_index, output." << std::endl;
+            help = true;
+        }
+        if (a.count("help") || help) {
+            print_help();
+            std::cout << "Use after MakeChunks to paint all haps against all." << std::endl;
+            return 0;
+        }
+        return paint(a, atoi(a.get("chunk_index").c_str()));
+    }
+
+    if (mode == "All") { // Relate.cpp:190-296 with Paint native
+        if (a.count("help") || !a.count("output") ||
+            (!a.count("chunk_index") && (!a.count("haps") || !a.count("sample") || !a.count("map"))))
+            return run_reference(ref, a.passthrough); // let the reference print its own usage text
+        const std::string out = a.get("output");
+        int start_chunk = 0, end_chunk = 0;
+        if (a.count("chunk_index")) {
+            start_chunk = end_chunk = atoi(a.get("chunk_index").c_str());
+        } else {
+            int rc = run_reference(ref, with_mode(a, "MakeChunks"));
+            if (rc != 0) return rc;
+            int hdr[3];
+            if (!read_ints(out + "/parameters.bin", hdr, 3)) {
+                std::cerr << "relate: cannot read " << out << "/parameters.bin" << std::endl;
+                return 1;
+            }
+            end_chunk = hdr[2] - 1;
+        }
+        for (int c = start_chunk; c <= end_chunk; c++) {
+            std::cerr << "---------------------------------------------------------" << std::endl;
+            std::cerr << "Starting chunk " << c << " of " << end_chunk << "." << std::endl;
+            std::cerr << "---------------------------------------------------------" << std::endl << std::endl;
+            int hdr[3];
+            if (!read_ints(out + "/parameters_c" + std::to_string(c) + ".bin", hdr, 3)) {
+                std::cerr << "relate: cannot read parameters_c" << c << ".bin" << std::endl;
+                return 1;
+            }
+            const int num_sections = hdr[2] - 1;
+            const std::string cs = std::to_string(c), ls = std::to_string(num_sections - 1);
+            int rc = paint(a, c);
+            if (rc) return rc;
+            if ((rc = run_reference(ref, with_mode(a, "BuildTopology", {"--chunk_index", cs, "--first_section", "0", "--last_section", ls})))) return rc;
+            if ((rc = run_reference(ref, with_mode(a, "FindEquivalentBranches", {"--chunk_index", cs})))) return rc;
+            if (a.count("postprocess")) {
+                if ((rc = run_reference(ref, with_mode(a, "PostProcess", {"--chunk_index", cs})))) return rc;
+            }
+            if ((rc = run_reference(ref, with_mode(a, "InferBranchLengths", {"--chunk_index", cs, "--first_section", "0", "--last_section", ls})))) return rc;
+            if ((rc = run_reference(ref, with_mode(a, "CombineSections", {"--chunk_index", cs})))) return rc;
+        }
+        if (!a.count("chunk_index")) {
+            int rc = run_reference(ref, with_mode(a, "Finalize"));
+            if (rc) return rc;
+        }
+        std::cerr << "---------------------------------------------------------" << std::endl;
+        std::cerr << "Done." << std::endl;
+        std::cerr << "---------------------------------------------------------" << std::endl;
+        return 0;
+    }
+
+    // everything else belongs to the reference binary
+    return run_reference(ref, a.passthrough);
+}

@@ -1,0 +1,357 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle, the golden fixtures and - where
+oracle/_ref travelled to the box - the unmodified reference binary.  Tolerances (BASELINE.json north_star):
+boundary SNPs exact; alpha/beta relative 1e-4 (fp32 state, observed ~1e-6); fp64 mode reproduces the oracle to
+<= 1 float ulp; d_ij through the reference's own GetMatrix within 1e-4*|log(theta/(1-theta))| absolute."""
+import filecmp
+import hashlib
+import json
+import os
+import shutil
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, make_case, rel_err, unpack_golden
+from oracle import oracle
+from relate_b200 import capi, chunkio, synth
+from test_oracle_cpu import kat_check, kat_inputs
+
+pytestmark = pytest.mark.gpu
+THETA = float(np.float32(0.001))  # what --painting 0.001,1 yields (Paint.cpp:47)
+RTOL = 1e-4
+EXE = os.path.join(ROOT, "relate_b200", "bin", "relate")
+
+
+def compare(g, o, rtol=RTOL, ls_atol=2e-3):
+    assert np.array_equal(g.site_begin, o["site_begin"])
+    assert np.array_equal(g.site_end, o["site_end"])
+    assert rel_err(g.alpha, o["alpha"]) <= rtol
+    assert rel_err(g.beta, o["beta"]) <= rtol
+    # log-scales are O(1e2..1e4) floats: one ulp at 4000 is 2.4e-4
+    assert np.abs(g.ls_alpha.astype(np.float64) - o["ls_alpha"]).max() <= ls_atol
+    assert np.abs(g.ls_beta.astype(np.float64) - o["ls_beta"]).max() <= ls_atol
+
+
+def ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    return np.abs(ai - bi)
+
+
+# (N, L, W, seed, words_per_thread, n_targets): single-warp teams, tails (N%32!=0), multi-warp teams, both WPT
+CASES = [
+    (8, 2500, 4, 1, 0, None),
+    (32, 800, 3, 2, 0, None),
+    (64, 600, 3, 3, 0, None),
+    (100, 1500, 6, 4, 0, None),
+    (1000, 1500, 4, 5, 0, 96),
+    (1024, 800, 2, 6, 0, 64),
+    (1500, 1200, 3, 7, 0, 48),
+    (1500, 1200, 3, 7, 1, 48),
+    (2100, 900, 3, 8, 0, 40),
+    (2100, 900, 3, 8, 1, 40),
+    (5000, 500, 2, 9, 0, 24),
+    (5000, 500, 2, 9, 1, 24),
+    (10000, 300, 2, 10, 0, 12),
+]
+
+
+@pytest.mark.parametrize("N,L,W,seed,wpt,nk", CASES)
+def test_fp32_matches_oracle(N, L, W, seed, wpt, nk):
+    hap, r, wb = make_case(N, L, W, seed)
+    nk = N if nk is None else nk
+    k0 = max(0, N - nk - 3)  # not always starting at 0: exercise k_begin
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        c.set_tune(words_per_thread=wpt)
+        g = c.paint_targets(k0, k0 + nk)
+    o = oracle.paint_targets(hap, r, wb, THETA, k0, k0 + nk)
+    compare(g, o)
+    assert g.stats["launches"] == 6 and g.stats["ms_paint"] > 0
+
+
+@pytest.mark.parametrize("N,L,W,seed,nk", [(8, 2500, 4, 1, None), (100, 1500, 6, 4, None), (1000, 1500, 4, 5, 64),
+                                           (2100, 900, 3, 8, 32), (5000, 500, 2, 9, 16)])
+def test_fp64_mode_reproduces_oracle_to_one_ulp(N, L, W, seed, nk):
+    hap, r, wb = make_case(N, L, W, seed)
+    nk = N if nk is None else nk
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA, fp64=True) as c:
+        g = c.paint_targets(0, nk)
+    o = oracle.paint_targets(hap, r, wb, THETA, 0, nk)
+    assert np.array_equal(g.site_begin, o["site_begin"]) and np.array_equal(g.site_end, o["site_end"])
+    for name in ("alpha", "beta", "ls_alpha", "ls_beta"):
+        d = ulp_diff(getattr(g, name), o[name])
+        assert d.max() <= 1, name
+        assert (d > 0).mean() < 1e-4, name  # the double->float store hides the summation-order differences
+
+
+def test_known_answer_5x5_on_gpu():
+    hap, r, wb, theta = kat_inputs()
+    with capi.DeviceChunk.from_arrays(hap, r, wb, theta) as c:
+        g = c.paint_targets(0, 5)
+    kat_check(dict(alpha=g.alpha, beta=g.beta, site_begin=g.site_begin, site_end=g.site_end), hap, theta)
+    o = oracle.paint_targets(hap, r, wb, theta, 0, 5)
+    compare(g, o)
+
+
+def test_device_fast_log_is_bit_exact():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([np.float32(10.0) ** np.arange(-37, 38, dtype=np.float32),
+                        rng.random(5000, dtype=np.float32) * np.float32(1e-10),
+                        rng.random(5000, dtype=np.float32) * np.float32(1e10)])
+    x = x[np.isfinite(x) & (x > 0)]
+    assert np.array_equal(capi.fast_log_device(x), oracle.fast_log(x))
+
+
+@pytest.mark.parametrize("N,L", [(8, 70), (100, 1000), (1056, 300), (37, 4097)])
+def test_bit_packing(N, L):
+    hap, _ = synth.block_kingman(N, L, 12)
+    G = np.zeros((L, (((N + 31) // 32 + 3) // 4) * 4), np.uint32)
+    GT = np.zeros((N, (L + 31) // 32), np.uint32)
+    wps, lw = ctypes_int(), ctypes_int()
+    capi.check(capi.lib().rp_debug_pack(0, N, L, hap.ctypes.data, G.ctypes.data, wps, GT.ctypes.data, lw))
+    bits = (hap == ord("1"))
+    exp = np.zeros((L, G.shape[1] * 32), bool)
+    exp[:, :N] = bits
+    expG = np.packbits(exp.reshape(L, -1, 32), axis=-1, bitorder="little").view(np.uint32).reshape(L, -1)
+    assert np.array_equal(G, expG)
+    expT = np.zeros((N, GT.shape[1] * 32), bool)
+    expT[:, :L] = bits.T
+    expGT = np.packbits(expT.reshape(N, -1, 32), axis=-1, bitorder="little").view(np.uint32).reshape(N, -1)
+    assert np.array_equal(GT, expGT)
+
+
+def ctypes_int():
+    import ctypes
+    return ctypes.byref(ctypes.c_int())
+
+
+# ---- edge cases ------------------------------------------------------------------------------
+def test_single_window_is_prior_and_ones():
+    hap, r, wb = make_case(40, 300, 1, 13)
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        g = c.paint_targets()
+    compare(g, oracle.paint_targets(hap, r, wb, THETA, 0, 40))
+    assert np.all(g.beta == 1.0) and np.all(g.site_begin == 0) and np.all(g.site_end == 299)
+
+
+def test_windows_without_derived_sites_share_boundaries():
+    # many tiny windows: most targets have no derived site in most windows, so several windows
+    # store the same vector (fast_painting.cpp:234-252,354-374,433-448,559-578)
+    hap, r, _ = make_case(24, 400, 1, 14)
+    wb = np.arange(0, 401, 8, dtype=np.int32)
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        g = c.paint_targets()
+    o = oracle.paint_targets(hap, r, wb, THETA, 0, 24)
+    compare(g, o)
+    assert (np.diff(g.site_begin, axis=1) == 0).any()
+
+
+def test_all_ancestral_and_all_derived_haplotypes():
+    hap, r, wb = make_case(70, 500, 4, 15)
+    hap[:, 3] = ord("0")   # visits SNP 0 and SNP L-1 only
+    hap[:, 69] = ord("1")  # visits every SNP (tail word, N % 32 = 6)
+    hap[:, 32] = ord("1")
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        g = c.paint_targets()
+    o = oracle.paint_targets(hap, r, wb, THETA, 0, 70)
+    compare(g, o)
+    assert g.stats["sites"] == sum(oracle.count_sites(hap, k) for k in range(70))
+
+
+def test_recombination_cap_and_rescaling_paths():
+    # huge gaps hit the rho>0.99 cap (fast_painting.cpp:78-81); theta tiny + many mismatches forces rescaling
+    hap, r, wb = make_case(50, 3000, 5, 16)
+    r = r.copy()
+    r[::97] = 30.0
+    r[5:9] = 1e-10 * 2500
+    theta = 1e-6
+    with capi.DeviceChunk.from_arrays(hap, r, wb, theta) as c:
+        g = c.paint_targets()
+    o = oracle.paint_targets(hap, r, wb, theta, 0, 50)
+    compare(g, o, ls_atol=2e-2)
+    # rescaling happened: forward log-scales are not just sums of nor terms
+    assert np.abs(o["ls_alpha"]).max() > 50
+
+
+def test_painting_rho_and_default_theta(tmp_path):
+    d = unpack_golden("synth_n96", str(tmp_path))
+    for painting in (None, "0.001,1", "0.0025,2.5"):
+        with capi.DeviceChunk.load(d, 0, painting) as c:
+            g = c.paint_targets(0, 16)
+        ch = chunkio.read_chunk(d, 0)
+        theta, rho = 0.001, 1.0
+        if painting:
+            a, b = painting.split(",")
+            theta, rho = float(np.float32(a)), float(np.float32(b))
+        compare(g, oracle.paint_targets(ch.hap, ch.r * rho, ch.wb, theta, 0, 16))
+
+
+def test_target_range_invariance_and_determinism():
+    hap, r, wb = make_case(300, 1200, 5, 17)
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        full = c.paint_targets(0, 300)
+        again = c.paint_targets(0, 300)
+        a = c.paint_targets(0, 117)
+        b = c.paint_targets(117, 300)
+    for name in ("alpha", "beta", "ls_alpha", "ls_beta", "site_begin", "site_end"):
+        assert np.array_equal(getattr(full, name), getattr(again, name)), name
+        assert np.array_equal(getattr(full, name), np.concatenate([getattr(a, name), getattr(b, name)])), name
+
+
+def test_unsupported_sizes_fail_loudly():
+    hap = np.full((40, 33000), ord("0"), np.uint8)
+    with pytest.raises(capi.PaintError) as e:
+        capi.DeviceChunk.from_arrays(hap, np.full(40, 1e-3), np.array([0, 40], np.int32))
+    assert e.value.code == -6
+
+
+# ---- golden fixtures and the reference binary ---------------------------------------------------
+def decoded_close(path_a, path_b, N, tol):
+    A, B = chunkio.read_paint_file(path_a, N), chunkio.read_paint_file(path_b, N)
+    assert len(A) == len(B) == N
+    flips = 0
+    for (a0, a1, aa, ab), (b0, b1, ba, bb) in zip(A, B):
+        assert (a0, a1) == (b0, b1)
+        for x, y in ((aa, ba), (ab, bb)):
+            assert x.site == y.site
+            assert abs(float(x.logscale) - float(y.logscale)) <= 2e-3
+            assert rel_err(x.expand(), y.expand()) <= tol
+            flips += int(len(x.lens) != len(y.lens) or not np.array_equal(x.lens, y.lens))
+    return flips
+
+
+@pytest.mark.parametrize("name,painting,ref_dir", [("example_c1", "0.001,1", "paint_ref"), ("synth_n96", "0.001,1", "paint_ref"),
+                                                   ("synth_n96", None, "paint_ref_noflag")])
+def test_paint_chunk_files_vs_reference_golden(tmp_path, name, painting, ref_dir):
+    d = unpack_golden(name, str(tmp_path))
+    ch = chunkio.read_chunk(d, 0)
+    st = capi.paint_chunk(d, 0, painting)
+    assert st["n_targets"] == ch.N
+    flips = 0
+    for w in range(ch.W):
+        mine = os.path.join(d, "chunk_0", "paint", f"relate_{w}.bin")
+        ref = os.path.join(GOLDEN, name, ref_dir, f"relate_{w}.bin")
+        # decoded values: the codec merges within 1e-3 of the run head, so allow 1e-3 + 1e-4
+        flips += decoded_close(mine, ref, ch.N, 1.1e-3)
+    assert flips <= max(2, ch.N * ch.W // 50)
+    # fp64 verification mode: the reference's bytes
+    shutil.rmtree(os.path.join(d, "chunk_0"))
+    capi.paint_chunk(d, 0, painting, fp64=True)
+    same = [filecmp.cmp(os.path.join(d, "chunk_0", "paint", f"relate_{w}.bin"), os.path.join(GOLDEN, name, ref_dir, f"relate_{w}.bin"),
+                        shallow=False) for w in range(ch.W)]
+    if not all(same):  # at most isolated last-bit differences
+        for w in range(ch.W):
+            decoded_close(os.path.join(d, "chunk_0", "paint", f"relate_{w}.bin"), os.path.join(GOLDEN, name, ref_dir, f"relate_{w}.bin"),
+                          ch.N, 1.001e-3)
+    assert sum(same) >= ch.W - 1
+
+
+def test_cli_paint_then_reference_buildtopology_gives_identical_trees(tmp_path, have_ref):
+    """`relate --mode Paint` output consumed unchanged by the reference's BuildTopology: .anc/.mut md5 equal to what
+    the reference derives from its own paint files (bundled example, chunk 1, --seed 1)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref/Relate did not travel to this box")
+    unpack_golden("example_c1", str(tmp_path), out="ex")
+    meta = json.load(open(os.path.join(GOLDEN, "example_c1", "topology_md5.json")))
+    p = subprocess.run([EXE, "--mode", "Paint", "--chunk_index", "0", "-o", "ex", "--painting", meta["painting"]],
+                       cwd=str(tmp_path), capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "Painting sequences..." in p.stderr and "CPU Time spent:" in p.stderr
+    oracle.run_reference(["--mode", "BuildTopology", "--chunk_index", "0", "--first_section", "0", "--last_section",
+                          str(meta["W"] - 1), "-o", "ex", "--painting", meta["painting"], "--seed", str(meta["seed"])], cwd=str(tmp_path))
+    for fn, want in meta["md5"].items():
+        got = hashlib.md5(open(os.path.join(str(tmp_path), "ex", "chunk_0", fn), "rb").read()).hexdigest()
+        assert got == want, fn
+
+
+def read_dlens(path):
+    buf = open(path, "rb").read()
+    N, cnt = struct.unpack_from("<ii", buf, 0)
+    off, out = 8, {}
+    for _ in range(cnt):
+        (snp,) = struct.unpack_from("<i", buf, off)
+        out[snp] = np.frombuffer(buf, "<f4", N * N, off + 4).reshape(N, N)
+        off += 4 + 4 * N * N
+    return out
+
+
+def test_dij_through_reference_getmatrix(tmp_path, have_ref):
+    """d_ij lens: the reference's DistanceMeasure::GetMatrix on reference-painted vs GPU-painted stepping stones."""
+    if not have_ref or not os.access(oracle.REF_DLENS, os.X_OK):
+        pytest.skip("oracle/_ref did not travel to this box")
+    N, L, W = 200, 3000, 3
+    for tag in ("ref", "gpu"):
+        synth.make_chunk_dir(str(tmp_path / tag / "o"), N, L, seed=31, n_windows=W)
+    oracle.run_reference(["--mode", "Paint", "--chunk_index", "0", "-o", "o", "--painting", "0.001,1"], cwd=str(tmp_path / "ref"))
+    capi.paint_chunk(str(tmp_path / "gpu" / "o"), 0, "0.001,1")
+    worst = 0.0
+    for sec in range(W):
+        outs = {}
+        for tag in ("ref", "gpu"):
+            out = str(tmp_path / f"d_{tag}_{sec}.bin")
+            subprocess.run([oracle.REF_DLENS, "o", "0", str(sec), "97", "0.001,1", out], cwd=str(tmp_path / tag), check=True)
+            outs[tag] = read_dlens(out)
+        assert outs["ref"].keys() == outs["gpu"].keys() and len(outs["ref"]) >= 3
+        for snp in outs["ref"]:
+            worst = max(worst, float(np.abs(outs["ref"][snp] - outs["gpu"][snp]).max()))
+    assert worst <= 1e-4 * abs(np.log(THETA / (1 - THETA))) + 1e-3 * 0  # 6.9e-4 absolute
+
+
+# ---- full-size properties (BASELINE.json configs[1]: N=1000 x L=50k, one chunk) ------------------
+@pytest.fixture(scope="module")
+def config2():
+    N, L = 1000, 50000
+    hap, bp = synth.block_kingman(N, L, 1)
+    r = chunkio.r_from_rpos(chunkio.uniform_map_rpos(bp))
+    wb = chunkio.window_boundaries(hap, 5.0)
+    return hap, r, wb
+
+
+def test_config2_full_size_properties(config2):
+    hap, r, wb = config2
+    N = hap.shape[1]
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        g = c.paint_targets(0, N)
+        h = c.paint_targets(0, N)
+        g64 = None
+    assert len(wb) - 1 >= 5
+    for name in ("alpha", "beta", "ls_alpha", "ls_beta"):
+        assert np.array_equal(getattr(g, name), getattr(h, name))        # deterministic
+        assert np.isfinite(getattr(g, name)).all()
+    # every stored vector is a stepping stone of target k: alpha[k]=0 always, beta[k]=0 except at the last SNP
+    L = hap.shape[0]
+    for k in range(0, N, 37):
+        assert np.all(g.alpha[k, :, k] == 0)
+        assert np.all((g.beta[k, :, k] == 0) | (g.site_end[k] == L - 1))
+    assert np.all(g.site_begin <= wb[:-1][None, :]) and np.all(g.site_end >= (wb[1:] - 1)[None, :])  # reader contract
+    assert g.stats["sites"] == int((hap[1:-1] == ord("1")).sum()) + 2 * N
+    # spot-check against the oracle on a handful of targets (65 ms of CPU each)
+    ks = [0, 1, 499, 998, 999]
+    for k in ks:
+        o = oracle.paint_targets(hap, r, wb, THETA, k, k + 1)
+        sub = capi.SteppingStones(k, g.alpha[k:k + 1], g.beta[k:k + 1], g.ls_alpha[k:k + 1], g.ls_beta[k:k + 1],
+                                  g.site_begin[k:k + 1], g.site_end[k:k + 1], {})
+        compare(sub, o)
+
+
+def test_config2_fp32_vs_fp64_state(config2):
+    hap, r, wb = config2
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c32, capi.DeviceChunk.from_arrays(hap, r, wb, THETA, fp64=True) as c64:
+        a = c32.paint_targets(400, 464)
+        b = c64.paint_targets(400, 464)
+    assert rel_err(a.alpha, b.alpha) <= RTOL and rel_err(a.beta, b.beta) <= RTOL
+    assert np.array_equal(a.site_begin, b.site_begin) and np.array_equal(a.site_end, b.site_end)
+
+
+def test_multi_gpu_paint_chunk_matches_single(tmp_path):
+    if capi.lib().rp_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    for tag in ("one", "two"):
+        synth.make_chunk_dir(str(tmp_path / tag), 600, 2000, seed=41, n_windows=4)
+    capi.paint_chunk(str(tmp_path / "one"), 0, "0.001,1", devices=[0])
+    capi.paint_chunk(str(tmp_path / "two"), 0, "0.001,1", devices=[0, 1])
+    for w in range(4):
+        assert filecmp.cmp(str(tmp_path / "one" / "chunk_0" / "paint" / f"relate_{w}.bin"),
+                           str(tmp_path / "two" / "chunk_0" / "paint" / f"relate_{w}.bin"), shallow=False)
