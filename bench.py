@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — painted cells/s of the B200-native `relate --mode Paint` hot path.
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU Paint (oracle/_ref/Relate)
+
+Workload (BASELINE.json configs[1]): synthetic block-Kingman haplotypes N=1000 x L=50000, one chunk, window
+plan of `--memory 5`, `--painting 0.001,1`.  A step = one pass of the hot path over one chunk: per-target site
+tables + the forward/backward kernel for all N targets.  With N GPUs every rank paints its own chunk of that
+shape (independent chunks, no data-path collective): weak scaling, value = total painted cells / max-over-ranks time.
+
+Keys beyond the base contract:
+  roofline     dominant kernel (paint_kernel): algorithmic FP32 lane-ops 7*N*U per launch (SURVEY.md 8d;
+               U = visited sites, counted exactly) / mean launch time (CUDA events on the launching stream),
+               against the measured FP32 lane-op rate of this box (rp_peak_fp32: same instruction mix, no memory).
+  e2e          the same metric through the whole reference-facing stage rp_paint_chunk (== `relate --mode Paint`):
+               chunk files in, chunk_0/paint/relate_<w>.bin out; host->device and device->host copies, RLE encoding
+               and file writes inside the timed region.
+  cpu_baseline the unmodified reference binary on a bounded sample of the same workload, on this box's host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_HAP, N_SNP, MEMORY_GB, PAINTING = 1000, 50000, 5.0, "0.001,1"
+WORKLOAD = f"synthetic block-Kingman N={N_HAP} x L={N_SNP}, single chunk, --memory {MEMORY_GB:g}, --painting {PAINTING}"
+METRIC, UNIT = "painted cells/s (N^2*L/s), relate --mode Paint", "cells/s"
+
+
+def make_chunk(out_dir, seed, L=N_SNP):
+    from relate_b200 import synth
+    return synth.make_chunk_dir(out_dir, N_HAP, L, seed, memory_gb=MEMORY_GB)
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    except (OSError, ValueError):
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    """The reference's own CPU Paint (oracle/_ref/Relate, built from /root/reference by oracle/Makefile) on this box's
+    host cores: P concurrent single-threaded `Relate --mode Paint` processes (Paint has no threads, Paint.cpp:81-87;
+    this is what RelateParallel.sh's disabled `parallelize $chunks` would do), each on its own bounded sample chunk
+    of the workload's shape (N=1000, L_s SNPs).  Falls back to the oracle port if the binary did not travel."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    L_s = int(os.environ.get("RELATE_BENCH_REF_SNPS", "1500"))
+    use_ref = oracle.have_reference()
+    tmp = tempfile.mkdtemp(prefix="relate_ref_")
+    try:
+        base = os.path.join(tmp, "base")
+        make_chunk(base, seed=1, L=L_s)
+        dirs = []
+        for i in range(procs):
+            d = os.path.join(tmp, f"p{i}", "o")
+            shutil.copytree(base, d)
+            dirs.append(d)
+
+        def one_step():
+            t0 = time.perf_counter()
+            if use_ref:
+                ps = [subprocess.Popen([oracle.REF_RELATE, "--mode", "Paint", "--chunk_index", "0", "-o", "o", "--painting", PAINTING],
+                                       cwd=os.path.dirname(d), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for d in dirs]
+                rcs = [p.wait() for p in ps]
+                assert all(rc == 0 for rc in rcs), rcs
+            else:
+                ts = [threading.Thread(target=oracle.paint_chunk, args=(d, 0, PAINTING)) for d in dirs]
+                [t.start() for t in ts]
+                [t.join() for t in ts]
+            dt = time.perf_counter() - t0
+            for d in dirs:
+                shutil.rmtree(os.path.join(d, "chunk_0"), ignore_errors=True)
+            return dt
+
+        for _ in range(args.warmup):
+            one_step()
+        times = [one_step() for _ in range(args.steps)]
+        ms = 1e3 * sum(times) / len(times)
+        value = procs * N_HAP * N_HAP * L_s / (ms * 1e-3)
+        kind = "reference" if use_ref else "port"
+        sample = (f"{procs} concurrent single-threaded Paint processes, each N={N_HAP} x L={L_s} SNPs of the workload's "
+                  f"generator (same --painting); {'oracle/_ref/Relate' if use_ref else 'oracle port'}")
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample,
+                                 "host_cores": cores},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def cpu_baseline_sample():
+    """Rank 0, N=1: the reference binary (1 core: Paint is single-threaded) on a bounded sample, ~10-20 s."""
+    from oracle import oracle
+    L_s = int(os.environ.get("RELATE_BENCH_CPU_SNPS", "10000"))
+    tmp = tempfile.mkdtemp(prefix="relate_cpu_")
+    try:
+        d = os.path.join(tmp, "o")
+        make_chunk(d, seed=1, L=L_s)
+        t0 = time.perf_counter()
+        if oracle.have_reference():
+            subprocess.run([oracle.REF_RELATE, "--mode", "Paint", "--chunk_index", "0", "-o", "o", "--painting", PAINTING],
+                           cwd=tmp, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            kind = "reference"
+        else:
+            oracle.paint_chunk(d, 0, PAINTING)
+            kind = "port"
+        dt = time.perf_counter() - t0
+        return {"value": N_HAP * N_HAP * L_s / dt, "unit": UNIT, "cores": 1, "kind": kind, "seconds": dt,
+                "sample": f"one Paint of N={N_HAP} x L={L_s} SNPs (first {L_s} SNPs' worth of the workload's generator), "
+                          f"1 core because the reference's Paint is single-threaded per chunk; host has {os.cpu_count()} cores"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--words-per-thread", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from relate_b200 import capi, chunkio, sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the painting path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    tmp = tempfile.mkdtemp(prefix=f"relate_bench_r{rank}_")
+    try:
+        out_dir = os.path.join(tmp, "o")
+        hap, bp, rpos, wb = make_chunk(out_dir, seed=1 + rank)
+        r = chunkio.r_from_rpos(rpos)
+        theta = float(np.float32(PAINTING.split(",")[0]))
+        W = len(wb) - 1
+        cells_per_step = N_HAP * N_HAP * N_SNP
+
+        stream = torch.cuda.Stream(device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+        chunk = capi.DeviceChunk.from_arrays(hap, r, wb, theta, device=local_rank)
+        chunk.set_tune(words_per_thread=args.words_per_thread, ctas_per_sm=args.ctas_per_sm)
+        chunk.set_stream(stream.cuda_stream)
+
+        def step():
+            return chunk.paint_targets_device(0, N_HAP)
+
+        with torch.cuda.stream(stream):
+            for _ in range(args.warmup):
+                flush.fill_(1)
+                st = step()
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            t_wall0 = time.perf_counter()
+            paint_ms, prep_ms, launches = [], [], 0
+            for i in range(args.steps):
+                flush.fill_(i & 0xFF)          # L2 flush between timed iterations (outside the event pair)
+                ev[i][0].record(stream)
+                st = step()                   # prep kernels + paint kernel on `stream`
+                ev[i][1].record(stream)
+                paint_ms.append(st["ms_paint"]); prep_ms.append(st["ms_prep"]); launches += st["launches"]
+            torch.cuda.synchronize(dev)
+            t_wall = time.perf_counter() - t_wall0
+            if world > 1:
+                dist.barrier()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        my_ms = sum(step_ms) / len(step_ms)
+        U = st["sites"]
+        kernel_ms = sum(paint_ms) / len(paint_ms)
+
+        # ---- end to end through the reference-facing stage (files in -> files out) ------------------------
+        def e2e_step():
+            shutil.rmtree(os.path.join(out_dir, "chunk_0"), ignore_errors=True)
+            t0 = time.perf_counter()
+            s = capi.paint_chunk(out_dir, 0, PAINTING, devices=[local_rank])
+            return time.perf_counter() - t0, s
+
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        e2e_runs = [e2e_step() for _ in range(max(3, min(args.steps, 5)))]
+        clocks = sampler.stop()
+        my_e2e = sum(t for t, _ in e2e_runs) / len(e2e_runs)
+        es = e2e_runs[-1][1]
+
+        (t_max, e2e_max, kern_max) = sharding.allreduce_scalars([my_ms, my_e2e, kernel_ms], "max", device=dev)
+        (u_sum,) = sharding.allreduce_scalars([float(U)], "sum", device=dev)
+
+        if rank == 0:
+            peaks, peak_src = measured_peaks()
+            mix, scalar = capi.peak_fp32(local_rank)
+            nominal = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6
+            alg_ops = 7.0 * N_HAP * U                      # 7 FP32 ops per (target, site, reference) pair
+            achieved = alg_ops / (kernel_ms * 1e-3)
+            hbm_alg = (N_SNP * chunk.words_per_snp * 4) + 8.0 * U + 2.0 * W * N_HAP * N_HAP * 4   # bit matrix + tables + stones
+            line = {
+                "metric": METRIC, "value": world * cells_per_step / (t_max * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD + f" (W={W} windows, U={U} visited sites); one such chunk per GPU",
+                           "l2": "flushed between timed iterations (256 MiB device write outside the event pair)",
+                           "timing": "torch.cuda.Event pairs on the stream the library launches on; max over ranks",
+                           "team_threads": st["team_threads"], "words_per_thread": st["words_per_thread"], "ctas": st["ctas"]},
+                "roofline": {"bound": "fp32", "achieved": achieved / 1e12, "peak": mix / 1e12, "unit": "TFLOP/s",
+                             "frac": achieved / mix, "traffic": None,
+                             "kernel": "paint_kernel", "kernel_ms": kernel_ms, "prep_ms": sum(prep_ms) / len(prep_ms),
+                             "algorithmic_ops": alg_ops, "executed_fp32_lane_ops": 6.0 * N_HAP * U,
+                             "peak_source": "measured on this box: rp_peak_fp32 (packed add + predicated-mul mix, no memory)",
+                             "peak_scalar_mix": scalar / 1e12, "peak_nominal_issue": nominal / 1e12,
+                             "frac_of_nominal_issue": achieved / nominal,
+                             "hbm": {"algorithmic_bytes": hbm_alg, "achieved_gbs": hbm_alg / (kernel_ms * 1e-3) / 1e9,
+                                     "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src}},
+                "e2e": {"value": world * cells_per_step / e2e_max, "unit": UNIT,
+                        "h2d_bytes_per_step": es["h2d_bytes"], "d2h_bytes_per_step": es["d2h_bytes"],
+                        "seconds_per_step": e2e_max, "call": "rp_paint_chunk (== relate --mode Paint): chunk files -> paint files",
+                        "breakdown_ms": {k: es[k] for k in ("ms_h2d", "ms_prep", "ms_paint", "ms_d2h", "ms_encode", "ms_total")}},
+                "gpu_launches": launches,
+                "clocks": clocks,
+                "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            }
+            if world == 1 and not args.no_cpu_baseline:
+                cb = cpu_baseline_sample()
+                line["cpu_baseline"] = cb
+            print(json.dumps(line), flush=True)
+        chunk.close()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
