@@ -119,11 +119,12 @@ int plan_launch(const rp_chunk *c, LaunchPlan &lp)
     if (wpt != 0 && wpt != 1 && wpt != 2) return fail(RP_EINVAL, "words_per_thread must be 0, 1 or 2");
     if (fp64) wpt = 1;
     if (wpt == 0) wpt = (nfw <= 32) ? 1 : 2;
+    if (!fp64 && wpt == 1 && nfw > 384) wpt = 2; // one word per thread: teams of at most 384 threads
     const int need = std::max(1, (nfw + wpt - 1) / wpt);
     lp.wpt = wpt;
     lp.multi = need > 32;
     lp.threads = ((need + 31) / 32) * 32;
-    const int maxt = (fp64 || wpt == 2) ? 512 : 1024;
+    const int maxt = (fp64 || wpt == 1) ? 384 : 512; // PaintCfg::kMaxThreads
     if (lp.threads > maxt)
         return fail(RP_EUNSUPPORTED, "N=" + std::to_string(c->N) + " needs " + std::to_string(lp.threads) +
                                          " threads per team; one CTA owns at most " + std::to_string(maxt * wpt * 32) +
@@ -139,21 +140,21 @@ int launch_paint_t(const rp_chunk *c, const rp::PaintParams &P, int threads, int
     RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
     if (occ < 1) return fail(RP_ECUDA, "paint kernel does not fit on an SM");
     if (c->tune.ctas_per_sm > 0) occ = std::min(occ, c->tune.ctas_per_sm);
-    ctas = std::min(P.njobs, occ * c->sm_count);
+    ctas = 2 * std::min(P.nt, std::max(1, occ * c->sm_count / 2)); // even CTAs paint forwards, odd ones backwards
     kern<<<ctas, threads, 0, c->stream>>>(P);
     RP_CUDA(cudaGetLastError());
     return RP_OK;
 }
 
 // grid size is needed before the launch to size the fp64 scratch; compute it the same way
-template <typename T, int WPT, bool MULTI> int grid_for(const rp_chunk *c, int njobs, int threads, int &ctas)
+template <typename T, int WPT, bool MULTI> int grid_for(const rp_chunk *c, int nt, int threads, int &ctas)
 {
     auto kern = rp::paint_kernel<T, WPT, MULTI>;
     int occ = 0;
     RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
     if (occ < 1) return fail(RP_ECUDA, "paint kernel does not fit on an SM");
     if (c->tune.ctas_per_sm > 0) occ = std::min(occ, c->tune.ctas_per_sm);
-    ctas = std::min(njobs, occ * c->sm_count);
+    ctas = 2 * std::min(nt, std::max(1, occ * c->sm_count / 2));
     return RP_OK;
 }
 
@@ -161,8 +162,8 @@ int launch_paint(const rp_chunk *c, rp::PaintParams &P, const LaunchPlan &lp, De
 {
     const bool fp64 = (c->flags & RP_FP64) != 0;
     if (fp64) {
-        if (lp.multi) RP_TRY((grid_for<double, 1, true>(c, P.njobs, lp.threads, ctas)));
-        else RP_TRY((grid_for<double, 1, false>(c, P.njobs, lp.threads, ctas)));
+        if (lp.multi) RP_TRY((grid_for<double, 1, true>(c, P.nt, lp.threads, ctas)));
+        else RP_TRY((grid_for<double, 1, false>(c, P.nt, lp.threads, ctas)));
         RP_TRY(scratch.ensure((size_t)ctas * c->N * sizeof(double)));
         P.scratch = scratch.as<double>();
         return lp.multi ? launch_paint_t<double, 1, true>(c, P, lp.threads, ctas)
@@ -323,7 +324,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
     RP_TRY(c->lsb.ensure(nw * 4));
     RP_TRY(c->alpha.ensure(nw * N * 4));
     RP_TRY(c->beta.ensure(nw * N * 4));
-    RP_TRY(c->queue.ensure(4));
+    RP_TRY(c->queue.ensure(8));
 
     cudaStream_t s = c->stream;
     int launches = 0;
@@ -338,8 +339,12 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
     RP_CUDA(cudaMemcpyAsync(c->h_total, c->off.as<long long>() + nt, 8, cudaMemcpyDeviceToHost, s));
     RP_CUDA(cudaStreamSynchronize(s));
     const long long U = *c->h_total;
+    // the paint kernel's prefetch reads up to 3 entries past either end of a target's list: pad both ends
     const size_t entsz = fp64 ? sizeof(rp::EntD) : sizeof(rp::EntF);
-    RP_TRY(c->ent.ensure((size_t)U * entsz));
+    const size_t pad = 4;
+    RP_TRY(c->ent.ensure(((size_t)U + 2 * pad) * entsz));
+    RP_CUDA(cudaMemsetAsync(c->ent.p, 0, pad * entsz, s));
+    RP_CUDA(cudaMemsetAsync(c->ent.as<char>() + (pad + (size_t)U) * entsz, 0, pad * entsz, s));
 
     rp::TableConsts tc;
     const double ntheta = 1.0 - c->theta;
@@ -348,7 +353,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
     tc.Nm1 = N - 1.0;
     const unsigned gb = (unsigned)((nw + th - 1) / th);
     if (fp64) {
-        auto *e = c->ent.as<rp::EntD>();
+        auto *e = c->ent.as<rp::EntD>() + pad;
         rp::fill_sites_kernel<<<gw, th, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->off.as<long long>(), e);
         rp::boundaries_kernel<<<gb, th, 0, s>>>(e, c->off.as<long long>(), nt, W, c->wbdev.as<int>(), c->ia.as<int>(),
                                                 c->ib.as<int>(), c->sb.as<int>(), c->se.as<int>());
@@ -356,7 +361,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
                                             c->Phi.as<double>(), c->Plo.as<double>(), tc, c->ia.as<int>(),
                                             c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>());
     } else {
-        auto *e = c->ent.as<rp::EntF>();
+        auto *e = c->ent.as<rp::EntF>() + pad;
         rp::fill_sites_kernel<<<gw, th, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->off.as<long long>(), e);
         rp::boundaries_kernel<<<gb, th, 0, s>>>(e, c->off.as<long long>(), nt, W, c->wbdev.as<int>(), c->ia.as<int>(),
                                                 c->ib.as<int>(), c->sb.as<int>(), c->se.as<int>());
@@ -366,7 +371,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
     }
     RP_CUDA(cudaGetLastError());
     launches += 3;
-    RP_CUDA(cudaMemsetAsync(c->queue.p, 0, 4, s));
+    RP_CUDA(cudaMemsetAsync(c->queue.p, 0, 8, s));
     RP_CUDA(cudaEventRecord(c->ev[1], s));
 
     rp::PaintParams P{};
@@ -379,8 +384,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
     P.tailn = c->tailn;
     P.k0 = k0;
     P.nt = nt;
-    P.njobs = 2 * nt;
-    P.ent = c->ent.p;
+    P.ent = c->ent.as<char>() + pad * entsz;
     P.off = c->off.as<long long>();
     P.ia = c->ia.as<int>();
     P.ib = c->ib.as<int>();
@@ -391,14 +395,20 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
     P.ls_alpha = c->lsa.as<float>();
     P.ls_beta = c->lsb.as<float>();
     P.queue = c->queue.as<int>();
-    // fast_painting.hpp:26-39, evaluated in fp64 exactly as written there
+    // fast_painting.hpp:26-39, evaluated in fp64 exactly as written there, then rounded once for the fp32 kernel
     const double theta_ratio = c->theta / (1.0 - c->theta) - 1.0;
-    P.tau_mul = 1.0 * theta_ratio + 1.0;
-    P.prior_n = ntheta / (N - 1.0);
-    P.ntheta = ntheta;
-    P.inv_ntheta = 1.0 / ntheta;
-    P.lower = 1e-10;
-    P.upper = 1.0 / P.lower;
+    P.cd.tau = 1.0 * theta_ratio + 1.0;
+    P.cd.prior_n = ntheta / (N - 1.0);
+    P.cd.ntheta = ntheta;
+    P.cd.inv_ntheta = 1.0 / ntheta;
+    P.cd.lower = 1e-10;
+    P.cd.upper = 1.0 / P.cd.lower;
+    P.cf.tau = (float)P.cd.tau;
+    P.cf.prior_n = (float)P.cd.prior_n;
+    P.cf.ntheta = (float)P.cd.ntheta;
+    P.cf.inv_ntheta = (float)P.cd.inv_ntheta;
+    P.cf.lower = (float)P.cd.lower;
+    P.cf.upper = (float)P.cd.upper;
     int ctas = 0;
     RP_TRY(launch_paint(c, P, lp, c->scratch, ctas));
     launches += 1;

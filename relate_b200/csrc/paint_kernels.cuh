@@ -351,101 +351,130 @@ template <> struct Real<double> {
     static __device__ __forceinline__ V2 mk(double x, double y) { return make_double2(x, y); }
 };
 
+template <typename T> struct PaintConsts { // fast_painting.hpp:26-39, already in the kernel's arithmetic type
+    T tau;        // theta_ratio + 1.0: the mismatch multiplier
+    T prior_n;    // ntheta/(N-1)
+    T ntheta;
+    T inv_ntheta;
+    T lower, upper; // rescaling band (1e-10, 1e10)
+};
+
 struct PaintParams {
     const uint32_t *G;     // SNP-major bits
     int wps;               // words per SNP row
     int N, L, W;
     int nfw;               // full 32-haplotype words: N / 32
     int tailn;             // N % 32
-    int k0, nt;            // targets [k0, k0+nt)
-    int njobs;             // 2*nt
-    const void *ent;       // EntF[] or EntD[]
+    int k0, nt;            // targets [k0, k0+nt); each is one forward and one backward job
+    const void *ent;       // EntF[] or EntD[], padded by 4 valid entries at both ends
     const long long *off;  // [nt+1]
     const int *ia, *ib;    // [nt][W] boundary indices into the site list
     const double *lsA, *lsB; // [nt][W] log-scale bases
     float *alpha, *beta;   // [nt][W][N]
     float *ls_alpha, *ls_beta; // [nt][W]
-    int *queue;            // job counter
+    int *queue;            // two job counters: [0] forward, [1] backward
     double *scratch;       // fp64 mode only: [gridDim.x][N] staging rows for backward stepping stones
-    // model constants, fp64 (fast_painting.hpp:26-39)
-    double tau_mul;        // theta_ratio + 1.0  (the mismatch multiplier)
-    double prior_n;        // ntheta/(N-1)
-    double ntheta;
-    double inv_ntheta;
-    double lower, upper;
+    PaintConsts<float> cf;
+    PaintConsts<double> cd;
 };
 
-// The team of T = blockDim.x threads owns the job's vector.  Thread t owns genotype words
-// j*T + t (j < WPT); a word's 32 haplotypes sit in 32 registers, rotated by rot = k & 31.
-//
-// Register budget: 32*WPT state registers (x2 for fp64) + ~25.  MAXT bounds blockDim so that
-// ptxas keeps the state in registers: fp32 WPT=1 -> 1024 threads (<=64 regs), fp32 WPT=2 and
-// fp64 WPT=1 -> 512 threads (<=128 regs).
+template <typename T> __device__ __forceinline__ const PaintConsts<T> &paint_consts(const PaintParams &P);
+template <> __device__ __forceinline__ const PaintConsts<float> &paint_consts<float>(const PaintParams &P) { return P.cf; }
+template <> __device__ __forceinline__ const PaintConsts<double> &paint_consts<double>(const PaintParams &P) { return P.cd; }
+
+// Launch geometry.  The team of T = blockDim.x threads owns a job's N-vector: thread t owns genotype words
+// j*T + t (j < WPT); a word's 32 haplotypes sit in 32 registers, rotated by rot = k & 31 so that the target
+// is slot 0 of its word.  Register budget: 32*WPT state registers (x2 for fp64) + ~30.
 template <typename T, int WPT, bool MULTI>
 struct PaintCfg {
     static constexpr int kStateRegs = 32 * WPT * (int)(sizeof(T) / 4);
-    static constexpr int kMaxThreads = MULTI ? (kStateRegs <= 32 ? 1024 : 512) : 32;
-    static constexpr int kMinBlocks = MULTI ? 1 : (kStateRegs <= 32 ? 16 : 8);
+    // register caps: multi-warp teams 80 (fp32, one word per thread: <=384 threads, 2 CTAs/SM), 128 (fp32, two
+    // words: <=512 threads) or 168 (fp64: <=384 threads); single-warp teams 128 or 255
+    static constexpr bool kF64 = sizeof(T) == 8;
+    static constexpr int kMaxThreads = MULTI ? ((kStateRegs <= 32 || kF64) ? 384 : 512) : 32;
+    static constexpr int kMinBlocks = MULTI ? (kStateRegs <= 32 ? 2 : 1) : (kStateRegs <= 32 ? 16 : 8);
 };
 
-template <typename T, int WPT, bool MULTI>
-__global__ void __launch_bounds__(PaintCfg<T, WPT, MULTI>::kMaxThreads, PaintCfg<T, WPT, MULTI>::kMinBlocks)
-paint_kernel(const PaintParams P)
+__device__ __forceinline__ void opaque(float &x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void opaque(double &x) { asm volatile("" : "+d"(x)); }
+
+template <typename T, int WPT, bool MULTI, int DIR>
+__device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (*s_part)[32])
 {
     using RT = Real<T>;
     using V2 = typename RT::V2;
     using Ent = typename RT::Ent;
+    constexpr int ES = DIR ? -1 : 1; // direction of travel through the site list
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int TT = blockDim.x, TW = TT >> 5;
-    __shared__ int s_job;
-    __shared__ T s_part[2][32];
-
-    const T tau = (T)P.tau_mul;
-    const T lower = (T)P.lower, upper = (T)P.upper;
+    const PaintConsts<T> &K = paint_consts<T>(P);
+    const T tau = K.tau;
     const Ent *ents = reinterpret_cast<const Ent *>(P.ent);
     T *scratch = reinterpret_cast<T *>(P.scratch) + (size_t)blockIdx.x * P.N; // dereferenced in fp64 mode only
+    int *queue = P.queue + DIR;
+    const unsigned rowbytes = (unsigned)P.wps * 4u;
 
+    // Long-lived per-thread facts are kept as multipliers / opaque registers rather than predicates: R2P
+    // rewrites P0-P6 four times per word, so a predicate cannot survive a step, and ptxas would otherwise
+    // rematerialise pointers and masks from the constant bank every iteration.
     bool valid[WPT];
+    const char *gthr[WPT]; // this thread's word within a row (threads without a word read word 0 and ignore it)
+    T vmul[WPT];           // 1 for threads that own a word, 0 otherwise: R*vmul keeps an unused slot at exactly 0
 #pragma unroll
-    for (int j = 0; j < WPT; j++) valid[j] = (j * TT + t) < P.nfw;
-    const bool tail_warp = (P.tailn > 0) && (warp == 0);
-    const bool tail_valid = tail_warp && (lane < P.tailn);
+    for (int j = 0; j < WPT; j++) {
+        valid[j] = (j * TT + t) < P.nfw;
+        gthr[j] = reinterpret_cast<const char *>(P.G + (valid[j] ? j * TT + t : 0));
+        vmul[j] = valid[j] ? (T)1 : (T)0;
+        asm volatile("" : "+l"(gthr[j]));
+        opaque(vmul[j]);
+    }
+    const bool has_tail = P.tailn > 0;                 // kernel-uniform
+    const bool tail_warp = has_tail && (warp == 0);
+    const bool tail_lane = tail_warp && (lane < P.tailn);
+    const char *gtail = reinterpret_cast<const char *>(P.G + (has_tail ? P.nfw : 0));
+    uint32_t lanebit = 1u << lane;
+    asm volatile("" : "+l"(gtail));
+    asm volatile("" : "+r"(lanebit));
+
+    const T chk = DIR ? K.ntheta : (T)1;        // the band is tested on chk*S  (B = ntheta*G backward)
+    const T resc_R = DIR ? K.inv_ntheta : (T)1; // R after a rescale, before *c_i
 
     for (;;) {
-        int job;
+        int kk;
         if (MULTI) {
             __syncthreads();
-            if (t == 0) s_job = atomicAdd(P.queue, 1);
+            if (t == 0) *s_job = atomicAdd(queue, 1);
             __syncthreads();
-            job = s_job;
+            kk = *s_job;
         } else {
-            job = 0;
-            if (lane == 0) job = atomicAdd(P.queue, 1);
-            job = __shfl_sync(0xffffffffu, job, 0);
+            kk = 0;
+            if (lane == 0) kk = atomicAdd(queue, 1);
+            kk = __shfl_sync(0xffffffffu, kk, 0);
         }
-        if (job >= P.njobs) break;
-        const int kk = job >> 1, dir = job & 1, k = P.k0 + kk;
+        if (kk >= P.nt) break;
+        const int k = P.k0 + kk;
         const long long base = P.off[kk];
         const int m = (int)(P.off[kk + 1] - base) - 1;
-        const Ent *ent = ents + base;
+        const Ent *pe = ents + base + (DIR ? m : 0); // entry of step p is pe[p*ES]
         const int rot = k & 31, wk = k >> 5;
         bool own[WPT];
 #pragma unroll
         for (int j = 0; j < WPT; j++) own[j] = (wk < P.nfw) && (j * TT + t == wk);
-        const bool own_tail = tail_valid && (wk == P.nfw) && (lane == rot);
+        const bool tail_live = tail_lane && !((wk == P.nfw) && (lane == rot)); // valid tail slot that is not the target
+        T ownmul[WPT]; // 0 on the thread/word holding the target (slot 0 after rotation), else 1
+#pragma unroll
+        for (int j = 0; j < WPT; j++) { ownmul[j] = own[j] ? (T)0 : (T)1; opaque(ownmul[j]); }
+        T tailmul = tail_live ? (T)1 : (T)0;
+        opaque(tailmul);
 
-        // boundary bookkeeping, in step order
-        const int *bidx = (dir ? P.ib : P.ia) + (size_t)kk * P.W;
-        const double *lsb = (dir ? P.lsB : P.lsA) + (size_t)kk * P.W;
-        float *outv = (dir ? P.beta : P.alpha) + (size_t)kk * P.W * P.N;
-        float *outl = (dir ? P.ls_beta : P.ls_alpha) + (size_t)kk * P.W;
-        // q walks windows in the order the job meets them: forward w = q, backward w = W-1-q
+        // boundary bookkeeping, in the order the job meets the windows: forward w = q, backward w = W-1-q
+        const int *bidx = (DIR ? P.ib : P.ia) + (size_t)kk * P.W;
+        const double *lsb = (DIR ? P.lsB : P.lsA) + (size_t)kk * P.W;
+        float *outv = (DIR ? P.beta : P.alpha) + (size_t)kk * P.W * P.N;
+        float *outl = (DIR ? P.ls_beta : P.ls_alpha) + (size_t)kk * P.W;
+        auto bpos = [&](int qq) -> int { return DIR ? (m - bidx[P.W - 1 - qq]) : bidx[qq]; };
         int q = 0;
-        auto bpos = [&](int qq) -> int { // step position of the qq-th boundary
-            return dir ? (m - bidx[P.W - 1 - qq]) : bidx[qq];
-        };
-        int nextb = bpos(0);
 
         // state
         V2 a[WPT][16];
@@ -454,143 +483,196 @@ paint_kernel(const PaintParams P)
 #pragma unroll
             for (int e = 0; e < 16; e++) a[j][e] = RT::mk((T)0, (T)0);
         T tl = (T)0;
-        T R = dir ? (T)1 : (T)P.prior_n;  // first step is "(0 + R0) * m"
-        const T chk = dir ? (T)P.ntheta : (T)1;      // band is tested on chk*S
-        const T resc_R = dir ? (T)P.inv_ntheta : (T)1; // R after a rescale (before *c_i)
         double lsr = 0.0; // log-scale added by rescaling
 
-        // software pipeline: entries 3 steps ahead, genotype words 2 steps ahead
-        auto eidx = [&](int p) -> int { p = p > m ? m : p; return dir ? m - p : p; };
-        Ent eC = ent[eidx(0)], eN = ent[eidx(1)], eNN = ent[eidx(2)];
-        uint32_t wC[WPT], wN[WPT], twC = 0, twN = 0;
-#pragma unroll
-        for (int j = 0; j < WPT; j++) {
-            wC[j] = valid[j] ? P.G[(size_t)eC.site * P.wps + j * TT + t] : 0u;
-            wN[j] = valid[j] ? P.G[(size_t)eN.site * P.wps + j * TT + t] : 0u;
-        }
-        if (tail_warp) {
-            twC = P.G[(size_t)eC.site * P.wps + P.nfw];
-            twN = P.G[(size_t)eN.site * P.wps + P.nfw];
-        }
-
-        for (int p = 0; p <= m + 1; p++) {
-            // ---- stepping-stone stores (rare) -------------------------------------------
-            // forward: the state after step p-1 (post-rescale) is the stored alpha (:354-374).
-            // backward: the stored beta at step p is b = g_old + R' *before* the emission
-            // multiply (:481-488), divided by B if this step rescales (:538-551 precede :559-578);
-            // it is written in T precision first (fp32: straight into the output row, fp64:
-            // into this CTA's scratch row) and finalised after the chain below.
-            const bool bnd = dir ? (nextb == p) : (nextb == p - 1);
-            int q1 = q;
-            if (bnd) {
-                while (q1 < P.W && bpos(q1) == nextb) q1++;
-                const bool ones = dir && (p == 0);
-                const T addR = dir ? R : (T)0;
-                auto store_vec = [&](auto *o) {
-                    using O = typename std::remove_pointer<decltype(o)>::type;
-#pragma unroll
-                    for (int j = 0; j < WPT; j++) {
-                        if (valid[j]) {
-                            const int n0 = (j * TT + t) * 32;
-#pragma unroll
-                            for (int e = 0; e < 16; e++) {
-                                T vx = a[j][e].x + addR, vy = a[j][e].y + addR;
-                                if (ones) { vx = (T)1; vy = (T)1; }
-                                else if (e == 0 && own[j]) vx = (T)0;
-                                o[n0 + ((2 * e + rot) & 31)] = (O)vx;
-                                o[n0 + ((2 * e + 1 + rot) & 31)] = (O)vy;
-                            }
-                        }
-                    }
-                    if (tail_valid) {
-                        T v = tl + addR;
-                        if (ones) v = (T)1; else if (own_tail) v = (T)0;
-                        o[P.nfw * 32 + lane] = (O)v;
-                    }
-                };
-                if (dir && sizeof(T) == 8) {
-                    store_vec(scratch);
-                } else {
-                    for (int qq = q; qq < q1; qq++) {
-                        const int w = dir ? P.W - 1 - qq : qq;
-                        store_vec(outv + (size_t)w * P.N);
-                        if (!dir && t == 0) outl[w] = (float)(lsb[w] + lsr);
-                    }
-                }
-                if (!dir) { q = q1; nextb = q < P.W ? bpos(q) : 0x7fffffff; }
-            }
-            if (p > m) break;
-
-            // ---- prefetch --------------------------------------------------------------
-            const Ent eNNN = ent[eidx(p + 3)];
-            uint32_t wNN[WPT], twNN = 0;
-#pragma unroll
-            for (int j = 0; j < WPT; j++) wNN[j] = valid[j] ? P.G[(size_t)eNN.site * P.wps + j * TT + t] : 0u;
-            if (tail_warp) twNN = P.G[(size_t)eNN.site * P.wps + P.nfw];
-
-            // ---- the step: x <- (x + R) * (mis ? tau : 1), S = sum x -----------------------
-            // mis = target derived && reference ancestral.  Interior sites are derived by
-            // construction; SNP 0 and SNP L-1 are visited regardless (fast_painting.cpp:52-59,150).
-            uint32_t tdm = 0xffffffffu;
-            if (p == 0 || p == m) {
-                const uint32_t kw = P.G[(size_t)eC.site * P.wps + wk];
-                tdm = ((kw >> rot) & 1u) ? 0xffffffffu : 0u;
-            }
-            V2 S0 = RT::mk((T)0, (T)0), S1 = RT::mk((T)0, (T)0);
-            const V2 R2 = RT::mk(R, R);
+        // x <- (x + R) * (mis ? tau : 1);  returns the team-wide sum.  mis = target derived && reference
+        // ancestral; tdm is all-ones when the target is derived at the site (always, except SNP 0 / L-1).
+        auto step = [&](const uint32_t (&w)[WPT], uint32_t tw, uint32_t tdm, T R, int parity) -> T {
+            V2 S0, S1, S2, S3;
 #pragma unroll
             for (int j = 0; j < WPT; j++) {
-                if (valid[j]) {
-                    const uint32_t nb = ~wC[j] & tdm;
-                    const uint32_t mw = __funnelshift_r(nb, nb, rot);
+                const T Rj = R * vmul[j];
+                const V2 R2 = RT::mk(Rj, Rj);
+                const uint32_t nb = ~w[j] & tdm;
+                const uint32_t mw = __funnelshift_r(nb, nb, rot);
 #pragma unroll
-                    for (int e = 0; e < 16; e++) {
-                        V2 v = RT::add2(a[j][e], R2);
-                        if (mw & (1u << (2 * e))) v.x *= tau;
-                        if (mw & (2u << (2 * e))) v.y *= tau;
-                        if (e == 0 && own[j]) v.x = (T)0;
-                        a[j][e] = v;
-                        if (e & 1) S1 = RT::add2(S1, v); else S0 = RT::add2(S0, v);
-                    }
+                for (int e = 0; e < 16; e++) {
+                    V2 v = RT::add2(a[j][e], R2);
+                    if (mw & (1u << (2 * e))) v.x *= tau;
+                    if (mw & (2u << (2 * e))) v.y *= tau;
+                    if (e == 0) v.x *= ownmul[j];
+                    a[j][e] = v;
+                    if (j == 0 && e < 4) { // the first four pairs seed the accumulators
+                        if (e == 0) S0 = v; else if (e == 1) S1 = v; else if (e == 2) S2 = v; else S3 = v;
+                    } else if ((e & 3) == 0) S0 = RT::add2(S0, v);
+                    else if ((e & 3) == 1) S1 = RT::add2(S1, v);
+                    else if ((e & 3) == 2) S2 = RT::add2(S2, v);
+                    else S3 = RT::add2(S3, v);
                 }
             }
-            S0 = RT::add2(S0, S1);
+            S0 = RT::add2(RT::add2(S0, S1), RT::add2(S2, S3));
             T S = S0.x + S0.y;
-            if (tail_warp) {
+            if (MULTI ? tail_warp : has_tail) {
                 T v = tl + R;
-                if ((~twC & tdm) >> lane & 1u) v *= tau;
-                if (!tail_valid || own_tail) v = (T)0;
-                tl = v;
-                S += v;
+                if (~tw & tdm & lanebit) v *= tau;
+                tl = v * tailmul;
+                S += tl;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
             if (MULTI) {
-                T *part = s_part[p & 1];
+                T *part = s_part[parity];
                 if (lane == 0) part[warp] = S;
                 __syncthreads();
                 S = part[0];
-                for (int w = 1; w < TW; w++) S += part[w];
+#pragma unroll 4
+                for (int ww = 1; ww < TW; ww++) S += part[ww];
+            }
+            return S;
+        };
+
+        // writes the team's vector (x + addR, target forced to 0; or all ones) to o[0..N)
+        auto store_vec = [&](auto *o, T addR, bool ones) {
+            using O = typename std::remove_pointer<decltype(o)>::type;
+#pragma unroll
+            for (int j = 0; j < WPT; j++) {
+                if (valid[j]) {
+                    const int n0 = (j * TT + t) * 32;
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        T vx = a[j][e].x + addR, vy = a[j][e].y + addR;
+                        if (ones) { vx = (T)1; vy = (T)1; }
+                        else if (e == 0 && own[j]) vx = (T)0;
+                        o[n0 + ((2 * e + rot) & 31)] = (O)vx;
+                        o[n0 + ((2 * e + 1 + rot) & 31)] = (O)vy;
+                    }
+                }
+            }
+            if (tail_lane) {
+                T v = tl + addR;
+                if (ones) v = (T)1; else if (!tail_live) v = (T)0;
+                o[P.nfw * 32 + lane] = (O)v;
+            }
+        };
+
+        // target's own allele at the first and the last step (SNP 0 / SNP L-1 are visited regardless, :52-59,150)
+        const int site_first = pe[0].site, site_last = pe[m * ES].site;
+        const uint32_t td_first = ((P.G[(size_t)site_first * P.wps + wk] >> rot) & 1u) ? 0xffffffffu : 0u;
+        const uint32_t td_last = ((P.G[(size_t)site_last * P.wps + wk] >> rot) & 1u) ? 0xffffffffu : 0u;
+
+        // ---- software pipeline -------------------------------------------------------------------
+        // At step p the team holds the genotype words of steps p and p+1, loads those of step p+2 (whose
+        // site index was loaded during step p-1) and the site index of step p+3.  Entries up to 3 past
+        // either end of the target's list are read and never used (the table is padded).
+        uint32_t wC[WPT], wN[WPT], wNN[WPT], twC = 0, twN = 0, twNN = 0;
+        {
+            const int s1 = pe[ES].site; // m >= 1
+#pragma unroll
+            for (int j = 0; j < WPT; j++) {
+                wC[j] = *reinterpret_cast<const uint32_t *>(gthr[j] + (size_t)(unsigned)site_first * rowbytes);
+                wN[j] = *reinterpret_cast<const uint32_t *>(gthr[j] + (size_t)(unsigned)s1 * rowbytes);
+            }
+            if (MULTI ? tail_warp : has_tail) {
+                twC = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)site_first * rowbytes);
+                twN = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)s1 * rowbytes);
+            }
+        }
+        int sNN = pe[2 * ES].site, sNNN = 0; // sites of steps p+2, p+3
+        T cC = (T)pe[0].c, cNext = (T)0;     // c of steps p, p+1
+        const Ent *pf = pe + 3 * ES;         // entry of step p+3
+        auto prefetch = [&]() {
+#pragma unroll
+            for (int j = 0; j < WPT; j++)
+                wNN[j] = *reinterpret_cast<const uint32_t *>(gthr[j] + (size_t)(unsigned)sNN * rowbytes);
+            if (MULTI ? tail_warp : has_tail) twNN = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)sNN * rowbytes);
+            sNNN = pf->site;
+            cNext = (T)(pf - 2 * ES)->c;
+        };
+        auto rotate = [&]() {
+#pragma unroll
+            for (int j = 0; j < WPT; j++) { wC[j] = wN[j]; wN[j] = wNN[j]; }
+            twC = twN; twN = twNN;
+            sNN = sNNN;
+            cC = cNext;
+            pf += ES;
+        };
+
+        // ---- step 0: x = (0 + R0) * m.  No rescale test at the first site (:206-263, :401-458). ----
+        if (DIR) { // beta at SNP L-1 is all ones, the target included (:413-418, :433-448)
+            int q1 = q;
+            while (q1 < P.W && bpos(q1) == 0) q1++;
+            for (int qq = q; qq < q1; qq++) {
+                const int w = P.W - 1 - qq;
+                store_vec(outv + (size_t)w * P.N, (T)0, true);
+                if (t == 0) outl[w] = (float)lsb[w];
+            }
+            q = q1;
+        }
+        prefetch();
+        T R = step(wC, twC, td_first, DIR ? (T)1 : K.prior_n, 0) * cC;
+        rotate();
+
+        // next event: a stepping-stone store (forward: after step bpos, i.e. at the top of step bpos+1;
+        // backward: at step bpos) or the last step (target allele mask)
+        auto next_event = [&]() -> int {
+            const int nb = q < P.W ? bpos(q) + (DIR ? 0 : 1) : 0x7fffffff;
+            return nb < m ? nb : m;
+        };
+        int pev = next_event();
+        uint32_t tdm = 0xffffffffu;
+
+        for (int p = 1; p <= m; p++) {
+            bool post = false; // backward: stepping stone(s) of this step to finalise after the chain
+            int q1 = q;
+            if (__builtin_expect(p == pev, 0)) { // rare
+                if (p == m) tdm = td_last;
+                const int bp_now = q < P.W ? bpos(q) : -1;
+                if (bp_now == (DIR ? p : p - 1)) {
+                    while (q1 < P.W && bpos(q1) == bp_now) q1++;
+                    if (!DIR) { // alpha after step p-1, post-rescale (:354-374)
+                        for (int qq = q; qq < q1; qq++) {
+                            store_vec(outv + (size_t)qq * P.N, (T)0, false);
+                            if (t == 0) outl[qq] = (float)(lsb[qq] + lsr);
+                        }
+                        q = q1;
+                    } else { // beta of this step is b = g_old + R' before the emission multiply (:481-488)
+                        post = true;
+                        if (sizeof(T) == 8) store_vec(scratch, R, false);
+                        else for (int qq = q; qq < q1; qq++) store_vec(outv + (size_t)(P.W - 1 - qq) * P.N, R, false);
+                    }
+                }
+                if (!post) pev = (p == m) ? 0x7fffffff : next_event();
             }
 
-            // ---- scalar chain: rescale test, next R (fast_painting.cpp:331-352, 536-556) ----
+            prefetch();
+            const T S = step(wC, twC, tdm, R, p & 1);
+
+            // scalar chain: rescale test, next R (:331-352, :536-556)
             const T B = chk * S;
             bool rescaled = false;
-            if (p > 0 && (B < lower || B > upper)) {
+            if (__builtin_expect(B < K.lower || B > K.upper, 0)) { // about one step in 50 on coalescent data
                 rescaled = true;
+                if (sizeof(T) == 4) { // fp32 state: one reciprocal, then multiplies (<= 1 ulp from the division)
+                    const T inv = (T)1 / B;
 #pragma unroll
-                for (int j = 0; j < WPT; j++)
+                    for (int j = 0; j < WPT; j++)
 #pragma unroll
-                    for (int e = 0; e < 16; e++) { a[j][e].x /= B; a[j][e].y /= B; }
-                tl /= B;
-                lsr += dir ? (double)fast_log_dev((float)B) : log((double)B);
-                R = resc_R;
+                        for (int e = 0; e < 16; e++) { a[j][e].x *= inv; a[j][e].y *= inv; }
+                    tl *= inv;
+                } else { // fp64 verification mode divides, as the reference does (:338-342, :543-547)
+#pragma unroll
+                    for (int j = 0; j < WPT; j++)
+#pragma unroll
+                        for (int e = 0; e < 16; e++) { a[j][e].x /= B; a[j][e].y /= B; }
+                    tl /= B;
+                }
+                lsr += DIR ? (double)fast_log_dev((float)B) : log((double)B);
+                R = resc_R * cC;
             } else {
-                R = S;
+                R = S * cC;
             }
-            R *= (T)eC.c;
 
-            if (dir && bnd) { // finalise the backward stepping stone(s) of this step
+            if (DIR && __builtin_expect(post, 0)) { // finalise the backward stepping stone(s): divide by B if this step rescaled
                 for (int qq = q; qq < q1; qq++) {
                     const int w = P.W - 1 - qq;
                     float *o = outv + (size_t)w * P.N;
@@ -607,7 +689,7 @@ paint_kernel(const PaintParams P)
                                 }
                             }
                         }
-                        if (tail_valid) {
+                        if (tail_lane) {
                             T v = src[P.nfw * 32 + lane];
                             if (rescaled) v /= B;
                             o[P.nfw * 32 + lane] = (float)v;
@@ -616,16 +698,30 @@ paint_kernel(const PaintParams P)
                     if (t == 0) outl[w] = (float)(lsb[w] + lsr);
                 }
                 q = q1;
-                nextb = q < P.W ? bpos(q) : 0x7fffffff;
+                pev = (p == m) ? 0x7fffffff : next_event();
             }
+            rotate();
+        }
 
-            // ---- rotate the pipeline -----------------------------------------------------
-            eC = eN; eN = eNN; eNN = eNNN;
-#pragma unroll
-            for (int j = 0; j < WPT; j++) { wC[j] = wN[j]; wN[j] = wNN[j]; }
-            twC = twN; twN = twNN;
+        if (!DIR) { // alpha stepping stones at the last visited site
+            while (q < P.W) {
+                store_vec(outv + (size_t)q * P.N, (T)0, false);
+                if (t == 0) outl[q] = (float)(lsb[q] + lsr);
+                q++;
+            }
         }
     }
+}
+
+template <typename T, int WPT, bool MULTI>
+__global__ void __launch_bounds__(PaintCfg<T, WPT, MULTI>::kMaxThreads, PaintCfg<T, WPT, MULTI>::kMinBlocks)
+paint_kernel(const PaintParams P)
+{
+    __shared__ int s_job;
+    __shared__ T s_part[2][32];
+    // even CTAs walk the site lists forwards (alpha), odd CTAs backwards (beta): two instantiations of one loop
+    if (blockIdx.x & 1) paint_jobs<T, WPT, MULTI, 1>(P, &s_job, s_part);
+    else paint_jobs<T, WPT, MULTI, 0>(P, &s_job, s_part);
 }
 
 } // namespace rp
