@@ -487,7 +487,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 
         // x <- (x + R) * (mis ? tau : 1);  returns the team-wide sum.  mis = target derived && reference
         // ancestral; tdm is all-ones when the target is derived at the site (always, except SNP 0 / L-1).
-        auto step = [&](const uint32_t (&w)[WPT], uint32_t tw, uint32_t tdm, T R, int parity) -> T {
+        auto step_local = [&](const uint32_t (&w)[WPT], uint32_t tw, uint32_t tdm, T R) -> T {
             V2 S0, S1, S2, S3;
 #pragma unroll
             for (int j = 0; j < WPT; j++) {
@@ -518,6 +518,10 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 tl = v * tailmul;
                 S += tl;
             }
+            return S;
+        };
+        // team-wide sum: warp butterfly, then (multi-warp teams) one bar.sync and a shared-memory exchange
+        auto reduce = [&](T S, int parity) -> T {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
             if (MULTI) {
@@ -608,9 +612,14 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             }
             q = q1;
         }
-        prefetch();
-        T R = step(wC, twC, td_first, DIR ? (T)1 : K.prior_n, 0) * cC;
-        rotate();
+        T R;
+        {
+            const T Sl = step_local(wC, twC, td_first, DIR ? (T)1 : K.prior_n);
+            const T c0 = cC;
+            prefetch();
+            rotate();
+            R = reduce(Sl, 0) * c0;
+        }
 
         // next event: a stepping-stone store (forward: after step bpos, i.e. at the top of step bpos+1;
         // backward: at step bpos) or the last step (target allele mask)
@@ -644,8 +653,13 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 if (!post) pev = (p == m) ? 0x7fffffff : next_event();
             }
 
+            // local update and partial sum; then the loads and pipeline rotation for later steps are issued
+            // in the shadow of the reduction's shuffle latency
+            const T Sl = step_local(wC, twC, tdm, R);
+            const T cthis = cC;
             prefetch();
-            const T S = step(wC, twC, tdm, R, p & 1);
+            rotate();
+            const T S = reduce(Sl, p & 1);
 
             // scalar chain: rescale test, next R (:331-352, :536-556)
             const T B = chk * S;
@@ -667,9 +681,9 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                     tl /= B;
                 }
                 lsr += DIR ? (double)fast_log_dev((float)B) : log((double)B);
-                R = resc_R * cC;
+                R = resc_R * cthis;
             } else {
-                R = S * cC;
+                R = S * cthis;
             }
 
             if (DIR && __builtin_expect(post, 0)) { // finalise the backward stepping stone(s): divide by B if this step rescaled
@@ -700,7 +714,6 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 q = q1;
                 pev = (p == m) ? 0x7fffffff : next_event();
             }
-            rotate();
         }
 
         if (!DIR) { // alpha stepping stones at the last visited site
