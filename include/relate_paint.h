@@ -64,6 +64,7 @@ typedef struct rp_stats {
     int words_per_thread;
     int ctas;            /* grid size of the paint kernel                                 */
     int reserved;
+    double ms_load;      /* rp_paint_chunk: reading the chunk files (wall)                */
 } rp_stats;
 
 typedef struct rp_tune { /* all zero = automatic */
@@ -124,6 +125,9 @@ int rp_paint_from_host(int device, int N, int L, const char *hap, const double *
  * <out_dir>/chunk_<c>/paint/relate_<w>.bin in target order.  devices==NULL: device 0 only. */
 int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
                    int n_devices, unsigned flags, rp_stats *stats);
+
+/* rp_paint_chunk parks device buffers, pinned staging and streams per device between calls; this frees them. */
+void rp_release_cache(void);
 
 /* ---- small pieces exposed for the parity tests -------------------------------------- */
 /* Host encoder used by rp_paint_chunk; returns the number of runs K (vals/lens sized n). */

@@ -37,7 +37,7 @@ class RpStats(C.Structure):
                 ("sites", C.c_longlong), ("cells", C.c_longlong), ("h2d_bytes", C.c_longlong),
                 ("d2h_bytes", C.c_longlong), ("launches", C.c_int), ("n_targets", C.c_int),
                 ("team_threads", C.c_int), ("words_per_thread", C.c_int), ("ctas", C.c_int),
-                ("reserved", C.c_int)]
+                ("reserved", C.c_int), ("ms_load", C.c_double)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -67,6 +67,7 @@ SYMBOLS = {
     "rp_paint_from_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_double, C.c_uint,
                                      C.POINTER(RpTune), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(RpStats)]),
     "rp_paint_chunk": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, _P, C.c_int, C.c_uint, C.POINTER(RpStats)]),
+    "rp_release_cache": (None, []),
     "rp_rle_encode": (C.c_int, [_P, C.c_int, _P, _P]),
     "rp_fast_log_device": (C.c_int, [C.c_int, _P, _P, C.c_int]),
     "rp_debug_pack": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int), _P, C.POINTER(C.c_int)]),

@@ -21,7 +21,8 @@ namespace rp {
 struct HostChunk {
     int N = 0, L = 0;
     std::vector<int> wb;      // W+1 window boundaries
-    std::vector<char> hap;    // L*N chars, SNP-major
+    char *hap = nullptr;      // L*N chars, SNP-major; points into hap_own or into caller-provided (pinned) memory
+    std::vector<char> hap_own;
     std::vector<double> r;    // L, multiplied by rho
     double theta = 0.001;     // data.cpp:95
 };
@@ -33,7 +34,10 @@ inline bool file_exists(const std::string &p)
 }
 
 // returns "" on success, else the error text
-inline std::string load_chunk_files(const std::string &dir, int chunk, const char *painting, HostChunk &hc)
+// alloc_hap(bytes) may hand out pinned memory for the L*N genotype chars (nullptr -> std::vector)
+template <typename AllocHap>
+inline std::string load_chunk_files(const std::string &dir, int chunk, const char *painting, HostChunk &hc,
+                                    AllocHap alloc_hap)
 {
     const std::string base = dir + "/chunk_" + std::to_string(chunk);
     {
@@ -62,8 +66,13 @@ inline std::string load_chunk_files(const std::string &dir, int chunk, const cha
             return p + ": dimensions disagree with parameters file";
         }
         if (ok) {
-            hc.hap.resize((size_t)uL * uN);
-            ok = fread(hc.hap.data(), 1, hc.hap.size(), fp) == hc.hap.size();
+            const size_t nbytes = (size_t)uL * uN;
+            hc.hap = alloc_hap(nbytes);
+            if (!hc.hap) {
+                hc.hap_own.resize(nbytes);
+                hc.hap = hc.hap_own.data();
+            }
+            ok = fread(hc.hap, 1, nbytes, fp) == nbytes;
         }
         fclose(fp);
         if (!ok) return "short read in " + p;
@@ -91,6 +100,11 @@ inline std::string load_chunk_files(const std::string &dir, int chunk, const cha
     }
     if (hc.wb.back() != hc.L || hc.wb.front() != 0) return "window boundaries do not span the chunk";
     return "";
+}
+
+inline std::string load_chunk_files(const std::string &dir, int chunk, const char *painting, HostChunk &hc)
+{
+    return load_chunk_files(dir, chunk, painting, hc, [](size_t) -> char * { return nullptr; });
 }
 
 // Run-length rule of the stepping-stone codec: v joins the run when

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -94,7 +95,7 @@ struct rp_chunk {
     std::vector<int> wb;
     rp_tune tune{};
     // resident
-    DevBuf G, GT, r, Phi, Plo, wbdev;
+    DevBuf G, GT, r, Phi, Plo, wbdev, chars;
     // per-paint work buffers (grown on demand, reused)
     DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch;
     long long *h_total = nullptr; // pinned
@@ -212,7 +213,12 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
     if (device < 0 || device >= ndev) return fail(RP_EINVAL, "device index out of range");
     RP_CUDA(cudaSetDevice(device));
 
-    rp_chunk *c = new rp_chunk();
+    // *out may carry a parked chunk of the same device whose buffers, stream and events are reused
+    rp_chunk *c = (*out && (*out)->device == device) ? *out : nullptr;
+    const bool reused = c != nullptr;
+    if (*out && !reused) rp_chunk_free(*out);
+    *out = nullptr;
+    if (!c) c = new rp_chunk();
     auto bail = [&](int rc) {
         std::string keep = g_err;
         rp_chunk_free(c);
@@ -241,19 +247,23 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
     c->tailn = N % 32;
     c->wps = (((N + 31) / 32) + 3) / 4 * 4; // rows padded to 16 bytes
     c->lw = (L + 31) / 32;
-    cudaDeviceProp prop;
-    RP_CUDAB(cudaGetDeviceProperties(&prop, device));
-    c->sm_count = prop.multiProcessorCount;
-    if (prop.major < 10) return bail(fail(RP_ENODEVICE, "device is not sm_100-class; this library ships sm_100a code only"));
-    RP_CUDAB(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    if (!reused) {
+        int major = 0, sms = 0;
+        RP_CUDAB(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+        RP_CUDAB(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        c->sm_count = sms;
+        if (major < 10) return bail(fail(RP_ENODEVICE, "device is not sm_100-class; this library ships sm_100a code only"));
+        RP_CUDAB(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        for (auto &e : c->ev) RP_CUDAB(cudaEventCreate(&e));
+        RP_CUDAB(cudaMallocHost(&c->h_total, sizeof(long long)));
+    }
     c->stream = c->own_stream;
-    for (auto &e : c->ev) RP_CUDAB(cudaEventCreate(&e));
-    RP_CUDAB(cudaMallocHost(&c->h_total, sizeof(long long)));
+    c->tune = rp_tune{};
     LaunchPlan lp;
     RP_TRYB(plan_launch(c, lp));
 
     const double t0 = now_ms();
-    DevBuf chars;
+    DevBuf &chars = c->chars;
     const size_t nchar = (size_t)L * N;
     RP_TRYB(chars.ensure(nchar));
     RP_TRYB(c->G.ensure((size_t)L * c->wps * 4));
@@ -284,7 +294,7 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
     }
     RP_CUDAB(cudaEventRecord(c->ev[2], c->stream));
     RP_CUDAB(cudaStreamSynchronize(c->stream));
-    chars.release();
+    if (!reused) chars.release(); // a parked workspace keeps its staging buffer for the next chunk
     if (st) {
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
@@ -490,6 +500,7 @@ void rp_host_free(void *p)
 int rp_chunk_create(int device, int N, int L, const char *hap, const double *r, const int *wb, int n_wb,
                     double theta, unsigned flags, rp_chunk **out)
 {
+    if (out) *out = nullptr;
     return chunk_from_host(device, N, L, hap, r, wb, n_wb, theta, flags, out, nullptr);
 }
 
@@ -497,10 +508,11 @@ int rp_chunk_load(int device, const char *out_dir, int chunk_index, const char *
                   rp_chunk **out)
 {
     if (!out_dir || !out) return fail(RP_EINVAL, "null argument");
+    *out = nullptr;
     rp::HostChunk hc;
     std::string err = rp::load_chunk_files(out_dir, chunk_index, painting, hc);
     if (!err.empty()) return fail(RP_EIO, err);
-    return chunk_from_host(device, hc.N, hc.L, hc.hap.data(), hc.r.data(), hc.wb.data(), (int)hc.wb.size(),
+    return chunk_from_host(device, hc.N, hc.L, hc.hap, hc.r.data(), hc.wb.data(), (int)hc.wb.size(),
                            hc.theta, flags, out, nullptr);
 }
 
@@ -540,7 +552,7 @@ void rp_chunk_free(rp_chunk *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
+    for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
                       &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch})
         b->release();
     if (c->h_total) cudaFreeHost(c->h_total);
@@ -672,20 +684,87 @@ int rp_debug_pack(int device, int N, int L, const char *hap, uint32_t *snp_major
     return RP_OK;
 }
 
+} // extern "C"
+
 // ---- the whole stage (pipeline/Paint.cpp:17-108) ----------------------------------------
-// Targets are cut into batches; device threads pull batch indices from one counter (dynamic
-// balance over GPUs, no collective), paint + copy back, RLE-encode their batch per window on
-// host threads, and append to the W files strictly in batch order.
-int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices, int n_devices,
-                   unsigned flags, rp_stats *stats)
+// chunk files -> pinned host -> every GPU's HBM (replica, own H2D, no collective) -> paint in batches of
+// targets pulled from one counter (dynamic balance over GPUs) -> pinned host -> RLE records encoded on host
+// threads per (window, block of targets) -> appended to the W files strictly in batch order.
+// Device buffers, pinned staging and streams are parked in a per-device cache between calls
+// (rp_release_cache() frees them), so a process painting many chunks pays for them once.
+namespace {
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return RP_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return fail(RP_ENOMEM, "cudaHostAlloc of " + std::to_string(bytes) + " bytes failed");
+        }
+        cap = bytes;
+        return RP_OK;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct DeviceWorkspace { // parked between rp_paint_chunk calls
+    rp_chunk *shell = nullptr; // keeps its DevBufs, stream and events
+    PinnedBuf ha, hb;
+};
+
+std::mutex g_stage_mu; // rp_paint_chunk calls are serialised (they share the cache)
+std::map<int, DeviceWorkspace> g_ws;
+PinnedBuf g_hap_in;
+
+template <typename F> void parallel_for(int n, int nthreads, F f)
+{
+    std::atomic<int> next{0};
+    auto body = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n) break;
+            f(i);
+        }
+    };
+    nthreads = std::max(1, std::min(nthreads, n));
+    std::vector<std::thread> ts;
+    for (int i = 1; i < nthreads; i++) ts.emplace_back(body);
+    body();
+    for (auto &t : ts) t.join();
+}
+
+} // namespace
+
+extern "C" void rp_release_cache(void)
+{
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    for (auto &kv : g_ws) {
+        cudaSetDevice(kv.first);
+        if (kv.second.shell) rp_chunk_free(kv.second.shell);
+        kv.second.ha.release();
+        kv.second.hb.release();
+    }
+    g_ws.clear();
+    g_hap_in.release();
+}
+
+extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
+                              int n_devices, unsigned flags, rp_stats *stats)
 {
     if (!out_dir) return fail(RP_EINVAL, "null out_dir");
     const double t0 = now_ms();
-    rp::HostChunk hc;
-    {
-        std::string err = rp::load_chunk_files(out_dir, chunk_index, painting, hc);
-        if (!err.empty()) return fail(RP_EIO, err);
-    }
     int ndev = rp_device_count();
     if (ndev < 1) return fail(RP_ENODEVICE, "no CUDA device (there is no CPU fallback)");
     std::vector<int> devs;
@@ -693,6 +772,17 @@ int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, c
     else devs.push_back(0);
     for (int d : devs)
         if (d < 0 || d >= ndev) return fail(RP_EINVAL, "device index out of range");
+    std::lock_guard<std::mutex> stage_lock(g_stage_mu);
+
+    rp::HostChunk hc;
+    {
+        RP_CUDA(cudaSetDevice(devs[0]));
+        std::string err = rp::load_chunk_files(out_dir, chunk_index, painting, hc, [&](size_t bytes) -> char * {
+            return g_hap_in.ensure(bytes) == RP_OK ? static_cast<char *>(g_hap_in.p) : nullptr;
+        });
+        if (!err.empty()) return fail(RP_EIO, err);
+    }
+    const double t_loaded = now_ms();
 
     const int N = hc.N, W = (int)hc.wb.size() - 1;
     const std::string cdir = std::string(out_dir) + "/chunk_" + std::to_string(chunk_index);
@@ -704,8 +794,8 @@ int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, c
     }
     std::vector<FILE *> files(W, nullptr);
     auto close_all = [&]() {
-        for (FILE *f : files)
-            if (f) fclose(f);
+        for (FILE *&f : files)
+            if (f) { fclose(f); f = nullptr; }
     };
     for (int w = 0; w < W; w++) {
         const std::string p = pdir + "/relate_" + std::to_string(w) + ".bin";
@@ -714,14 +804,16 @@ int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, c
             close_all();
             return fail(RP_EIO, "cannot create " + p);
         }
+        setvbuf(files[w], nullptr, _IONBF, 0); // blobs are written whole
     }
 
-    // batch size: bound the pinned staging per device (~1.5 GB), keep the GPU full
+    // batch size: bound the pinned staging per device (~1.5 GB), keep every GPU busy
     const size_t per_target = (size_t)2 * W * N * 4;
     long long bsz = (long long)((1536ull << 20) / per_target);
     bsz = std::max<long long>(bsz, 64);
     bsz = std::min<long long>(bsz, N);
-    if ((int)devs.size() > 1) bsz = std::min<long long>(bsz, std::max<long long>(64, (N + 2 * (long long)devs.size() - 1) / (2 * (long long)devs.size())));
+    if ((int)devs.size() > 1)
+        bsz = std::min<long long>(bsz, std::max<long long>(64, (N + 2 * (long long)devs.size() - 1) / (2 * (long long)devs.size())));
     const int B = (int)bsz;
     const int nbatch = (N + B - 1) / B;
 
@@ -733,27 +825,31 @@ int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, c
     std::string first_err;
     std::vector<rp_stats> dstats(devs.size());
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int enc_threads = (int)std::max<unsigned>(1, std::min<unsigned>(hw / (unsigned)devs.size(), 32));
+    const int enc_threads = (int)std::max<unsigned>(1, std::min<unsigned>(hw / (unsigned)devs.size(), 64));
+    const int TB = 32; // targets per encode task
 
     auto worker = [&](int di) {
         rp_stats &st = dstats[di];
         memset(&st, 0, sizeof st);
-        rp_chunk *c = nullptr;
-        int rc = chunk_from_host(devs[di], hc.N, hc.L, hc.hap.data(), hc.r.data(), hc.wb.data(), (int)hc.wb.size(),
-                                 hc.theta, flags, &c, &st);
-        float *ha = nullptr, *hb = nullptr;
+        DeviceWorkspace &ws = g_ws[devs[di]];
+        rp_chunk *c = ws.shell;
+        ws.shell = nullptr;
+        int rc = chunk_from_host(devs[di], hc.N, hc.L, hc.hap, hc.r.data(), hc.wb.data(), (int)hc.wb.size(), hc.theta,
+                                 flags, &c, &st);
         std::vector<float> lsa, lsb;
         std::vector<int> sb, se;
         if (rc == RP_OK) {
             const size_t vb = (size_t)B * W * N * 4;
-            if (cudaMallocHost(&ha, vb) != cudaSuccess || cudaMallocHost(&hb, vb) != cudaSuccess)
-                rc = fail(RP_ENOMEM, "cudaMallocHost for the staging buffers failed");
+            rc = ws.ha.ensure(vb);
+            if (rc == RP_OK) rc = ws.hb.ensure(vb);
             lsa.resize((size_t)B * W);
             lsb.resize((size_t)B * W);
             sb.resize((size_t)B * W);
             se.resize((size_t)B * W);
         }
-        std::vector<std::vector<char>> blobs(W);
+        float *ha = static_cast<float *>(ws.ha.p), *hb = static_cast<float *>(ws.hb.p);
+        const int nblk_max = (B + TB - 1) / TB;
+        std::vector<std::vector<char>> blobs((size_t)W * nblk_max);
         while (rc == RP_OK) {
             const int b = next_batch.fetch_add(1);
             if (b >= nbatch) break;
@@ -761,35 +857,37 @@ int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, c
             rc = rp_paint_targets(c, k0, k1, ha, hb, lsa.data(), lsb.data(), sb.data(), se.data(), &st);
             if (rc != RP_OK) break;
             const double te = now_ms();
-            std::vector<std::thread> pool;
-            for (int ti = 0; ti < enc_threads; ti++) {
-                pool.emplace_back([&, ti]() {
-                    std::vector<float> vals;
-                    std::vector<int> lens;
-                    for (int w = ti; w < W; w += enc_threads) {
-                        std::vector<char> &out = blobs[w];
-                        out.clear();
-                        const int a0 = hc.wb[w], b0 = hc.wb[w + 1] - 1;
-                        for (int kk = 0; kk < nt; kk++) { // fast_painting.cpp:589-601
-                            const size_t at = out.size();
-                            out.resize(at + 8);
-                            memcpy(out.data() + at, &a0, 4);
-                            memcpy(out.data() + at + 4, &b0, 4);
-                            const size_t row = ((size_t)kk * W + w);
-                            rp::append_record(out, ha + row * N, N, sb[row], lsa[row], vals, lens);
-                            rp::append_record(out, hb + row * N, N, se[row], lsb[row], vals, lens);
-                        }
-                    }
-                });
-            }
-            for (auto &t : pool) t.join();
+            const int nblk = (nt + TB - 1) / TB;
+            parallel_for(W * nblk, enc_threads, [&](int task) {
+                const int w = task / nblk, blk = task % nblk;
+                std::vector<char> &out = blobs[(size_t)w * nblk_max + blk];
+                out.clear();
+                std::vector<float> vals;
+                std::vector<int> lens;
+                const int a0 = hc.wb[w], b0 = hc.wb[w + 1] - 1;
+                const int kb = blk * TB, ke = std::min(nt, kb + TB);
+                for (int kk = kb; kk < ke; kk++) { // fast_painting.cpp:589-601
+                    const size_t at = out.size();
+                    out.resize(at + 8);
+                    memcpy(out.data() + at, &a0, 4);
+                    memcpy(out.data() + at + 4, &b0, 4);
+                    const size_t row = ((size_t)kk * W + w);
+                    rp::append_record(out, ha + row * N, N, sb[row], lsa[row], vals, lens);
+                    rp::append_record(out, hb + row * N, N, se[row], lsb[row], vals, lens);
+                }
+            });
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return next_write == b || first_rc != RP_OK; });
                 if (first_rc == RP_OK) {
-                    for (int w = 0; w < W && rc == RP_OK; w++)
-                        if (fwrite(blobs[w].data(), 1, blobs[w].size(), files[w]) != blobs[w].size())
-                            rc = fail(RP_EIO, "short write to relate_" + std::to_string(w) + ".bin");
+                    std::atomic<int> werr{0};
+                    parallel_for(W, std::min(enc_threads, 16), [&](int w) { // one writer per window file
+                        for (int blk = 0; blk < nblk; blk++) {
+                            const std::vector<char> &o = blobs[(size_t)w * nblk_max + blk];
+                            if (fwrite(o.data(), 1, o.size(), files[w]) != o.size()) werr = 1;
+                        }
+                    });
+                    if (werr) rc = fail(RP_EIO, "short write to the paint files");
                     next_write = b + 1;
                 }
                 cv.notify_all();
@@ -804,12 +902,11 @@ int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, c
             }
             cv.notify_all();
         }
-        if (ha) cudaFreeHost(ha);
-        if (hb) cudaFreeHost(hb);
-        if (c) rp_chunk_free(c);
+        ws.shell = c; // park the workspace (may be nullptr if creation failed)
     };
     std::vector<std::thread> threads;
-    for (int di = 0; di < (int)devs.size(); di++) threads.emplace_back(worker, di);
+    for (int di = 1; di < (int)devs.size(); di++) threads.emplace_back(worker, di);
+    worker(0);
     for (auto &t : threads) t.join();
     close_all();
     if (first_rc != RP_OK) return fail(first_rc, first_err);
@@ -831,9 +928,8 @@ int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, c
             stats->words_per_thread = s.words_per_thread;
             stats->ctas = s.ctas;
         }
+        stats->ms_load = t_loaded - t0;
         stats->ms_total = now_ms() - t0;
     }
     return RP_OK;
 }
-
-} // extern "C"
