@@ -89,6 +89,23 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic():
+    """DRAM bytes per paint_kernel launch from the latest committed `ncu --set full` summary (profiles/), or None."""
+    import glob
+    best = None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_config2_paint_*_ncu_summary.csv"))):
+        rd = wr = None
+        for line in open(p):
+            f = line.strip().split(",")
+            if f[0] == "dram__bytes_read.sum":
+                rd = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}.get(f[1], 1)
+            if f[0] == "dram__bytes_write.sum":
+                wr = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}.get(f[1], 1)
+        if rd is not None and wr is not None:
+            best = (rd + wr, os.path.basename(p))
+    return best
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -232,6 +249,8 @@ def main():
         def step():
             return chunk.paint_targets_device(0, N_HAP)
 
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         with torch.cuda.stream(stream):
             for _ in range(args.warmup):
                 flush.fill_(1)
@@ -239,8 +258,6 @@ def main():
             torch.cuda.synchronize(dev)
             if world > 1:
                 dist.barrier()
-            sampler = ClockSampler(local_rank)
-            sampler.start()
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
             t_wall0 = time.perf_counter()
             paint_ms, prep_ms, launches = [], [], 0
@@ -293,7 +310,8 @@ def main():
                            "timing": "torch.cuda.Event pairs on the stream the library launches on; max over ranks",
                            "team_threads": st["team_threads"], "words_per_thread": st["words_per_thread"], "ctas": st["ctas"]},
                 "roofline": {"bound": "fp32", "achieved": achieved / 1e12, "peak": mix / 1e12, "unit": "TFLOP/s",
-                             "frac": achieved / mix, "traffic": None,
+                             "frac": achieved / mix, "traffic": (ncu_traffic() or (None, None))[0],
+                             "traffic_source": (ncu_traffic() or (None, None))[1],
                              "kernel": "paint_kernel", "kernel_ms": kernel_ms, "prep_ms": sum(prep_ms) / len(prep_ms),
                              "algorithmic_ops": alg_ops, "executed_fp32_lane_ops": 6.0 * N_HAP * U,
                              "peak_source": "measured on this box: rp_peak_fp32 (packed add + predicated-mul mix, no memory)",
