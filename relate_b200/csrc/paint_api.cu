@@ -133,10 +133,10 @@ int plan_launch(const rp_chunk *c, LaunchPlan &lp)
     return RP_OK;
 }
 
-template <typename T, int WPT, bool MULTI>
+template <typename T, int WPT, bool MULTI, bool DENSE = false>
 int launch_paint_t(const rp_chunk *c, const rp::PaintParams &P, int threads, int &ctas)
 {
-    auto kern = rp::paint_kernel<T, WPT, MULTI>;
+    auto kern = rp::paint_kernel<T, WPT, MULTI, DENSE>;
     int occ = 0;
     RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
     if (occ < 1) return fail(RP_ECUDA, "paint kernel does not fit on an SM");
@@ -174,6 +174,8 @@ int launch_paint(const rp_chunk *c, rp::PaintParams &P, const LaunchPlan &lp, De
     if (lp.wpt == 1)
         return lp.multi ? launch_paint_t<float, 1, true>(c, P, lp.threads, ctas)
                         : launch_paint_t<float, 1, false>(c, P, lp.threads, ctas);
+    if (lp.multi && lp.threads <= 160 && c->tune.reserved[0] == 2) // opt-in: measured no faster than the 128-register variant
+        return launch_paint_t<float, 2, true, true>(c, P, lp.threads, ctas); // 96-register variant: more CTAs per SM
     return lp.multi ? launch_paint_t<float, 2, true>(c, P, lp.threads, ctas)
                     : launch_paint_t<float, 2, false>(c, P, lp.threads, ctas);
 }

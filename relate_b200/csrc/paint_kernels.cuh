@@ -382,18 +382,34 @@ template <typename T> __device__ __forceinline__ const PaintConsts<T> &paint_con
 template <> __device__ __forceinline__ const PaintConsts<float> &paint_consts<float>(const PaintParams &P) { return P.cf; }
 template <> __device__ __forceinline__ const PaintConsts<double> &paint_consts<double>(const PaintParams &P) { return P.cd; }
 
-// Launch geometry.  The team of T = blockDim.x threads owns a job's N-vector: thread t owns genotype words
-// j*T + t (j < WPT); a word's 32 haplotypes sit in 32 registers, rotated by rot = k & 31 so that the target
+// Launch geometry.  The team of T = blockDim.x threads owns a job's N-vector: thread t owns the WPT adjacent
+// genotype words t*WPT + j; a word's 32 haplotypes sit in 32 registers, rotated by rot = k & 31 so that the target
 // is slot 0 of its word.  Register budget: 32*WPT state registers (x2 for fp64) + ~30.
-template <typename T, int WPT, bool MULTI>
+// DENSE selects a tighter register cap for multi-warp teams of <= 160 threads with two words per thread
+// (96 registers -> 4 CTAs of 160 threads, or 7 of 96, per SM instead of 3 / 5).
+template <typename T, int WPT, bool MULTI, bool DENSE = false>
 struct PaintCfg {
     static constexpr int kStateRegs = 32 * WPT * (int)(sizeof(T) / 4);
     // register caps: multi-warp teams 80 (fp32, one word per thread: <=384 threads, 2 CTAs/SM), 128 (fp32, two
     // words: <=512 threads) or 168 (fp64: <=384 threads); single-warp teams 128 or 255
     static constexpr bool kF64 = sizeof(T) == 8;
-    static constexpr int kMaxThreads = MULTI ? ((kStateRegs <= 32 || kF64) ? 384 : 512) : 32;
-    static constexpr int kMinBlocks = MULTI ? (kStateRegs <= 32 ? 2 : 1) : (kStateRegs <= 32 ? 16 : 8);
+    static constexpr int kMaxThreads = MULTI ? (DENSE ? 160 : ((kStateRegs <= 32 || kF64) ? 384 : 512)) : 32;
+    static constexpr int kMinBlocks = MULTI ? (DENSE ? 4 : (kStateRegs <= 32 ? 2 : 1)) : (kStateRegs <= 32 ? 16 : 8);
 };
+
+template <int WPT> __device__ __forceinline__ void load_words(uint32_t (&w)[WPT], const char *p)
+{
+    if (WPT == 1) {
+        w[0] = *reinterpret_cast<const uint32_t *>(p);
+    } else if (WPT == 2) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(p);
+        w[0] = v.x;
+        w[WPT - 1] = v.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < WPT; j++) w[j] = reinterpret_cast<const uint32_t *>(p)[j];
+    }
+}
 
 __device__ __forceinline__ void opaque(float &x) { asm volatile("" : "+f"(x)); }
 __device__ __forceinline__ void opaque(double &x) { asm volatile("" : "+d"(x)); }
@@ -419,16 +435,18 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
     // rewrites P0-P6 four times per word, so a predicate cannot survive a step, and ptxas would otherwise
     // rematerialise pointers and masks from the constant bank every iteration.
     bool valid[WPT];
-    const char *gthr[WPT]; // this thread's word within a row (threads without a word read word 0 and ignore it)
-    T vmul[WPT];           // 1 for threads that own a word, 0 otherwise: R*vmul keeps an unused slot at exactly 0
+    T vmul[WPT];           // 1 for words this thread owns, 0 otherwise: R*vmul keeps an unused slot at exactly 0
 #pragma unroll
     for (int j = 0; j < WPT; j++) {
-        valid[j] = (j * TT + t) < P.nfw;
-        gthr[j] = reinterpret_cast<const char *>(P.G + (valid[j] ? j * TT + t : 0));
+        valid[j] = (t * WPT + j) < P.nfw;
         vmul[j] = valid[j] ? (T)1 : (T)0;
-        asm volatile("" : "+l"(gthr[j]));
         opaque(vmul[j]);
     }
+    // this thread's WPT adjacent words within a row: one (vector) load per visited site, 4*WPT bytes per lane,
+    // coalesced across the warp.  Rows are padded to 16 bytes and a word past the last full one is either the tail
+    // word or padding, so threads beyond the row's end read word 0 and ignore it.
+    const char *gthr = reinterpret_cast<const char *>(P.G + ((t * WPT + WPT - 1) < P.wps ? t * WPT : 0));
+    asm volatile("" : "+l"(gthr));
     const bool has_tail = P.tailn > 0;                 // kernel-uniform
     const bool tail_warp = has_tail && (warp == 0);
     const bool tail_lane = tail_warp && (lane < P.tailn);
@@ -460,7 +478,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         const int rot = k & 31, wk = k >> 5;
         bool own[WPT];
 #pragma unroll
-        for (int j = 0; j < WPT; j++) own[j] = (wk < P.nfw) && (j * TT + t == wk);
+        for (int j = 0; j < WPT; j++) own[j] = (wk < P.nfw) && (t * WPT + j == wk);
         const bool tail_live = tail_lane && !((wk == P.nfw) && (lane == rot)); // valid tail slot that is not the target
         T ownmul[WPT]; // 0 on the thread/word holding the target (slot 0 after rotation), else 1
 #pragma unroll
@@ -488,6 +506,9 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         // x <- (x + R) * (mis ? tau : 1);  returns the team-wide sum.  mis = target derived && reference
         // ancestral; tdm is all-ones when the target is derived at the site (always, except SNP 0 / L-1).
         auto step_local = [&](const uint32_t (&w)[WPT], uint32_t tw, uint32_t tdm, T R) -> T {
+            // partial sums: four independent chains when a thread owns one word, two when it owns two
+            // (register budget of the 96-register multi-warp variant)
+            constexpr int NACC = (WPT == 1) ? 4 : 2;
             V2 S0, S1, S2, S3;
 #pragma unroll
             for (int j = 0; j < WPT; j++) {
@@ -502,15 +523,17 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                     if (mw & (2u << (2 * e))) v.y *= tau;
                     if (e == 0) v.x *= ownmul[j];
                     a[j][e] = v;
-                    if (j == 0 && e < 4) { // the first four pairs seed the accumulators
-                        if (e == 0) S0 = v; else if (e == 1) S1 = v; else if (e == 2) S2 = v; else S3 = v;
-                    } else if ((e & 3) == 0) S0 = RT::add2(S0, v);
-                    else if ((e & 3) == 1) S1 = RT::add2(S1, v);
-                    else if ((e & 3) == 2) S2 = RT::add2(S2, v);
+                    const int ch = e % NACC;
+                    if (j == 0 && e < NACC) { // the first pairs seed the accumulators
+                        if (ch == 0) S0 = v; else if (ch == 1) S1 = v; else if (ch == 2) S2 = v; else S3 = v;
+                    } else if (ch == 0) S0 = RT::add2(S0, v);
+                    else if (ch == 1) S1 = RT::add2(S1, v);
+                    else if (ch == 2) S2 = RT::add2(S2, v);
                     else S3 = RT::add2(S3, v);
                 }
             }
-            S0 = RT::add2(RT::add2(S0, S1), RT::add2(S2, S3));
+            S0 = RT::add2(S0, S1);
+            if (NACC == 4) S0 = RT::add2(S0, RT::add2(S2, S3));
             T S = S0.x + S0.y;
             if (MULTI ? tail_warp : has_tail) {
                 T v = tl + R;
@@ -528,9 +551,22 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 T *part = s_part[parity];
                 if (lane == 0) part[warp] = S;
                 __syncthreads();
-                S = part[0];
-#pragma unroll 4
-                for (int ww = 1; ww < TW; ww++) S += part[ww];
+                if (sizeof(T) == 4) { // rows are zero beyond TW: whole float4s, fixed order in every thread
+                    const float4 *p4 = reinterpret_cast<const float4 *>(part);
+                    float4 v = p4[0];
+                    float acc = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+                    for (int i = 1; i < 4; i++) {
+                        if (4 * i < TW) {
+                            v = p4[i];
+                            acc += (v.x + v.y) + (v.z + v.w);
+                        }
+                    }
+                    S = (T)acc;
+                } else {
+                    S = part[0];
+                    for (int ww = 1; ww < TW; ww++) S += part[ww];
+                }
             }
             return S;
         };
@@ -541,7 +577,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 #pragma unroll
             for (int j = 0; j < WPT; j++) {
                 if (valid[j]) {
-                    const int n0 = (j * TT + t) * 32;
+                    const int n0 = (t * WPT + j) * 32;
 #pragma unroll
                     for (int e = 0; e < 16; e++) {
                         T vx = a[j][e].x + addR, vy = a[j][e].y + addR;
@@ -564,107 +600,51 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         const uint32_t td_first = ((P.G[(size_t)site_first * P.wps + wk] >> rot) & 1u) ? 0xffffffffu : 0u;
         const uint32_t td_last = ((P.G[(size_t)site_last * P.wps + wk] >> rot) & 1u) ? 0xffffffffu : 0u;
 
-        // ---- software pipeline -------------------------------------------------------------------
-        // At step p the team holds the genotype words of steps p and p+1, loads those of step p+2 (whose
-        // site index was loaded during step p-1) and the site index of step p+3.  Entries up to 3 past
-        // either end of the target's list are read and never used (the table is padded).
-        uint32_t wC[WPT], wN[WPT], wNN[WPT], twC = 0, twN = 0, twNN = 0;
-        {
-            const int s1 = pe[ES].site; // m >= 1
-#pragma unroll
-            for (int j = 0; j < WPT; j++) {
-                wC[j] = *reinterpret_cast<const uint32_t *>(gthr[j] + (size_t)(unsigned)site_first * rowbytes);
-                wN[j] = *reinterpret_cast<const uint32_t *>(gthr[j] + (size_t)(unsigned)s1 * rowbytes);
-            }
-            if (MULTI ? tail_warp : has_tail) {
-                twC = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)site_first * rowbytes);
-                twN = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)s1 * rowbytes);
-            }
-        }
-        int sNN = pe[2 * ES].site, sNNN = 0; // sites of steps p+2, p+3
-        T cC = (T)pe[0].c, cNext = (T)0;     // c of steps p, p+1
-        const Ent *pf = pe + 3 * ES;         // entry of step p+3
-        auto prefetch = [&]() {
-#pragma unroll
-            for (int j = 0; j < WPT; j++)
-                wNN[j] = *reinterpret_cast<const uint32_t *>(gthr[j] + (size_t)(unsigned)sNN * rowbytes);
-            if (MULTI ? tail_warp : has_tail) twNN = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)sNN * rowbytes);
-            sNNN = pf->site;
-            cNext = (T)(pf - 2 * ES)->c;
-        };
-        auto rotate = [&]() {
-#pragma unroll
-            for (int j = 0; j < WPT; j++) { wC[j] = wN[j]; wN[j] = wNN[j]; }
-            twC = twN; twN = twNN;
-            sNN = sNNN;
-            cC = cNext;
-            pf += ES;
-        };
+        // ---- pipeline state ---------------------------------------------------------------------------
+        // Two register sets (A/B) alternate between consecutive steps, so nothing is moved between steps:
+        // while step p computes from set X, the genotype words of step p+1 are loaded into set Y (their site
+        // index was loaded during step p-1) together with c_{p+1} and the site index of step p+2.
+        // Entries up to 2 past either end of the target's list are read and never used (the table is padded).
+        uint32_t wA[WPT], wB[WPT], twA = 0, twB = 0;
+        int sA, sB;   // site index whose words go INTO set A / B next
+        T cA, cB;     // c of the step that computes from set A / B
+        load_words(wA, gthr + (size_t)(unsigned)site_first * rowbytes);
+        if (MULTI ? tail_warp : has_tail) twA = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)site_first * rowbytes);
+        cA = (T)pe[0].c;
+        sB = pe[ES].site;  // step 1's words go into set B during step 0
+        sA = 0;
+        cB = (T)0;
 
-        // ---- step 0: x = (0 + R0) * m.  No rescale test at the first site (:206-263, :401-458). ----
+        T R = DIR ? (T)1 : K.prior_n; // step 0 is x = (0 + R0) * m
+        uint32_t tdm = td_first;
+        int q1 = q;
+        bool post = false;
+
         if (DIR) { // beta at SNP L-1 is all ones, the target included (:413-418, :433-448)
-            int q1 = q;
-            while (q1 < P.W && bpos(q1) == 0) q1++;
-            for (int qq = q; qq < q1; qq++) {
+            int qe = q;
+            while (qe < P.W && bpos(qe) == 0) qe++;
+            for (int qq = q; qq < qe; qq++) {
                 const int w = P.W - 1 - qq;
                 store_vec(outv + (size_t)w * P.N, (T)0, true);
                 if (t == 0) outl[w] = (float)lsb[w];
             }
-            q = q1;
+            q = qe;
         }
-        T R;
-        {
-            const T Sl = step_local(wC, twC, td_first, DIR ? (T)1 : K.prior_n);
-            const T c0 = cC;
-            prefetch();
-            rotate();
-            R = reduce(Sl, 0) * c0;
-        }
-
-        // next event: a stepping-stone store (forward: after step bpos, i.e. at the top of step bpos+1;
-        // backward: at step bpos) or the last step (target allele mask)
+        // pev = the step before which the rare-path handler must run: a stepping-stone store (forward: alpha
+        // after step bpos, i.e. before step bpos+1; backward: beta at step bpos), the last step (target allele
+        // mask), or the step after a backward store (its finalisation)
         auto next_event = [&]() -> int {
             const int nb = q < P.W ? bpos(q) + (DIR ? 0 : 1) : 0x7fffffff;
             return nb < m ? nb : m;
         };
-        int pev = next_event();
-        uint32_t tdm = 0xffffffffu;
+        int pev = 1; // the handler always runs after step 0 (it switches the allele mask to all-ones)
 
-        for (int p = 1; p <= m; p++) {
-            bool post = false; // backward: stepping stone(s) of this step to finalise after the chain
-            int q1 = q;
-            if (__builtin_expect(p == pev, 0)) { // rare
-                if (p == m) tdm = td_last;
-                const int bp_now = q < P.W ? bpos(q) : -1;
-                if (bp_now == (DIR ? p : p - 1)) {
-                    while (q1 < P.W && bpos(q1) == bp_now) q1++;
-                    if (!DIR) { // alpha after step p-1, post-rescale (:354-374)
-                        for (int qq = q; qq < q1; qq++) {
-                            store_vec(outv + (size_t)qq * P.N, (T)0, false);
-                            if (t == 0) outl[qq] = (float)(lsb[qq] + lsr);
-                        }
-                        q = q1;
-                    } else { // beta of this step is b = g_old + R' before the emission multiply (:481-488)
-                        post = true;
-                        if (sizeof(T) == 8) store_vec(scratch, R, false);
-                        else for (int qq = q; qq < q1; qq++) store_vec(outv + (size_t)(P.W - 1 - qq) * P.N, R, false);
-                    }
-                }
-                if (!post) pev = (p == m) ? 0x7fffffff : next_event();
-            }
-
-            // local update and partial sum; then the loads and pipeline rotation for later steps are issued
-            // in the shadow of the reduction's shuffle latency
-            const T Sl = step_local(wC, twC, tdm, R);
-            const T cthis = cC;
-            prefetch();
-            rotate();
-            const T S = reduce(Sl, p & 1);
-
-            // scalar chain: rescale test, next R (:331-352, :536-556)
+        // rare path, run between step p and step p+1
+        auto handler = [&](int p, T S, T cthis) {
             const T B = chk * S;
             bool rescaled = false;
-            if (__builtin_expect(B < K.lower || B > K.upper, 0)) { // about one step in 50 on coalescent data
+            if (p == 0) tdm = 0xffffffffu; // steps 1..m-1 visit sites where the target is derived
+            if (p != 0 && (B < K.lower || B > K.upper)) { // :334-347, :538-551; no test at the first site
                 rescaled = true;
                 if (sizeof(T) == 4) { // fp32 state: one reciprocal, then multiplies (<= 1 ulp from the division)
                     const T inv = (T)1 / B;
@@ -673,7 +653,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 #pragma unroll
                         for (int e = 0; e < 16; e++) { a[j][e].x *= inv; a[j][e].y *= inv; }
                     tl *= inv;
-                } else { // fp64 verification mode divides, as the reference does (:338-342, :543-547)
+                } else { // fp64 verification mode divides, as the reference does
 #pragma unroll
                     for (int j = 0; j < WPT; j++)
 #pragma unroll
@@ -682,11 +662,8 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 }
                 lsr += DIR ? (double)fast_log_dev((float)B) : log((double)B);
                 R = resc_R * cthis;
-            } else {
-                R = S * cthis;
             }
-
-            if (DIR && __builtin_expect(post, 0)) { // finalise the backward stepping stone(s): divide by B if this step rescaled
+            if (DIR && post) { // finalise the backward stepping stone(s) of step p: divide by B if it rescaled
                 for (int qq = q; qq < q1; qq++) {
                     const int w = P.W - 1 - qq;
                     float *o = outv + (size_t)w * P.N;
@@ -695,7 +672,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 #pragma unroll
                         for (int j = 0; j < WPT; j++) {
                             if (valid[j]) {
-                                const int n0 = (j * TT + t) * 32;
+                                const int n0 = (t * WPT + j) * 32;
                                 for (int e = 0; e < 32; e++) {
                                     T v = src[n0 + e];
                                     if (rescaled) v /= B;
@@ -712,8 +689,55 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                     if (t == 0) outl[w] = (float)(lsb[w] + lsr);
                 }
                 q = q1;
-                pev = (p == m) ? 0x7fffffff : next_event();
+                post = false;
             }
+            const int pn = p + 1; // events of the coming step
+            if (pn > m) { pev = 0x7fffffff; return; }
+            pev = next_event();
+            if (pev == pn) {
+                if (pn == m) tdm = td_last;
+                const int bp_now = q < P.W ? bpos(q) : -1;
+                if (bp_now == (DIR ? pn : pn - 1)) {
+                    q1 = q;
+                    while (q1 < P.W && bpos(q1) == bp_now) q1++;
+                    if (!DIR) { // alpha after step p, post-rescale (:354-374)
+                        for (int qq = q; qq < q1; qq++) {
+                            store_vec(outv + (size_t)qq * P.N, (T)0, false);
+                            if (t == 0) outl[qq] = (float)(lsb[qq] + lsr);
+                        }
+                        q = q1;
+                    } else { // beta of step pn is b = g_old + R' before the emission multiply (:481-488)
+                        post = true;
+                        if (sizeof(T) == 8) store_vec(scratch, R, false);
+                        else for (int qq = q; qq < q1; qq++) store_vec(outv + (size_t)(P.W - 1 - qq) * P.N, R, false);
+                    }
+                }
+                pev = post ? pn + 1 : (pn == m ? 0x7fffffff : next_event());
+                if (!post && pev == pn) pev = pn + 1; // unreachable guard: never re-fire for the same step
+            }
+        };
+
+        // one step computing from set X while filling set Y
+        auto do_step = [&](int p, uint32_t (&wX)[WPT], uint32_t &twX, T &cX, int &sX,
+                           uint32_t (&wY)[WPT], uint32_t &twY, T &cY, int &sY) {
+            // loads for later steps first: words of step p+1 into Y, c_{p+1}, site of step p+2 (-> X's next fill)
+            load_words(wY, gthr + (size_t)(unsigned)sY * rowbytes);
+            if (MULTI ? tail_warp : has_tail) twY = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)sY * rowbytes);
+            cY = (T)pe[(p + 1) * ES].c;
+            sX = pe[(p + 2) * ES].site;
+            const T Sl = step_local(wX, twX, tdm, R);
+            const T S = reduce(Sl, p & 1);
+            R = S * cX;
+            const T B = chk * S;
+            const bool oob = (B < K.lower) || (B > K.upper);
+            if (__builtin_expect(oob || (p + 1 == pev), 0)) handler(p, S, cX);
+        };
+
+        // steps 0..m, two per iteration (even steps compute from set A, odd ones from set B)
+        for (int p = 0; p <= m; p += 2) {
+            do_step(p, wA, twA, cA, sA, wB, twB, cB, sB);
+            if (p + 1 > m) break;
+            do_step(p + 1, wB, twB, cB, sB, wA, twA, cA, sA);
         }
 
         if (!DIR) { // alpha stepping stones at the last visited site
@@ -726,12 +750,16 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
     }
 }
 
-template <typename T, int WPT, bool MULTI>
-__global__ void __launch_bounds__(PaintCfg<T, WPT, MULTI>::kMaxThreads, PaintCfg<T, WPT, MULTI>::kMinBlocks)
+template <typename T, int WPT, bool MULTI, bool DENSE = false>
+__global__ void __launch_bounds__(PaintCfg<T, WPT, MULTI, DENSE>::kMaxThreads, PaintCfg<T, WPT, MULTI, DENSE>::kMinBlocks)
 paint_kernel(const PaintParams P)
 {
     __shared__ int s_job;
-    __shared__ T s_part[2][32];
+    __shared__ __align__(16) T s_part[2][32];
+    if (MULTI) { // partial-sum rows are read as whole vectors: zero the slots no warp writes
+        if (threadIdx.x < 64) (&s_part[0][0])[threadIdx.x] = (T)0;
+        __syncthreads();
+    }
     // even CTAs walk the site lists forwards (alpha), odd CTAs backwards (beta): two instantiations of one loop
     if (blockIdx.x & 1) paint_jobs<T, WPT, MULTI, 1>(P, &s_job, s_part);
     else paint_jobs<T, WPT, MULTI, 0>(P, &s_job, s_part);
