@@ -369,7 +369,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
         rp::fill_sites_kernel<<<gw, th, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->off.as<long long>(), e);
         rp::boundaries_kernel<<<gb, th, 0, s>>>(e, c->off.as<long long>(), nt, W, c->wbdev.as<int>(), c->ia.as<int>(),
                                                 c->ib.as<int>(), c->sb.as<int>(), c->se.as<int>());
-        rp::tables_kernel<<<gw, th, 0, s>>>(e, c->off.as<long long>(), nt, c->L, W, c->r.as<double>(),
+        rp::tables_kernel<rp::EntD, 16><<<gw, th, 0, s>>>(e, c->off.as<long long>(), nt, c->L, W, c->r.as<double>(),
                                             c->Phi.as<double>(), c->Plo.as<double>(), tc, c->ia.as<int>(),
                                             c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>());
     } else {
@@ -377,7 +377,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
         rp::fill_sites_kernel<<<gw, th, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->off.as<long long>(), e);
         rp::boundaries_kernel<<<gb, th, 0, s>>>(e, c->off.as<long long>(), nt, W, c->wbdev.as<int>(), c->ia.as<int>(),
                                                 c->ib.as<int>(), c->sb.as<int>(), c->se.as<int>());
-        rp::tables_kernel<<<gw, th, 0, s>>>(e, c->off.as<long long>(), nt, c->L, W, c->r.as<double>(),
+        rp::tables_kernel<rp::EntF, 0><<<gw, th, 0, s>>>(e, c->off.as<long long>(), nt, c->L, W, c->r.as<double>(),
                                             c->Phi.as<double>(), c->Plo.as<double>(), tc, c->ia.as<int>(),
                                             c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>());
     }

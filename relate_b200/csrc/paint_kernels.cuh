@@ -260,7 +260,9 @@ struct TableConsts {
     double log_ntheta, log_small, Nm1;
 };
 
-template <typename ENT>
+// SEQ_GAP: gaps of at most this many SNPs are summed in the reference's order (fp64 verification mode: 16);
+// the fp32 path takes every gap from the double-double prefix (SEQ_GAP = 0), which is exact to ~1e-30.
+template <typename ENT, int SEQ_GAP>
 __global__ void tables_kernel(ENT *__restrict__ ent, const long long *__restrict__ off, int nt, int L, int W,
                               const double *__restrict__ r, const double *__restrict__ Phi,
                               const double *__restrict__ Plo, TableConsts tc, const int *__restrict__ ia,
@@ -275,47 +277,59 @@ __global__ void tables_kernel(ENT *__restrict__ ent, const long long *__restrict
     int qa = 0, qb = 0;
     // windows whose forward boundary is index 0 have an empty sum
     while (qa < W && ja[qa] == 0) { if (lane == 0) oa[qa] = 0.0; qa++; }
+    int nexta = qa < W ? ja[qa] - 1 : 0x7fffffff, nextb = jb[0];
     double carry = 0.0;
-    for (int i0 = 0; i0 < D; i0 += 32) {
-        const int i = i0 + lane;
-        double nor = 0.0;
-        if (i < D) {
-            const int a = e[i].site;
-            const int b = (i + 1 < D) ? e[i + 1].site : L;
-            double x;
-            if (b - a <= 16) {
-                x = r[a];
-                for (int s = a + 1; s < b; s++) x += r[s];
-            } else {
-                x = (Phi[b] - Phi[a]) + (Plo[b] - Plo[a]);
-            }
-            nor = -x + tc.log_ntheta;
-            double rho = 1.0 - exp(-x);
-            if (rho > 0.99) {
-                rho = 0.99;
-                nor = tc.log_small + tc.log_ntheta;
-            }
-            e[i].set_c(rho / ((1.0 - rho) * tc.Nm1));
-        }
-        double incl = nor;
+    constexpr int TILES = 4; // independent 32-entry tiles per iteration (latency hiding: one warp per target)
+    for (int i0 = 0; i0 < D; i0 += 32 * TILES) {
+        double nor[TILES];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            double v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+        for (int u = 0; u < TILES; u++) {
+            const int i = i0 + 32 * u + lane;
+            nor[u] = 0.0;
+            if (i < D) {
+                const int a = e[i].site;
+                const int b = (i + 1 < D) ? e[i + 1].site : L;
+                double x;
+                if (SEQ_GAP > 0 && b - a <= SEQ_GAP) {
+                    x = r[a];
+                    for (int s = a + 1; s < b; s++) x += r[s];
+                } else {
+                    x = (Phi[b] - Phi[a]) + (Plo[b] - Plo[a]);
+                }
+                nor[u] = -x + tc.log_ntheta;
+                double rho = 1.0 - exp(-x);
+                if (rho > 0.99) {
+                    rho = 0.99;
+                    nor[u] = tc.log_small + tc.log_ntheta;
+                }
+                e[i].set_c(rho / ((1.0 - rho) * tc.Nm1));
+            }
         }
-        incl += carry; // cum_i = sum_{j<=i} nor_j
-        // forward bases need cum_{ia-1}; backward ones cum_{ib} (finalised below)
-        while (qa < W && ja[qa] - 1 < i0 + 32) {
-            double v = __shfl_sync(0xffffffffu, incl, ja[qa] - 1 - i0);
-            if (lane == 0) oa[qa] = v;
-            qa++;
+#pragma unroll
+        for (int u = 0; u < TILES; u++) {
+            const int t0 = i0 + 32 * u;
+            double incl = nor[u];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                double v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            incl += carry; // cum_i = sum_{j<=i} nor_j
+            // forward bases need cum_{ia-1}; backward ones cum_{ib} (finalised below)
+            while (nexta < t0 + 32) {
+                double v = __shfl_sync(0xffffffffu, incl, nexta - t0);
+                if (lane == 0) oa[qa] = v;
+                qa++;
+                nexta = qa < W ? ja[qa] - 1 : 0x7fffffff;
+            }
+            while (nextb < t0 + 32) {
+                double v = __shfl_sync(0xffffffffu, incl, nextb - t0);
+                if (lane == 0) ob[qb] = v; // provisional: cum_{ib}
+                qb++;
+                nextb = qb < W ? jb[qb] : 0x7fffffff;
+            }
+            carry = __shfl_sync(0xffffffffu, incl, 31);
         }
-        while (qb < W && jb[qb] < i0 + 32) {
-            double v = __shfl_sync(0xffffffffu, incl, jb[qb] - i0);
-            if (lane == 0) ob[qb] = v; // provisional: cum_{ib}
-            qb++;
-        }
-        carry = __shfl_sync(0xffffffffu, incl, 31);
     }
     // carry == cum_{m}; lsB = norm + (cum_m - cum_ib)
     const double norm = log(tc.Nm1) - (double)D * tc.log_ntheta;
