@@ -355,3 +355,28 @@ def test_multi_gpu_paint_chunk_matches_single(tmp_path):
     for w in range(4):
         assert filecmp.cmp(str(tmp_path / "one" / "chunk_0" / "paint" / f"relate_{w}.bin"),
                            str(tmp_path / "two" / "chunk_0" / "paint" / f"relate_{w}.bin"), shallow=False)
+
+
+# ---- BASELINE.json configs[3] shape: N=10,000 x L=100,000 (1000G-scale sample count), one chunk ----------------
+def test_config4_shape_subset_of_targets():
+    """Full-size inputs (1 GB of genotype chars -> 125 MB of bits in HBM, --memory 100 window plan), a spread of
+    targets painted; oracle spot-check on two of them; sharding invariance across separate calls."""
+    N, L = 10000, 100000
+    hap, bp = synth.block_kingman(N, L, 3)
+    r = chunkio.r_from_rpos(chunkio.uniform_map_rpos(bp))
+    wb = chunkio.window_boundaries(hap, 100.0)
+    assert 30 <= len(wb) - 1 <= 60
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        assert c.hbm_bytes < 400e6
+        a = c.paint_targets(0, 48)
+        b = c.paint_targets(9990, 10000)
+        a2 = c.paint_targets(16, 32)
+    assert np.array_equal(a.alpha[16:32], a2.alpha) and np.array_equal(a.beta[16:32], a2.beta)
+    for g, k in ((a, 7), (b, 9999)):
+        i = k - g.k_begin
+        o = oracle.paint_targets(hap, r, wb, THETA, k, k + 1)
+        sub = capi.SteppingStones(k, g.alpha[i:i + 1], g.beta[i:i + 1], g.ls_alpha[i:i + 1], g.ls_beta[i:i + 1],
+                                  g.site_begin[i:i + 1], g.site_end[i:i + 1], {})
+        compare(sub, o, ls_atol=5e-3)
+    assert np.isfinite(a.alpha).all() and np.isfinite(b.beta).all()
+    assert a.stats["words_per_thread"] == 2 and a.stats["team_threads"] == 160
