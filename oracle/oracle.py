@@ -103,3 +103,27 @@ def have_reference() -> bool:
 def run_reference(args, cwd, check=True):
     """Run the unmodified reference binary (oracle/_ref/Relate) with the given CLI args."""
     return subprocess.run([REF_RELATE] + list(args), cwd=cwd, capture_output=True, text=True, check=check)
+
+
+def window_distances(out_dir: str, chunk: int, section: int, stride: int, painting: str | None, out_path: str) -> None:
+    """Oracle restatement of RePaintSection + GetMatrix over one window; same output format as oracle/_ref/dlens."""
+    l = lib()
+    l.ro_window_distances.restype = C.c_int
+    l.ro_window_distances.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+    rc = l.ro_window_distances(out_dir.encode(), chunk, section, stride, (painting or "-").encode(), out_path.encode())
+    if rc:
+        raise RuntimeError(f"ro_window_distances failed: {rc}")
+
+
+def read_distances(path: str) -> dict:
+    """-> {snp: float32 [N,N]} from a dlens / window_distances file (plain or .gz)."""
+    import gzip
+    import struct
+    buf = (gzip.open(path, "rb") if path.endswith(".gz") else open(path, "rb")).read()
+    N, cnt = struct.unpack_from("<ii", buf, 0)
+    off, out = 8, {}
+    for _ in range(cnt):
+        (snp,) = struct.unpack_from("<i", buf, off)
+        out[snp] = np.frombuffer(buf, "<f4", N * N, off + 4).reshape(N, N)
+        off += 4 + 4 * N * N
+    return out

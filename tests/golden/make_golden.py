@@ -9,7 +9,9 @@ Fixtures (all produced by the UNMODIFIED reference binary oracle/_ref/Relate):
                      the reference's paint files with --painting 0.001,1 (paint_ref/relate_<w>.bin) and the
                      md5 of the .anc/.mut files the reference's BuildTopology --seed 1 derives from them.
   synth_n96/         a 96-haplotype x 700-SNP synthetic chunk (this repo's generator, seed 5), 5 windows,
-                     painted by the reference with --painting 0.001,1 and without the flag.
+                     painted by the reference with --painting 0.001,1 and without the flag; dlens_ref/ holds the
+                     distance matrices the reference's DistanceMeasure::GetMatrix derives from those paint files
+                     (windows 1 and 3, every 61st SNP), written by oracle/_ref/dlens.
 """
 import gzip
 import hashlib
@@ -42,7 +44,7 @@ def pack_chunk(src_dir, c, dst):
     os.makedirs(dst, exist_ok=True)
     shutil.copy(os.path.join(src_dir, f"parameters_c{c}.bin"), os.path.join(dst, "parameters_c0.bin"))
     for e in CHUNK_EXT:
-        with open(os.path.join(src_dir, f"chunk_{c}.{e}"), "rb") as f, gzip.open(os.path.join(dst, f"chunk_0.{e}.gz"), "wb", 9) as g:
+        with open(os.path.join(src_dir, f"chunk_{c}.{e}"), "rb") as f, gzip.GzipFile(os.path.join(dst, f"chunk_0.{e}.gz"), "wb", 9, mtime=0) as g:
             g.write(f.read())
 
 
@@ -100,6 +102,15 @@ def main():
         os.makedirs(os.path.join(dst, tag))
         for w in range(5):
             shutil.copy(os.path.join(w2, "sy", "chunk_0", "paint", f"relate_{w}.bin"), os.path.join(dst, tag))
+    # d_ij lens outputs of the reference (oracle/_ref/dlens drives the reference's GetMatrix) on its own paint files
+    shutil.rmtree(os.path.join(w2, "sy", "chunk_0"), ignore_errors=True)
+    run(["--mode", "Paint", "--chunk_index", "0", "-o", "sy", "--painting", "0.001,1"], w2)
+    os.makedirs(os.path.join(dst, "dlens_ref"))
+    for sec in (1, 3):
+        out = os.path.join(w2, f"d_{sec}.bin")
+        subprocess.run([os.path.join(ROOT, "oracle", "_ref", "dlens"), "sy", "0", str(sec), "61", "0.001,1", out], cwd=w2, check=True)
+        with open(out, "rb") as f, gzip.GzipFile(os.path.join(dst, "dlens_ref", f"d_{sec}.bin.gz"), "wb", 9, mtime=0) as g:
+            g.write(f.read())
     shutil.rmtree(tmp)
     total = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(HERE) for f in fs)
     print("golden fixtures written,", total, "bytes")
