@@ -126,6 +126,23 @@ int rp_paint_from_host(int device, int N, int L, const char *hap, const double *
 int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
                    int n_devices, unsigned flags, rp_stats *stats);
 
+/* ---- window repaint + distance matrices (consumer side, SURVEY.md 8 "next" row f1) ------------------
+ *   rp_window_open      <- FastPainting::RePaintSection for every target     src/fast_painting.cpp:620-1092
+ *                          (as DistanceMeasure::GetTopologyWithRepaint drives it, src/anc_builder.cpp:48-106)
+ *   rp_window_distance  <- DistanceMeasure::GetMatrix(snp)                   src/anc_builder.cpp:108-207
+ * The posterior rows of the whole window stay in HBM; each distance call returns the N x N float matrix d for
+ * one SNP of the window (row n = "n painted against everyone", diagonal 0, row minimum subtracted). */
+typedef struct rp_window rp_window;
+/* alpha, beta: float [N][N] = the DECODED stepping stones of window w (what ReadFromFile yields) for targets
+ * 0..N-1; ls_alpha, ls_beta: float [N]; rpos: double [L+1] (chunk_<c>.rpos). */
+int rp_window_open(rp_chunk *c, int w, const float *alpha, const float *beta, const float *ls_alpha,
+                   const float *ls_beta, const double *rpos, rp_window **out, rp_stats *stats);
+/* Same, reading <out_dir>/chunk_<c>/paint/relate_<w>.bin and chunk_<c>.rpos. */
+int rp_window_open_files(rp_chunk *c, const char *out_dir, int chunk_index, int w, rp_window **out, rp_stats *stats);
+int rp_window_distance(rp_window *win, int snp, float *d);
+long long rp_window_rows(const rp_window *win);
+void rp_window_close(rp_window *win);
+
 /* rp_paint_chunk parks device buffers, pinned staging and streams per device between calls; this frees them. */
 void rp_release_cache(void);
 

@@ -68,6 +68,11 @@ SYMBOLS = {
                                      C.POINTER(RpTune), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(RpStats)]),
     "rp_paint_chunk": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, _P, C.c_int, C.c_uint, C.POINTER(RpStats)]),
     "rp_release_cache": (None, []),
+    "rp_window_open": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(RpStats)]),
+    "rp_window_open_files": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(RpStats)]),
+    "rp_window_distance": (C.c_int, [_P, C.c_int, _P]),
+    "rp_window_rows": (C.c_longlong, [_P]),
+    "rp_window_close": (None, [_P]),
     "rp_rle_encode": (C.c_int, [_P, C.c_int, _P, _P]),
     "rp_fast_log_device": (C.c_int, [C.c_int, _P, _P, C.c_int]),
     "rp_debug_pack": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int), _P, C.POINTER(C.c_int)]),
@@ -193,6 +198,45 @@ class DeviceChunk:
             self.close()
         except Exception:
             pass
+
+
+class Window:
+    """Posterior rows of one window resident in HBM (``rp_window``): the GPU side of RePaintSection + GetMatrix."""
+
+    def __init__(self, chunk: DeviceChunk, handle, stats):
+        self._c, self._h, self.stats = chunk, handle, stats
+        self.rows = lib().rp_window_rows(handle)
+
+    @classmethod
+    def open_files(cls, chunk: DeviceChunk, out_dir: str, chunk_index: int, w: int) -> "Window":
+        h, st = C.c_void_p(), RpStats()
+        check(lib().rp_window_open_files(chunk._h, out_dir.encode(), chunk_index, w, C.byref(h), C.byref(st)))
+        return cls(chunk, h, st.as_dict())
+
+    @classmethod
+    def open(cls, chunk: DeviceChunk, w: int, alpha, beta, ls_alpha, ls_beta, rpos) -> "Window":
+        arrs = [np.ascontiguousarray(alpha, np.float32), np.ascontiguousarray(beta, np.float32),
+                np.ascontiguousarray(ls_alpha, np.float32), np.ascontiguousarray(ls_beta, np.float32),
+                np.ascontiguousarray(rpos, np.float64)]
+        h, st = C.c_void_p(), RpStats()
+        check(lib().rp_window_open(chunk._h, w, *[_ptr(a) for a in arrs], C.byref(h), C.byref(st)))
+        return cls(chunk, h, st.as_dict())
+
+    def distance(self, snp: int) -> np.ndarray:
+        d = np.empty((self._c.N, self._c.N), np.float32)
+        check(lib().rp_window_distance(self._h, snp, _ptr(d)))
+        return d
+
+    def close(self) -> None:
+        if self._h:
+            lib().rp_window_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def paint_from_host(hap, r, wb, theta=0.001, device=0, fp64=False, k_begin=0, k_end=None, out=None,

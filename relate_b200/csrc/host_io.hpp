@@ -149,4 +149,42 @@ inline void append_record(std::vector<char> &out, const float *v, int n, int sit
     memcpy(p + 28 + (size_t)4 * k, lens.data(), (size_t)4 * k);
 }
 
+// Reads chunk_<c>/paint/relate_<w>.bin into dense [N][N] alpha/beta (run heads expanded, as
+// CollapsedMatrix<float>::ReadFromFile does, collapsed_matrix.hpp:268-296) and the per-target log-scales.
+inline std::string decode_paint_file(const std::string &path, int N, int want_start, int want_end, float *alpha,
+                                     float *beta, float *ls_alpha, float *ls_beta)
+{
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp) return "cannot open " + path;
+    std::vector<float> vals;
+    std::vector<int> lens;
+    auto rec = [&](float *dst, float *ls) -> bool {
+        uint64_t one = 0, sub = 0;
+        int site = 0, k = 0;
+        if (fread(&one, 8, 1, fp) != 1 || fread(&sub, 8, 1, fp) != 1 || one != 1 || (int)sub != N) return false;
+        if (fread(&site, 4, 1, fp) != 1 || fread(ls, 4, 1, fp) != 1 || fread(&k, 4, 1, fp) != 1 || k < 1 || k > N) return false;
+        vals.resize(k);
+        lens.resize(k);
+        if (fread(vals.data(), 4, k, fp) != (size_t)k || fread(lens.data(), 4, k, fp) != (size_t)k) return false;
+        int i = 0;
+        for (int j = 0; j < k; j++)
+            for (int t = 0; t < lens[j]; t++) {
+                if (i >= N) return false;
+                dst[i++] = vals[j];
+            }
+        return i == N;
+    };
+    for (int n = 0; n < N; n++) {
+        int a = 0, b = 0;
+        bool ok = fread(&a, 4, 1, fp) == 1 && fread(&b, 4, 1, fp) == 1 && a == want_start && b == want_end &&
+                  rec(alpha + (size_t)n * N, ls_alpha + n) && rec(beta + (size_t)n * N, ls_beta + n);
+        if (!ok) {
+            fclose(fp);
+            return "malformed record for target " + std::to_string(n) + " in " + path;
+        }
+    }
+    fclose(fp);
+    return "";
+}
+
 } // namespace rp

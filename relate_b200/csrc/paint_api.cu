@@ -97,7 +97,7 @@ struct rp_chunk {
     // resident
     DevBuf G, GT, r, Phi, Plo, wbdev, chars;
     // per-paint work buffers (grown on demand, reused)
-    DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch;
+    DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch, nor;
     long long *h_total = nullptr; // pinned
     cudaStream_t stream = nullptr;       // the stream every copy and kernel of this chunk is issued on
     cudaStream_t own_stream = nullptr;   // created by the library; `stream` may be replaced by a caller's
@@ -314,7 +314,7 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
 }
 
 // Runs prep + paint for targets [k0,k1) on the chunk's stream; results stay in c->alpha etc.
-int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
+int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = true, bool want_nor = false)
 {
     if (!c) return fail(RP_EINVAL, "null chunk");
     if (k0 < 0 || k1 > c->N || k0 >= k1) return fail(RP_EINVAL, "bad target range");
@@ -334,8 +334,10 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
     RP_TRY(c->se.ensure(nw * 4));
     RP_TRY(c->lsa.ensure(nw * 4));
     RP_TRY(c->lsb.ensure(nw * 4));
-    RP_TRY(c->alpha.ensure(nw * N * 4));
-    RP_TRY(c->beta.ensure(nw * N * 4));
+    if (run_paint) {
+        RP_TRY(c->alpha.ensure(nw * N * 4));
+        RP_TRY(c->beta.ensure(nw * N * 4));
+    }
     RP_TRY(c->queue.ensure(8));
 
     cudaStream_t s = c->stream;
@@ -357,6 +359,11 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
     RP_TRY(c->ent.ensure(((size_t)U + 2 * pad) * entsz));
     RP_CUDA(cudaMemsetAsync(c->ent.p, 0, pad * entsz, s));
     RP_CUDA(cudaMemsetAsync(c->ent.as<char>() + (pad + (size_t)U) * entsz, 0, pad * entsz, s));
+    double *nor_out = nullptr;
+    if (want_nor) {
+        RP_TRY(c->nor.ensure((size_t)U * 8));
+        nor_out = c->nor.as<double>();
+    }
 
     rp::TableConsts tc;
     const double ntheta = 1.0 - c->theta;
@@ -371,7 +378,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
                                                 c->ib.as<int>(), c->sb.as<int>(), c->se.as<int>());
         rp::tables_kernel<rp::EntD, 16><<<gw, th, 0, s>>>(e, c->off.as<long long>(), nt, c->L, W, c->r.as<double>(),
                                             c->Phi.as<double>(), c->Plo.as<double>(), tc, c->ia.as<int>(),
-                                            c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>());
+                                            c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>(), nor_out);
     } else {
         auto *e = c->ent.as<rp::EntF>() + pad;
         rp::fill_sites_kernel<<<gw, th, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->off.as<long long>(), e);
@@ -379,12 +386,23 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st)
                                                 c->ib.as<int>(), c->sb.as<int>(), c->se.as<int>());
         rp::tables_kernel<rp::EntF, 0><<<gw, th, 0, s>>>(e, c->off.as<long long>(), nt, c->L, W, c->r.as<double>(),
                                             c->Phi.as<double>(), c->Plo.as<double>(), tc, c->ia.as<int>(),
-                                            c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>());
+                                            c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>(), nor_out);
     }
     RP_CUDA(cudaGetLastError());
     launches += 3;
     RP_CUDA(cudaMemsetAsync(c->queue.p, 0, 8, s));
     RP_CUDA(cudaEventRecord(c->ev[1], s));
+    if (!run_paint) { // site tables only (the window repaint builds on them)
+        RP_CUDA(cudaStreamSynchronize(s));
+        if (st) {
+            float a = 0;
+            cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+            st->ms_prep += a;
+            st->sites += U;
+            st->launches += launches;
+        }
+        return RP_OK;
+    }
 
     rp::PaintParams P{};
     P.G = c->G.as<uint32_t>();
@@ -555,7 +573,7 @@ void rp_chunk_free(rp_chunk *c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
-                      &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch})
+                      &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch, &c->nor})
         b->release();
     if (c->h_total) cudaFreeHost(c->h_total);
     for (auto &e : c->ev)
@@ -684,6 +702,179 @@ int rp_debug_pack(int device, int N, int L, const char *hap, uint32_t *snp_major
     rp_chunk_free(c);
     if (e != cudaSuccess) return fail(RP_ECUDA, cudaGetErrorString(e));
     return RP_OK;
+}
+
+// ---- window repaint + distance matrices ("next" row f1) -------------------------------------------
+struct rp_window {
+    rp_chunk *c = nullptr;
+    int w = 0, start = 0, end = 0;
+    long long rows = 0;
+    DevBuf top, ls, rowoff, rpos, d, ab, be, lsa, lsb;
+};
+
+int rp_window_open(rp_chunk *c, int w, const float *alpha, const float *beta, const float *ls_alpha,
+                   const float *ls_beta, const double *rpos, rp_window **out, rp_stats *stats)
+{
+    if (!c || !alpha || !beta || !ls_alpha || !ls_beta || !rpos || !out) return fail(RP_EINVAL, "null argument");
+    if (w < 0 || w >= c->W) return fail(RP_EINVAL, "window index out of range");
+    if (c->flags & RP_FP64) return fail(RP_EUNSUPPORTED, "window repaint runs with fp32 state");
+    *out = nullptr;
+    const double t0 = now_ms();
+    const int N = c->N, W = c->W, L = c->L;
+    RP_CUDA(cudaSetDevice(c->device));
+    RP_TRY(paint_device(c, 0, N, stats, /*run_paint=*/false, /*want_nor=*/true));
+    LaunchPlan lp;
+    RP_TRY(plan_launch(c, lp));
+    if (lp.multi && lp.threads > (lp.wpt == 1 ? 512 : 256)) return fail(RP_EUNSUPPORTED, "N too large for the window repaint kernel");
+    cudaStream_t s = c->stream;
+    // rows per target = ib - ia + 1; prefix on the host (N ints each way)
+    std::vector<int> ia((size_t)N * W), ib((size_t)N * W);
+    RP_CUDA(cudaMemcpyAsync(ia.data(), c->ia.p, ia.size() * 4, cudaMemcpyDeviceToHost, s));
+    RP_CUDA(cudaMemcpyAsync(ib.data(), c->ib.p, ib.size() * 4, cudaMemcpyDeviceToHost, s));
+    RP_CUDA(cudaStreamSynchronize(s));
+    std::vector<long long> rowoff((size_t)N + 1, 0);
+    for (int k = 0; k < N; k++) rowoff[k + 1] = rowoff[k] + (ib[(size_t)k * W + w] - ia[(size_t)k * W + w] + 1);
+    rp_window *win = new rp_window();
+    win->c = c;
+    win->w = w;
+    win->start = c->wb[w];
+    win->end = (w < W - 1) ? c->wb[w + 1] - 1 : L - 1;
+    win->rows = rowoff[N];
+    auto bail = [&](int rc) {
+        std::string keep = g_err;
+        rp_window_close(win);
+        g_err = keep;
+        return rc;
+    };
+    int rc = RP_OK;
+    const size_t nn = (size_t)N * N;
+    if ((rc = win->top.ensure((size_t)win->rows * N * 4)) || (rc = win->ls.ensure((size_t)win->rows * 4)) ||
+        (rc = win->rowoff.ensure(((size_t)N + 1) * 8)) || (rc = win->rpos.ensure(((size_t)L + 1) * 8)) ||
+        (rc = win->d.ensure(nn * 4)) || (rc = win->ab.ensure(nn * 4)) || (rc = win->be.ensure(nn * 4)) ||
+        (rc = win->lsa.ensure((size_t)N * 4)) || (rc = win->lsb.ensure((size_t)N * 4)))
+        return bail(rc);
+#define RP_CUDAW(call)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess) return bail(fail(RP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
+    } while (0)
+    RP_CUDAW(cudaEventRecord(c->ev[0], s));
+    RP_CUDAW(cudaMemcpyAsync(win->rowoff.p, rowoff.data(), rowoff.size() * 8, cudaMemcpyHostToDevice, s));
+    RP_CUDAW(cudaMemcpyAsync(win->rpos.p, rpos, ((size_t)L + 1) * 8, cudaMemcpyHostToDevice, s));
+    RP_CUDAW(cudaMemcpyAsync(win->ab.p, alpha, nn * 4, cudaMemcpyHostToDevice, s));
+    RP_CUDAW(cudaMemcpyAsync(win->be.p, beta, nn * 4, cudaMemcpyHostToDevice, s));
+    RP_CUDAW(cudaMemcpyAsync(win->lsa.p, ls_alpha, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    RP_CUDAW(cudaMemcpyAsync(win->lsb.p, ls_beta, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    RP_CUDAW(cudaMemsetAsync(c->queue.p, 0, 8, s));
+    RP_CUDAW(cudaEventRecord(c->ev[1], s));
+    rp::RepaintParams P{};
+    P.G = c->G.as<uint32_t>();
+    P.wps = c->wps; P.N = N; P.L = L; P.W = W; P.nfw = c->nfw; P.tailn = c->tailn;
+    P.w = w; P.nt = N;
+    P.ent = c->ent.as<char>() + 4 * sizeof(rp::EntF);
+    P.off = c->off.as<long long>();
+    P.nor = c->nor.as<double>();
+    P.r = c->r.as<double>();
+    P.ia = c->ia.as<int>(); P.ib = c->ib.as<int>();
+    P.alpha_begin = win->ab.as<float>(); P.beta_end = win->be.as<float>();
+    P.ls_alpha = win->lsa.as<float>(); P.ls_beta = win->lsb.as<float>();
+    P.top = win->top.as<float>(); P.ls = win->ls.as<float>();
+    P.rowoff = win->rowoff.as<long long>();
+    P.queue = c->queue.as<int>();
+    const double ntheta = 1.0 - c->theta;
+    const double theta_ratio = c->theta / (1.0 - c->theta) - 1.0;
+    P.cf.tau = (float)(1.0 * theta_ratio + 1.0);
+    P.cf.prior_n = (float)(ntheta / (N - 1.0));
+    P.cf.ntheta = (float)ntheta;
+    P.cf.inv_ntheta = (float)(1.0 / ntheta);
+    P.cf.lower = (float)1e-10;
+    P.cf.upper = (float)(1.0 / 1e-10);
+    P.log_ntheta = log(ntheta); P.log_small = log(0.01); P.Nm1 = N - 1.0;
+    int occ = 0, ctas = 0;
+    auto launch = [&](auto kern) -> int {
+        RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, lp.threads, 0));
+        if (occ < 1) return fail(RP_ECUDA, "repaint kernel does not fit on an SM");
+        ctas = std::min(N, occ * c->sm_count);
+        kern<<<ctas, lp.threads, 0, s>>>(P);
+        RP_CUDA(cudaGetLastError());
+        return RP_OK;
+    };
+    if (lp.wpt == 1) rc = lp.multi ? launch(rp::repaint_kernel<1, true>) : launch(rp::repaint_kernel<1, false>);
+    else rc = lp.multi ? launch(rp::repaint_kernel<2, true>) : launch(rp::repaint_kernel<2, false>);
+    if (rc != RP_OK) return bail(rc);
+    RP_CUDAW(cudaEventRecord(c->ev[2], s));
+    RP_CUDAW(cudaStreamSynchronize(s));
+    for (DevBuf *b : {&win->ab, &win->be}) b->release();
+    if (stats) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+        stats->ms_h2d += a;
+        stats->ms_paint += b; // the repaint kernel
+        stats->h2d_bytes += (long long)(2 * nn * 4 + ((size_t)L + 1) * 8);
+        stats->launches += 1;
+        stats->n_targets = N;
+        stats->team_threads = lp.threads;
+        stats->words_per_thread = lp.wpt;
+        stats->ctas = ctas;
+        stats->cells = win->rows; // rows of the posterior held in HBM
+        stats->ms_total += now_ms() - t0;
+    }
+    *out = win;
+    return RP_OK;
+#undef RP_CUDAW
+}
+
+int rp_window_open_files(rp_chunk *c, const char *out_dir, int chunk_index, int w, rp_window **out, rp_stats *stats)
+{
+    if (!c || !out_dir || !out) return fail(RP_EINVAL, "null argument");
+    if (w < 0 || w >= c->W) return fail(RP_EINVAL, "window index out of range");
+    const int N = c->N, L = c->L;
+    const std::string base = std::string(out_dir) + "/chunk_" + std::to_string(chunk_index);
+    std::vector<double> rpos((size_t)L + 1);
+    {
+        FILE *fp = fopen((base + ".rpos").c_str(), "rb");
+        if (!fp) return fail(RP_EIO, "cannot open " + base + ".rpos");
+        unsigned n = 0;
+        bool ok = fread(&n, 4, 1, fp) == 1 && (int)n == L + 1 && fread(rpos.data(), 8, (size_t)L + 1, fp) == (size_t)L + 1;
+        fclose(fp);
+        if (!ok) return fail(RP_EIO, "short read in " + base + ".rpos");
+    }
+    std::vector<float> alpha((size_t)N * N), beta((size_t)N * N), lsa(N), lsb(N);
+    const std::string pf = base + "/paint/relate_" + std::to_string(w) + ".bin";
+    std::string err = rp::decode_paint_file(pf, N, c->wb[w], c->wb[w + 1] - 1, alpha.data(), beta.data(), lsa.data(), lsb.data());
+    if (!err.empty()) return fail(RP_EIO, err);
+    return rp_window_open(c, w, alpha.data(), beta.data(), lsa.data(), lsb.data(), rpos.data(), out, stats);
+}
+
+int rp_window_distance(rp_window *win, int snp, float *d)
+{
+    if (!win || !d) return fail(RP_EINVAL, "null argument");
+    if (snp < win->start || snp > win->end) return fail(RP_EINVAL, "snp outside the window");
+    rp_chunk *c = win->c;
+    RP_CUDA(cudaSetDevice(c->device));
+    rp::DistanceParams P{};
+    P.GT = c->GT.as<uint32_t>();
+    P.lw = c->lw; P.N = c->N; P.L = c->L; P.W = c->W; P.w = win->w; P.start = win->start; P.snp = snp;
+    P.rpos = win->rpos.as<double>();
+    P.top = win->top.as<float>(); P.ls = win->ls.as<float>();
+    P.rowoff = win->rowoff.as<long long>();
+    P.d = win->d.as<float>();
+    rp::distance_kernel<<<c->N, 256, 0, c->stream>>>(P);
+    RP_CUDA(cudaGetLastError());
+    RP_CUDA(cudaMemcpyAsync(d, win->d.p, (size_t)c->N * c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+    RP_CUDA(cudaStreamSynchronize(c->stream));
+    return RP_OK;
+}
+
+long long rp_window_rows(const rp_window *win) { return win ? win->rows : 0; }
+
+void rp_window_close(rp_window *win)
+{
+    if (!win) return;
+    if (win->c) cudaSetDevice(win->c->device);
+    for (DevBuf *b : {&win->top, &win->ls, &win->rowoff, &win->rpos, &win->d, &win->ab, &win->be, &win->lsa, &win->lsb}) b->release();
+    delete win;
 }
 
 } // extern "C"

@@ -266,11 +266,13 @@ template <typename ENT, int SEQ_GAP>
 __global__ void tables_kernel(ENT *__restrict__ ent, const long long *__restrict__ off, int nt, int L, int W,
                               const double *__restrict__ r, const double *__restrict__ Phi,
                               const double *__restrict__ Plo, TableConsts tc, const int *__restrict__ ia,
-                              const int *__restrict__ ib, double *__restrict__ lsA, double *__restrict__ lsB)
+                              const int *__restrict__ ib, double *__restrict__ lsA, double *__restrict__ lsB,
+                              double *__restrict__ nor_out)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nt) return;
     ENT *e = ent + off[warp];
+    double *no = nor_out ? nor_out + off[warp] : nullptr; // per-entry nor_i, kept for the window repaint
     const int D = (int)(off[warp + 1] - off[warp]);
     const int *ja = ia + (size_t)warp * W, *jb = ib + (size_t)warp * W;
     double *oa = lsA + (size_t)warp * W, *ob = lsB + (size_t)warp * W;
@@ -303,6 +305,7 @@ __global__ void tables_kernel(ENT *__restrict__ ent, const long long *__restrict
                     nor[u] = tc.log_small + tc.log_ntheta;
                 }
                 e[i].set_c(rho / ((1.0 - rho) * tc.Nm1));
+                if (no) no[i] = nor[u];
             }
         }
 #pragma unroll
@@ -777,6 +780,402 @@ paint_kernel(const PaintParams P)
     // even CTAs walk the site lists forwards (alpha), odd CTAs backwards (beta): two instantiations of one loop
     if (blockIdx.x & 1) paint_jobs<T, WPT, MULTI, 1>(P, &s_job, s_part);
     else paint_jobs<T, WPT, MULTI, 0>(P, &s_job, s_part);
+}
+
+// =========================================================================================
+// Window repaint ("next" row f1): the consumer side of the stepping stones.
+//   repaint_kernel   <- FastPainting::RePaintSection            (src/fast_painting.cpp:620-1092)
+//   distance_kernel  <- DistanceMeasure::GetMatrix              (src/anc_builder.cpp:108-207)
+// For window w every target k is re-painted between its boundary sites bS_k <= wb[w] and eS_k >= wb[w+1]-1 from
+// the stored (alpha, beta) pair; ALL visited sites are kept: the forward sweep writes alpha rows to HBM, the
+// backward sweep multiplies them in place into the posterior rows top[k][i][:] = alpha_i * beta_i and finishes the
+// per-row log-scales.  The window's entries are the slice ia[k][w]..ib[k][w] of the chunk-level site table; only
+// the last entry's recombination term differs (x_m = r[eS], :700-709).
+//
+// Rows are stored in the painter's register order: word-wise, each word rotated by k & 31 (reference haplotype j of
+// target k sits at (j & ~31) | ((j - k) & 31)); the tail haplotypes (N % 32) are stored unrotated.  This kernel
+// is HBM-bound: 3 * 4 * N * (sites in window) bytes per target against 6 FP32 ops per element.
+struct RepaintParams {
+    const uint32_t *G;
+    int wps, N, L, W, nfw, tailn;
+    int w;                   // window
+    int nt;                  // targets 0..nt-1 (all N)
+    const void *ent;         // chunk-level table (EntF)
+    const long long *off;    // [N+1]
+    const double *nor;       // [U] nor_i of the chunk-level table
+    const double *r;         // [L]
+    const int *ia, *ib;      // [N][W]
+    const float *alpha_begin, *beta_end; // [N][N] decoded stepping stones of window w (natural order)
+    const float *ls_alpha, *ls_beta;     // [N]
+    float *top;              // posterior rows, target k at row offset rowoff[k]
+    float *ls;               // per-row log-scales, same row indexing
+    const long long *rowoff; // [N+1] prefix of (ib-ia+1)
+    int *queue;
+    PaintConsts<float> cf;
+    double log_ntheta, log_small, Nm1;
+};
+
+template <int WPT, bool MULTI>
+__global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1 : 8) repaint_kernel(const RepaintParams P)
+{
+    using T = float;
+    using RT = Real<T>;
+    using V2 = float2;
+    __shared__ int s_job;
+    __shared__ __align__(16) T s_part[2][32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, TT = blockDim.x, TW = TT >> 5;
+    if (MULTI) {
+        if (t < 64) (&s_part[0][0])[t] = 0.f;
+        __syncthreads();
+    }
+    const PaintConsts<T> &K = P.cf;
+    const T tau = K.tau;
+    const EntF *ents = reinterpret_cast<const EntF *>(P.ent);
+    const unsigned rowbytes = (unsigned)P.wps * 4u;
+    bool valid[WPT];
+    T vmul[WPT];
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
+        valid[j] = (t * WPT + j) < P.nfw;
+        vmul[j] = valid[j] ? 1.f : 0.f;
+    }
+    const char *gthr = reinterpret_cast<const char *>(P.G + ((t * WPT + WPT - 1) < P.wps ? t * WPT : 0));
+    const bool has_tail = P.tailn > 0, tail_warp = has_tail && warp == 0, tail_lane = tail_warp && lane < P.tailn;
+    const char *gtail = reinterpret_cast<const char *>(P.G + (has_tail ? P.nfw : 0));
+    const uint32_t lanebit = 1u << lane;
+    const int N = P.N;
+
+    auto reduce = [&](T S, int parity) -> T {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+        if (MULTI) {
+            T *part = s_part[parity];
+            if (lane == 0) part[warp] = S;
+            __syncthreads();
+            const float4 *p4 = reinterpret_cast<const float4 *>(part);
+            float4 v = p4[0];
+            float acc = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+            for (int i = 1; i < 4; i++)
+                if (4 * i < TW) { v = p4[i]; acc += (v.x + v.y) + (v.z + v.w); }
+            S = acc;
+        }
+        return S;
+    };
+
+    for (;;) {
+        int k;
+        if (MULTI) {
+            __syncthreads();
+            if (t == 0) s_job = atomicAdd(P.queue, 1);
+            __syncthreads();
+            k = s_job;
+        } else {
+            k = 0;
+            if (lane == 0) k = atomicAdd(P.queue, 1);
+            k = __shfl_sync(0xffffffffu, k, 0);
+        }
+        if (k >= P.nt) break;
+        const int i0 = P.ia[(size_t)k * P.W + P.w], i1 = P.ib[(size_t)k * P.W + P.w];
+        const int m = i1 - i0;                      // rows 0..m
+        const EntF *pe = ents + P.off[k] + i0;      // entry of row i is pe[i]
+        const double *pnor = P.nor + P.off[k] + i0;
+        float *top = P.top + (size_t)P.rowoff[k] * N;
+        float *lsrow = P.ls + P.rowoff[k];
+        const int rot = k & 31, wk = k >> 5;
+        T ownmul[WPT];
+#pragma unroll
+        for (int j = 0; j < WPT; j++) ownmul[j] = ((wk < P.nfw) && (t * WPT + j == wk)) ? 0.f : 1.f;
+        const bool tail_live = tail_lane && !((wk == P.nfw) && (lane == rot));
+        const T tailmul = tail_live ? 1.f : 0.f;
+        // the window's last recombination term: x_m = r[eS] (:700-709)
+        const int eS = pe[m].site;
+        double nor_last, c_last;
+        {
+            const double x = P.r[eS];
+            nor_last = -x + P.log_ntheta;
+            double rho = 1.0 - exp(-x);
+            if (rho > 0.99) { rho = 0.99; nor_last = P.log_small + P.log_ntheta; }
+            c_last = rho / ((1.0 - rho) * P.Nm1);
+        }
+        // mis bits of row i for this thread's words, rotated; td = target's own allele mask
+        auto mask_words = [&](int site, uint32_t (&mw)[WPT], uint32_t &tmw) {
+            uint32_t w[WPT];
+            load_words(w, gthr + (size_t)(unsigned)site * rowbytes);
+            const uint32_t kw = P.G[(size_t)site * P.wps + wk];
+            const uint32_t td = ((kw >> rot) & 1u) ? 0xffffffffu : 0u;
+#pragma unroll
+            for (int j = 0; j < WPT; j++) {
+                const uint32_t nb = ~w[j] & td;
+                mw[j] = __funnelshift_r(nb, nb, rot);
+            }
+            tmw = 0;
+            if (tail_warp) tmw = ~*reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)site * rowbytes) & td;
+        };
+        const size_t slot0 = (size_t)t * WPT * 32; // this thread's first element within a row
+
+        // ---------------- forward: alpha rows -> top ----------------
+        V2 a[WPT][16];
+        T tl = 0.f;
+        {   // row 0 = alpha_begin, target zeroed (:757-779)
+            const float *ab = P.alpha_begin + (size_t)k * N;
+#pragma unroll
+            for (int j = 0; j < WPT; j++)
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const int n0 = (t * WPT + j) * 32;
+                    T x = valid[j] ? ab[n0 + ((2 * e + rot) & 31)] : 0.f;
+                    T y = valid[j] ? ab[n0 + ((2 * e + 1 + rot) & 31)] : 0.f;
+                    if (e == 0) x *= ownmul[j];
+                    a[j][e] = make_float2(x, y);
+                }
+            if (tail_lane) tl = ab[P.nfw * 32 + lane] * tailmul;
+        }
+        auto store_row = [&](float *row) {
+#pragma unroll
+            for (int j = 0; j < WPT; j++)
+                if (valid[j]) {
+                    float4 *o = reinterpret_cast<float4 *>(row + slot0 + j * 32);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) o[e] = make_float4(a[j][2 * e].x, a[j][2 * e].y, a[j][2 * e + 1].x, a[j][2 * e + 1].y);
+                }
+            if (tail_lane) row[P.nfw * 32 + lane] = tl;
+        };
+        auto local_sum = [&]() -> T {
+            V2 S0 = make_float2(0.f, 0.f), S1 = S0;
+#pragma unroll
+            for (int j = 0; j < WPT; j++)
+#pragma unroll
+                for (int e = 0; e < 16; e++) { if (e & 1) S1 = RT::add2(S1, a[j][e]); else S0 = RT::add2(S0, a[j][e]); }
+            S0 = RT::add2(S0, S1);
+            return S0.x + S0.y + tl;
+        };
+        int par = 0; // alternates the partial-sum buffer between consecutive reductions
+        store_row(top);
+        T S = reduce(local_sum(), par ^= 1);
+        double prev_ls = (double)P.ls_alpha[k];
+        if (t == 0) lsrow[0] = P.ls_alpha[k];
+        T R = S * pe[0].c;
+        for (int i = 1; i <= m; i++) {
+            uint32_t mw[WPT], tmw;
+            mask_words(pe[i].site, mw, tmw);
+            V2 S0 = make_float2(0.f, 0.f), S1 = S0;
+#pragma unroll
+            for (int j = 0; j < WPT; j++) {
+                const T Rj = R * vmul[j];
+                const V2 R2 = make_float2(Rj, Rj);
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    V2 v = RT::add2(a[j][e], R2);
+                    if (mw[j] & (1u << (2 * e))) v.x *= tau;
+                    if (mw[j] & (2u << (2 * e))) v.y *= tau;
+                    if (e == 0) v.x *= ownmul[j];
+                    a[j][e] = v;
+                    if (e & 1) S1 = RT::add2(S1, v); else S0 = RT::add2(S0, v);
+                }
+            }
+            S0 = RT::add2(S0, S1);
+            T Sl = S0.x + S0.y;
+            if (tail_warp) {
+                T v = tl + R;
+                if (tmw & lanebit) v *= tau;
+                tl = v * tailmul;
+                Sl += tl;
+            }
+            S = reduce(Sl, par ^= 1);
+            prev_ls += pnor[i - 1];
+            float lsi = (float)prev_ls;
+            if (S < K.lower || S > K.upper) { // :865-876
+                const T inv = 1.f / S;
+#pragma unroll
+                for (int j = 0; j < WPT; j++)
+#pragma unroll
+                    for (int e = 0; e < 16; e++) { a[j][e].x *= inv; a[j][e].y *= inv; }
+                tl *= inv;
+                const double lg = log((double)S);
+                prev_ls += lg;
+                lsi = (float)((double)lsi + lg);
+                R = 1.f;
+            } else {
+                R = S;
+            }
+            R *= (i == m) ? (T)c_last : pe[i].c;
+            store_row(top + (size_t)i * N);
+            if (t == 0) lsrow[i] = lsi;
+        }
+
+        // ---------------- backward: top[i] = alpha_i * beta_i, in place ----------------
+        // carried in g = b * m_s as in the painter; b_i = g_{i+1} + R' is the plain beta the reference multiplies in.
+        // The posterior row is taken BEFORE a rescale of this step while its log-scale receives +log(B) (:1033-1061).
+        const T chk = K.ntheta, resc_R = K.inv_ntheta; // B = ntheta * sum g;  R' after a rescale is 1/ntheta
+        V2 g[WPT][16];
+        T gt = 0.f;
+        T Rp = 0.f;
+        double prevb = (double)P.ls_beta[k];
+        for (int i = m; i >= 0; i--) {
+            float *row = top + (size_t)i * N;
+            uint32_t mw[WPT], tmw;
+            mask_words(pe[i].site, mw, tmw);
+            V2 S0 = make_float2(0.f, 0.f), S1 = S0;
+            if (i == m) { // b_m = beta_end (:895-909)
+                const float *be = P.beta_end + (size_t)k * N;
+#pragma unroll
+                for (int j = 0; j < WPT; j++)
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const int n0 = (t * WPT + j) * 32;
+                        g[j][e] = make_float2(valid[j] ? be[n0 + ((2 * e + rot) & 31)] : 0.f,
+                                              valid[j] ? be[n0 + ((2 * e + 1 + rot) & 31)] : 0.f);
+                    }
+                if (tail_lane) gt = be[P.nfw * 32 + lane];
+            }
+#pragma unroll
+            for (int j = 0; j < WPT; j++) {
+                const T Rj = (i == m) ? 0.f : Rp * vmul[j];
+                const V2 R2 = make_float2(Rj, Rj);
+                float4 *o = reinterpret_cast<float4 *>(row + slot0 + j * 32);
+#pragma unroll
+                for (int e2 = 0; e2 < 8; e2++) {
+                    float4 av = valid[j] ? o[e2] : make_float4(0.f, 0.f, 0.f, 0.f); // alpha_i
+                    V2 b0 = RT::add2(g[j][2 * e2], R2), b1 = RT::add2(g[j][2 * e2 + 1], R2);
+                    if (e2 == 0) b0.x *= ownmul[j]; // b[k] = 0
+                    if (valid[j]) o[e2] = make_float4(av.x * b0.x, av.y * b0.y, av.z * b1.x, av.w * b1.y);
+                    if (mw[j] & (1u << (4 * e2))) b0.x *= tau;
+                    if (mw[j] & (2u << (4 * e2))) b0.y *= tau;
+                    if (mw[j] & (4u << (4 * e2))) b1.x *= tau;
+                    if (mw[j] & (8u << (4 * e2))) b1.y *= tau;
+                    g[j][2 * e2] = b0;
+                    g[j][2 * e2 + 1] = b1;
+                    S0 = RT::add2(S0, b0);
+                    S1 = RT::add2(S1, b1);
+                }
+            }
+            S0 = RT::add2(S0, S1);
+            T Sl = S0.x + S0.y;
+            if (tail_warp) {
+                T b = ((i == m) ? gt : gt + Rp) * tailmul;
+                if (tail_lane) row[P.nfw * 32 + lane] = row[P.nfw * 32 + lane] * b;
+                if (tmw & lanebit) b *= tau;
+                gt = b;
+                Sl += b;
+            }
+            const T G = reduce(Sl, par ^= 1);
+            const T B = chk * G;
+            // log-scale of the row (thread 0): float accumulations exactly as the reference orders them
+            float lsi = 0.f;
+            if (t == 0) {
+                lsi = lsrow[i];
+                if (i == m) lsi = lsi + P.ls_beta[k];
+                else {
+                    prevb += (i + 1 == m) ? nor_last : pnor[i + 1];
+                    lsi = (float)((double)lsi + prevb);
+                }
+            }
+            if (i < m && (B < K.lower || B > K.upper)) {
+                const T inv = 1.f / B;
+#pragma unroll
+                for (int j = 0; j < WPT; j++)
+#pragma unroll
+                    for (int e = 0; e < 16; e++) { g[j][e].x *= inv; g[j][e].y *= inv; }
+                gt *= inv;
+                const double lg = log((double)B);
+                prevb += lg;
+                lsi = (float)((double)lsi + lg);
+                Rp = resc_R;
+            } else {
+                Rp = G;
+            }
+            Rp *= (i == m) ? (T)c_last : pe[i].c;
+            if (t == 0) lsrow[i] = lsi;
+        }
+    }
+}
+
+// DistanceMeasure::GetMatrix (src/anc_builder.cpp:108-207) for one SNP of the open window: one CTA per target row n.
+// v = number of n-derived sites in [start, snp] (row index into top[n], row 0 = bS_n), rpos_prev / rpos_next = genetic
+// positions of the last n-derived site <= snp (else SNP 0) and the first one >= snp (else SNP L-1); all three are
+// recomputed from the haplotype-major bit rows, which makes the call stateless (the reference carries them along).
+struct DistanceParams {
+    const uint32_t *GT;  // [N][lw]
+    int lw, N, L, W, w, start, snp;
+    const double *rpos;  // [L+1]
+    const float *top, *ls;
+    const long long *rowoff;
+    float *d;            // [N][N]
+};
+
+__global__ void __launch_bounds__(256) distance_kernel(const DistanceParams P)
+{
+    const int n = blockIdx.x, t = threadIdx.x, N = P.N;
+    __shared__ int s_v, s_prev, s_next, s_der;
+    __shared__ float s_min[8];
+    if (t == 0) {
+        const uint32_t *row = P.GT + (size_t)n * P.lw;
+        const int snp = P.snp;
+        auto bit = [&](int s) { return (row[s >> 5] >> (s & 31)) & 1u; };
+        // v: derived sites in [start, snp], not counting SNP 0 (the caller increments only for snp > start, and the
+        // initial count at snp == start skips snp == 0; anc_builder.cpp:79-90, 487-495)
+        int v = 0;
+        const int lo = P.start > 0 ? P.start : 1;
+        for (int wd = lo >> 5; wd <= (snp >> 5) && lo <= snp; wd++) {
+            uint32_t x = row[wd];
+            if (wd == (lo >> 5)) x &= 0xffffffffu << (lo & 31);
+            if (wd == (snp >> 5)) x &= (snp & 31) == 31 ? 0xffffffffu : ((1u << ((snp & 31) + 1)) - 1u);
+            v += __popc(x);
+        }
+        int p = snp;
+        while (!bit(p) && p > 0) p--;
+        int q = snp;
+        while (!bit(q) && q < P.L - 1) q++;
+        s_v = v; s_prev = p; s_next = q; s_der = (int)bit(snp);
+    }
+    __syncthreads();
+    const int v = s_v, rot = n & 31;
+    const int nfw32 = (N >> 5) << 5;
+    const float *top_n = P.top + (size_t)P.rowoff[n] * N;
+    const float *ls_n = P.ls + P.rowoff[n];
+    auto slot = [&](int j) { return j < nfw32 ? ((j & ~31) | ((j - rot) & 31)) : j; }; // painter's register order
+    float *out = P.d + (size_t)n * N;
+    const float scale = -1.0f;
+    float mn = INFINITY;
+    if (s_der || P.snp == 0 || P.snp == P.L - 1) {
+        const float *tr = top_n + (size_t)v * N;
+        const float lsp = ls_n[v];
+        for (int j = t; j < N; j += blockDim.x) {
+            const float m = __fmul_rn(__fadd_rn(fast_log_dev(tr[slot(j)]), lsp), scale);
+            out[j] = m;
+            mn = fminf(mn, m);
+        }
+    } else {
+        const double rp = P.rpos[s_prev], rn = P.rpos[s_next], rs = P.rpos[P.snp];
+        double wl, wr;
+        if (rp == rn) { wl = 0.5; wr = 0.5; }
+        else { const double den = rn - rp; wl = (rn - rs) / den; wr = (rs - rp) / den; }
+        const float *tp = top_n + (size_t)v * N, *tn = top_n + (size_t)(v + 1) * N;
+        const float lsp = ls_n[v], lsn = ls_n[v + 1];
+        const float e_pn = expf(lsp - lsn), e_np = expf(lsn - lsp);
+        for (int j = t; j < N; j += blockDim.x) {
+            const int sj = slot(j);
+            float m;
+            if (lsp <= lsn) {
+                const float arg = (float)__dadd_rn(__dmul_rn(__dmul_rn(wl, (double)tp[sj]), (double)e_pn), __dmul_rn(wr, (double)tn[sj]));
+                m = __fmul_rn(__fadd_rn(fast_log_dev(arg), lsn), scale);
+            } else {
+                const float arg = (float)__dadd_rn(__dmul_rn(wl, (double)tp[sj]), __dmul_rn(__dmul_rn(wr, (double)tn[sj]), (double)e_np));
+                m = __fmul_rn(__fadd_rn(fast_log_dev(arg), lsp), scale);
+            }
+            out[j] = m;
+            mn = fminf(mn, m);
+        }
+    }
+    // row minimum over all j (taken before the diagonal is zeroed, :187-192)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if ((t & 31) == 0) s_min[t >> 5] = mn;
+    __syncthreads();
+    mn = s_min[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); i++) mn = fminf(mn, s_min[i]);
+    for (int j = t; j < N; j += blockDim.x) out[j] = (j == n) ? 0.0f : __fsub_rn(out[j], mn);
 }
 
 } // namespace rp

@@ -380,3 +380,43 @@ def test_config4_shape_subset_of_targets():
         compare(sub, o, ls_atol=5e-3)
     assert np.isfinite(a.alpha).all() and np.isfinite(b.beta).all()
     assert a.stats["words_per_thread"] == 2 and a.stats["team_threads"] == 160
+
+
+# ---- window repaint + distance matrices (SURVEY.md 8 "next" row f1) ------------------------------------------
+def test_window_distances_match_reference_golden(tmp_path):
+    """GPU RePaintSection + GetMatrix on the reference's own paint files vs the matrices the reference's GetMatrix
+    produced from them (tests/golden/synth_n96/dlens_ref).  fp32 state vs the reference's fp64: the gate is the
+    d_ij tolerance 1e-4*|log(theta/(1-theta))| absolute."""
+    d = unpack_golden("synth_n96", str(tmp_path))
+    os.makedirs(os.path.join(d, "chunk_0", "paint"))
+    for w in range(5):
+        shutil.copy(os.path.join(GOLDEN, "synth_n96", "paint_ref", f"relate_{w}.bin"), os.path.join(d, "chunk_0", "paint"))
+    tol = 1e-4 * abs(np.log(THETA / (1 - THETA)))
+    with capi.DeviceChunk.load(d, 0, "0.001,1") as c:
+        for sec in (1, 3):
+            want = oracle.read_distances(os.path.join(GOLDEN, "synth_n96", "dlens_ref", f"d_{sec}.bin.gz"))
+            with capi.Window.open_files(c, d, 0, sec) as win:
+                assert win.rows > 0
+                for snp, ref in want.items():
+                    got = win.distance(snp)
+                    assert np.all(np.diag(got) == 0)
+                    assert float(np.abs(got - ref).max()) <= tol, (sec, snp)
+
+
+@pytest.mark.parametrize("N,L,W", [(200, 3000, 3), (1000, 1500, 2), (2100, 700, 2)])
+def test_window_distances_vs_oracle_on_gpu_painted_files(tmp_path, N, L, W):
+    """Paint on the GPU, then the GPU window path vs the oracle's RePaintSection+GetMatrix on the same files
+    (single-warp, tail and multi-warp teams)."""
+    d = str(tmp_path / "o")
+    synth.make_chunk_dir(d, N, L, seed=51, n_windows=W)
+    capi.paint_chunk(d, 0, "0.001,1")
+    tol = 1e-4 * abs(np.log(THETA / (1 - THETA)))
+    stride = max(1, L // W // 3)
+    with capi.DeviceChunk.load(d, 0, "0.001,1") as c:
+        for sec in range(W):
+            out = str(tmp_path / f"ora_{sec}.bin")
+            oracle.window_distances(d, 0, sec, stride, "0.001,1", out)
+            want = oracle.read_distances(out)
+            with capi.Window.open_files(c, d, 0, sec) as win:
+                worst = max(float(np.abs(win.distance(snp) - ref).max()) for snp, ref in want.items())
+            assert worst <= tol, (sec, worst)
