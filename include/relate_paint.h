@@ -65,6 +65,8 @@ typedef struct rp_stats {
     int ctas;            /* grid size of the paint kernel                                 */
     int reserved;
     double ms_load;      /* rp_paint_chunk: reading the chunk files (wall)                */
+    double ms_rle;       /* device record encoder (CUDA events)                            */
+    double ms_write;     /* rp_paint_chunk: writing the paint files (wall, overlaps painting) */
 } rp_stats;
 
 typedef struct rp_tune { /* all zero = automatic */
@@ -111,6 +113,14 @@ int rp_paint_targets(rp_chunk *c, int k_begin, int k_end, float *alpha, float *b
 int rp_paint_targets_device(rp_chunk *c, int k_begin, int k_end, const float **dev_alpha,
                             const float **dev_beta, const float **dev_ls_alpha, const float **dev_ls_beta,
                             const int **dev_site_begin, const int **dev_site_end, rp_stats *stats);
+
+/* Paint targets [k_begin, k_end) and encode them on the device into the records the reference writes
+ * (fast_painting.cpp:589-601 + CollapsedMatrix<float>::DumpToFile, collapsed_matrix.hpp:228-265): for each window
+ * w the bytes that targets k_begin..k_end-1 contribute to chunk_<c>/paint/relate_<w>.bin, contiguous and in target
+ * order.  The W images are laid out back to back in HBM; win_off (W+1 entries, host) receives their byte offsets,
+ * win_off[W] = total size.  rp_records_copy then copies `bytes` bytes starting at byte `offset` to the host. */
+int rp_paint_records(rp_chunk *c, int k_begin, int k_end, long long *win_off, rp_stats *stats);
+int rp_records_copy(rp_chunk *c, long long offset, long long bytes, void *host_image, rp_stats *stats);
 
 /* One call from a host-resident Data to host-resident stepping stones: chunk_create + paint_targets + free.
  * This is the call bench.py times for its end-to-end ("e2e") number: hap/r go host->device and the

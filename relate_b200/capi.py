@@ -37,7 +37,8 @@ class RpStats(C.Structure):
                 ("sites", C.c_longlong), ("cells", C.c_longlong), ("h2d_bytes", C.c_longlong),
                 ("d2h_bytes", C.c_longlong), ("launches", C.c_int), ("n_targets", C.c_int),
                 ("team_threads", C.c_int), ("words_per_thread", C.c_int), ("ctas", C.c_int),
-                ("reserved", C.c_int), ("ms_load", C.c_double)]
+                ("reserved", C.c_int), ("ms_load", C.c_double), ("ms_rle", C.c_double),
+                ("ms_write", C.c_double)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -64,6 +65,8 @@ SYMBOLS = {
     "rp_peak_fp32": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rp_paint_targets": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(RpStats)]),
     "rp_paint_targets_device": (C.c_int, [_P, C.c_int, C.c_int] + [C.POINTER(_P)] * 6 + [C.POINTER(RpStats)]),
+    "rp_paint_records": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(RpStats)]),
+    "rp_records_copy": (C.c_int, [_P, C.c_longlong, C.c_longlong, _P, C.POINTER(RpStats)]),
     "rp_paint_from_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_double, C.c_uint,
                                      C.POINTER(RpTune), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(RpStats)]),
     "rp_paint_chunk": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, _P, C.c_int, C.c_uint, C.POINTER(RpStats)]),
@@ -181,6 +184,16 @@ class DeviceChunk:
         d = st.as_dict()
         d["dev_ptrs"] = [p.value for p in ptrs]
         return d
+
+    def paint_records(self, k_begin: int = 0, k_end: int | None = None):
+        """Paint + device record encoder: -> (list of W ``bytes`` file images for these targets, stats)."""
+        k_end = self.N if k_end is None else k_end
+        off = np.zeros(self.W + 1, np.int64)
+        st = RpStats()
+        check(lib().rp_paint_records(self._h, k_begin, k_end, _ptr(off), C.byref(st)))
+        img = np.empty(int(off[-1]), np.uint8)
+        check(lib().rp_records_copy(self._h, 0, int(off[-1]), _ptr(img), C.byref(st)))
+        return [img[off[w]:off[w + 1]].tobytes() for w in range(self.W)], st.as_dict()
 
     def close(self) -> None:
         if self._h:

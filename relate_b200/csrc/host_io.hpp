@@ -13,7 +13,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <vector>
 
 namespace rp {
@@ -33,13 +35,13 @@ inline bool file_exists(const std::string &p)
     return stat(p.c_str(), &st) == 0;
 }
 
-// returns "" on success, else the error text
-// alloc_hap(bytes) may hand out pinned memory for the L*N genotype chars (nullptr -> std::vector)
-template <typename AllocHap>
-inline std::string load_chunk_files(const std::string &dir, int chunk, const char *painting, HostChunk &hc,
-                                    AllocHap alloc_hap)
+// Everything of a chunk except the genotype bytes: parameters, .r, presence of the four files the reference loader
+// also opens, --painting handling.  Opens chunk_<c>.hap, checks its header and returns the descriptor in *hap_fd
+// (the L*N genotype chars start at byte 16).  Returns "" on success, else the error text.
+inline std::string load_chunk_small(const std::string &dir, int chunk, const char *painting, HostChunk &hc, int *hap_fd)
 {
     const std::string base = dir + "/chunk_" + std::to_string(chunk);
+    *hap_fd = -1;
     {
         const std::string p = dir + "/parameters_c" + std::to_string(chunk) + ".bin";
         FILE *fp = fopen(p.c_str(), "rb");
@@ -55,28 +57,6 @@ inline std::string load_chunk_files(const std::string &dir, int chunk, const cha
     }
     for (const char *ext : {".bp", ".dist", ".rpos", ".state"}) // the reference loader opens all six
         if (!file_exists(base + ext)) return "missing " + base + ext;
-    {
-        const std::string p = base + ".hap";
-        FILE *fp = fopen(p.c_str(), "rb");
-        if (!fp) return "cannot open " + p;
-        uint64_t uL = 0, uN = 0;
-        bool ok = fread(&uL, 8, 1, fp) == 1 && fread(&uN, 8, 1, fp) == 1;
-        if (ok && ((int)uL != hc.L || (int)uN != hc.N)) {
-            fclose(fp);
-            return p + ": dimensions disagree with parameters file";
-        }
-        if (ok) {
-            const size_t nbytes = (size_t)uL * uN;
-            hc.hap = alloc_hap(nbytes);
-            if (!hc.hap) {
-                hc.hap_own.resize(nbytes);
-                hc.hap = hc.hap_own.data();
-            }
-            ok = fread(hc.hap, 1, nbytes, fp) == nbytes;
-        }
-        fclose(fp);
-        if (!ok) return "short read in " + p;
-    }
     {
         const std::string p = base + ".r";
         FILE *fp = fopen(p.c_str(), "rb");
@@ -99,6 +79,59 @@ inline std::string load_chunk_files(const std::string &dir, int chunk, const cha
         for (auto &x : hc.r) x *= rho;
     }
     if (hc.wb.back() != hc.L || hc.wb.front() != 0) return "window boundaries do not span the chunk";
+    {
+        const std::string p = base + ".hap";
+        const int fd = open(p.c_str(), O_RDONLY);
+        if (fd < 0) return "cannot open " + p;
+        uint64_t hdr[2] = {0, 0};
+        if (pread(fd, hdr, 16, 0) != 16) {
+            close(fd);
+            return "short read in " + p;
+        }
+        if ((int)hdr[0] != hc.L || (int)hdr[1] != hc.N) {
+            close(fd);
+            return p + ": dimensions disagree with parameters file";
+        }
+        struct stat sb;
+        if (fstat(fd, &sb) != 0 || (uint64_t)sb.st_size < 16 + hdr[0] * hdr[1]) {
+            close(fd);
+            return "short read in " + p;
+        }
+        *hap_fd = fd;
+    }
+    return "";
+}
+
+// Reads bytes [off, off+n) of the genotype matrix (file offset 16+off) into dst; false on a short read.
+inline bool read_hap_range(int fd, size_t off, size_t n, char *dst)
+{
+    while (n > 0) {
+        const ssize_t got = pread(fd, dst, n, (off_t)(16 + off));
+        if (got <= 0) return false;
+        dst += got;
+        off += (size_t)got;
+        n -= (size_t)got;
+    }
+    return true;
+}
+
+// alloc_hap(bytes) may hand out pinned memory for the L*N genotype chars (nullptr -> std::vector)
+template <typename AllocHap>
+inline std::string load_chunk_files(const std::string &dir, int chunk, const char *painting, HostChunk &hc,
+                                    AllocHap alloc_hap)
+{
+    int fd = -1;
+    std::string err = load_chunk_small(dir, chunk, painting, hc, &fd);
+    if (!err.empty()) return err;
+    const size_t nbytes = (size_t)hc.L * hc.N;
+    hc.hap = alloc_hap(nbytes);
+    if (!hc.hap) {
+        hc.hap_own.resize(nbytes);
+        hc.hap = hc.hap_own.data();
+    }
+    const bool ok = read_hap_range(fd, 0, nbytes, hc.hap);
+    close(fd);
+    if (!ok) return "short read in " + dir + "/chunk_" + std::to_string(chunk) + ".hap";
     return "";
 }
 

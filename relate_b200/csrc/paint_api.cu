@@ -10,7 +10,9 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <future>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -98,6 +100,10 @@ struct rp_chunk {
     DevBuf G, GT, r, Phi, Plo, wbdev, chars;
     // per-paint work buffers (grown on demand, reused)
     DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch, nor;
+    // record encoder (device RLE): run counts, byte offsets, the W file images of the last batch
+    DevBuf rleK, rec_off, win_bytes, img_off, image;
+    std::vector<long long> h_img_off; // W+1 offsets of the last encoded batch
+    int enc_targets = 0;              // targets in c->image (0: none)
     long long *h_total = nullptr; // pinned
     cudaStream_t stream = nullptr;       // the stream every copy and kernel of this chunk is issued on
     cudaStream_t own_stream = nullptr;   // created by the library; `stream` may be replaced by a caller's
@@ -200,8 +206,16 @@ void dd_prefix(const double *r, int L, std::vector<double> &hi, std::vector<doub
     }
 }
 
+// Genotype bytes that are still being read from disk: slice i of `slice` bytes may be copied once ready[i] != 0
+// (1 = read, -1 = read failed).  Lets the host->device copy run behind the file reads.
+struct HapFeed {
+    size_t slice = 0;
+    int nsl = 0;
+    std::unique_ptr<std::atomic<int>[]> ready;
+};
+
 int chunk_from_host(int device, int N, int L, const char *hap, const double *r, const int *wb, int n_wb,
-                    double theta, unsigned flags, rp_chunk **out, rp_stats *st)
+                    double theta, unsigned flags, rp_chunk **out, rp_stats *st, const HapFeed *feed = nullptr)
 {
     if (!out || !hap || !r || !wb) return fail(RP_EINVAL, "null argument");
     if (N < 2 || L < 2 || n_wb < 2) return fail(RP_EINVAL, "need N>=2, L>=2 and at least one window");
@@ -275,9 +289,19 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
     RP_TRYB(c->Plo.ensure((size_t)(L + 1) * 8));
     RP_TRYB(c->wbdev.ensure((size_t)n_wb * 4));
     RP_CUDAB(cudaEventRecord(c->ev[0], c->stream));
-    RP_CUDAB(cudaMemcpyAsync(chars.p, hap, nchar, cudaMemcpyHostToDevice, c->stream));
     std::vector<double> hi, lo;
     dd_prefix(r, L, hi, lo);
+    if (!feed) {
+        RP_CUDAB(cudaMemcpyAsync(chars.p, hap, nchar, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (int i = 0; i < feed->nsl; i++) {
+            int state;
+            while ((state = feed->ready[i].load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+            if (state < 0) return bail(fail(RP_EIO, "short read in the chunk's .hap file"));
+            const size_t at = (size_t)i * feed->slice, n = std::min(feed->slice, nchar - at);
+            RP_CUDAB(cudaMemcpyAsync(chars.as<char>() + at, hap + at, n, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
     RP_CUDAB(cudaMemcpyAsync(c->r.p, r, (size_t)L * 8, cudaMemcpyHostToDevice, c->stream));
     RP_CUDAB(cudaMemcpyAsync(c->Phi.p, hi.data(), (size_t)(L + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     RP_CUDAB(cudaMemcpyAsync(c->Plo.p, lo.data(), (size_t)(L + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -462,6 +486,61 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     return RP_OK;
 }
 
+// Device side of CollapsedMatrix<float>::DumpToFile for the batch painted last: counts runs, lays out the W file
+// images (window-major, targets in order) and writes the records into c->image.  c->h_img_off[w] = byte offset of
+// window w's image, [W] = total.
+int encode_device(rp_chunk *c, int nt, rp_stats *st)
+{
+    const int W = c->W, N = c->N;
+    const size_t nw = (size_t)nt * W;
+    cudaStream_t s = c->stream;
+    RP_TRY(c->rleK.ensure(nw * 2 * 4));
+    RP_TRY(c->rec_off.ensure(nw * 8));
+    RP_TRY(c->win_bytes.ensure((size_t)W * 8));
+    RP_TRY(c->img_off.ensure((size_t)(W + 1) * 8));
+    rp::RleParams P{};
+    P.alpha = c->alpha.as<float>();
+    P.beta = c->beta.as<float>();
+    P.ls_alpha = c->lsa.as<float>();
+    P.ls_beta = c->lsb.as<float>();
+    P.site_begin = c->sb.as<int>();
+    P.site_end = c->se.as<int>();
+    P.wb = c->wbdev.as<int>();
+    P.T = nt;
+    P.W = W;
+    P.N = N;
+    P.K = c->rleK.as<int>();
+    P.rec_off = c->rec_off.as<long long>();
+    P.img_off = c->img_off.as<long long>();
+    const long long nvec = (long long)nw * 2;
+    const unsigned grid = (unsigned)std::min<long long>((nvec + 7) / 8, (long long)c->sm_count * 64);
+    RP_CUDA(cudaEventRecord(c->ev[0], s));
+    rp::rle_kernel<false><<<grid, 256, 0, s>>>(P);
+    rp::rle_offsets_kernel<<<W, 256, 0, s>>>(c->rleK.as<int>(), nt, W, c->rec_off.as<long long>(),
+                                             c->win_bytes.as<long long>());
+    rp::rle_image_scan_kernel<<<1, 32, 0, s>>>(c->win_bytes.as<long long>(), W, c->img_off.as<long long>());
+    RP_CUDA(cudaGetLastError());
+    c->h_img_off.resize(W + 1);
+    RP_CUDA(cudaMemcpyAsync(c->h_img_off.data(), c->img_off.p, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, s));
+    RP_CUDA(cudaStreamSynchronize(s));
+    const long long total = c->h_img_off[W];
+    RP_TRY(c->image.ensure((size_t)total));
+    P.image = c->image.as<char>();
+    rp::rle_kernel<true><<<grid, 256, 0, s>>>(P);
+    RP_CUDA(cudaGetLastError());
+    RP_CUDA(cudaEventRecord(c->ev[1], s));
+    RP_CUDA(cudaStreamSynchronize(s));
+    c->enc_targets = nt;
+    if (st) {
+        float a = 0;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+        st->ms_rle += a;
+        st->launches += 4;
+        st->d2h_bytes += (long long)(W + 1) * 8;
+    }
+    return RP_OK;
+}
+
 int copy_out(rp_chunk *c, int nt, float *alpha, float *beta, float *ls_alpha, float *ls_beta, int *site_begin,
              int *site_end, rp_stats *st)
 {
@@ -573,7 +652,8 @@ void rp_chunk_free(rp_chunk *c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
-                      &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch, &c->nor})
+                      &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch, &c->nor,
+                      &c->rleK, &c->rec_off, &c->win_bytes, &c->img_off, &c->image})
         b->release();
     if (c->h_total) cudaFreeHost(c->h_total);
     for (auto &e : c->ev)
@@ -605,6 +685,36 @@ int rp_paint_targets(rp_chunk *c, int k_begin, int k_end, float *alpha, float *b
     RP_TRY(paint_device(c, k_begin, k_end, stats));
     RP_TRY(copy_out(c, k_end - k_begin, alpha, beta, ls_alpha, ls_beta, site_begin, site_end, stats));
     if (stats) stats->ms_total += now_ms() - t0;
+    return RP_OK;
+}
+
+int rp_paint_records(rp_chunk *c, int k_begin, int k_end, long long *win_off, rp_stats *stats)
+{
+    const double t0 = now_ms();
+    if (c) c->enc_targets = 0;
+    RP_TRY(paint_device(c, k_begin, k_end, stats));
+    RP_TRY(encode_device(c, k_end - k_begin, stats));
+    if (win_off) memcpy(win_off, c->h_img_off.data(), (size_t)(c->W + 1) * 8);
+    if (stats) stats->ms_total += now_ms() - t0;
+    return RP_OK;
+}
+
+int rp_records_copy(rp_chunk *c, long long offset, long long bytes, void *host_image, rp_stats *stats)
+{
+    if (!c || !host_image) return fail(RP_EINVAL, "null argument");
+    if (c->enc_targets == 0) return fail(RP_EINVAL, "no encoded batch on this chunk (call rp_paint_records first)");
+    if (offset < 0 || bytes < 0 || offset + bytes > c->h_img_off[c->W]) return fail(RP_EINVAL, "range outside the encoded images");
+    RP_CUDA(cudaSetDevice(c->device));
+    RP_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    RP_CUDA(cudaMemcpyAsync(host_image, c->image.as<char>() + offset, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    RP_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    RP_CUDA(cudaStreamSynchronize(c->stream));
+    if (stats) {
+        float a = 0;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+        stats->ms_d2h += a;
+        stats->d2h_bytes += bytes;
+    }
     return RP_OK;
 }
 
@@ -967,42 +1077,67 @@ extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *
         if (d < 0 || d >= ndev) return fail(RP_EINVAL, "device index out of range");
     std::lock_guard<std::mutex> stage_lock(g_stage_mu);
 
+    // ---- input: small files now, genotype bytes by reader threads while the devices already copy ----
     rp::HostChunk hc;
+    int hap_fd = -1;
+    RP_CUDA(cudaSetDevice(devs[0]));
     {
-        RP_CUDA(cudaSetDevice(devs[0]));
-        std::string err = rp::load_chunk_files(out_dir, chunk_index, painting, hc, [&](size_t bytes) -> char * {
-            return g_hap_in.ensure(bytes) == RP_OK ? static_cast<char *>(g_hap_in.p) : nullptr;
-        });
+        std::string err = rp::load_chunk_small(out_dir, chunk_index, painting, hc, &hap_fd);
         if (!err.empty()) return fail(RP_EIO, err);
     }
-    const double t_loaded = now_ms();
+    const size_t nchar = (size_t)hc.L * hc.N;
+    if (g_hap_in.ensure(nchar) != RP_OK) {
+        close(hap_fd);
+        return RP_ENOMEM;
+    }
+    hc.hap = static_cast<char *>(g_hap_in.p);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    HapFeed feed;
+    feed.slice = (size_t)4 << 20;
+    feed.nsl = (int)((nchar + feed.slice - 1) / feed.slice);
+    feed.ready.reset(new std::atomic<int>[feed.nsl]);
+    for (int i = 0; i < feed.nsl; i++) feed.ready[i].store(0);
+    std::atomic<int> next_slice{0}, readers_left{0};
+    double t_loaded = t0;
+    std::vector<std::thread> readers;
+    const int nread = (int)std::max(1u, std::min<unsigned>({8u, hw, (unsigned)feed.nsl}));
+    readers_left = nread;
+    for (int t = 0; t < nread; t++)
+        readers.emplace_back([&]() {
+            for (;;) {
+                const int i = next_slice.fetch_add(1);
+                if (i >= feed.nsl) break;
+                const size_t at = (size_t)i * feed.slice, n = std::min(feed.slice, nchar - at);
+                const bool ok = rp::read_hap_range(hap_fd, at, n, hc.hap + at);
+                feed.ready[i].store(ok ? 1 : -1, std::memory_order_release);
+            }
+            if (readers_left.fetch_sub(1) == 1) t_loaded = now_ms();
+        });
 
+    // ---- output files: created (and old ones truncated) in the background; the first write waits for it ----
     const int N = hc.N, W = (int)hc.wb.size() - 1;
-    const std::string cdir = std::string(out_dir) + "/chunk_" + std::to_string(chunk_index);
-    const std::string pdir = cdir + "/paint";
-    // filesys::MakeDir semantics (src/filesystem.cpp:4-24): create if absent, mode 0700
-    for (const std::string &d : {cdir, pdir}) {
-        struct stat sb;
-        if (stat(d.c_str(), &sb) != 0 && mkdir(d.c_str(), 0700) != 0) return fail(RP_EIO, "could not create directory " + d);
-    }
-    std::vector<FILE *> files(W, nullptr);
-    auto close_all = [&]() {
-        for (FILE *&f : files)
-            if (f) { fclose(f); f = nullptr; }
-    };
-    for (int w = 0; w < W; w++) {
-        const std::string p = pdir + "/relate_" + std::to_string(w) + ".bin";
-        files[w] = fopen(p.c_str(), "wb");
-        if (!files[w]) {
-            close_all();
-            return fail(RP_EIO, "cannot create " + p);
+    std::vector<int> fds(W, -1);
+    std::shared_future<std::string> files_open = std::async(std::launch::async, [&]() -> std::string {
+        const std::string cdir = std::string(out_dir) + "/chunk_" + std::to_string(chunk_index);
+        const std::string pdir = cdir + "/paint";
+        // filesys::MakeDir semantics (src/filesystem.cpp:4-24): create if absent, mode 0700
+        for (const std::string &d : {cdir, pdir}) {
+            struct stat sb;
+            if (stat(d.c_str(), &sb) != 0 && mkdir(d.c_str(), 0700) != 0) return "could not create directory " + d;
         }
-        setvbuf(files[w], nullptr, _IONBF, 0); // blobs are written whole
-    }
+        std::atomic<int> bad{-1};
+        parallel_for(W, 8, [&](int w) {
+            const std::string p = pdir + "/relate_" + std::to_string(w) + ".bin";
+            fds[w] = open(p.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+            if (fds[w] < 0) bad = w;
+        });
+        if (bad >= 0) return "cannot create " + pdir + "/relate_" + std::to_string(bad.load()) + ".bin";
+        return "";
+    }).share();
 
-    // batch size: bound the pinned staging per device (2 x 512 MB: pinning memory costs ~0.3 s/GB), keep every GPU busy
+    // batch size: bound the pinned staging per device (2 buffers: pinning memory costs ~0.3 s/GB), keep every GPU busy
     const size_t per_target = (size_t)2 * W * N * 4;
-    long long bsz = (long long)((1024ull << 20) / per_target);
+    long long bsz = (long long)((512ull << 20) / per_target);
     bsz = std::max<long long>(bsz, 64);
     bsz = std::min<long long>(bsz, N);
     if ((int)devs.size() > 1)
@@ -1016,10 +1151,49 @@ extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *
     int next_write = 0;
     int first_rc = RP_OK;
     std::string first_err;
+    double ms_write = 0;
     std::vector<rp_stats> dstats(devs.size());
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int enc_threads = (int)std::max<unsigned>(1, std::min<unsigned>(hw / (unsigned)devs.size(), 64));
-    const int TB = 32; // targets per encode task
+    auto set_error = [&](int rc, const std::string &msg) { // call with mu held
+        if (first_rc == RP_OK) {
+            first_rc = rc;
+            first_err = msg;
+        }
+        cv.notify_all();
+    };
+
+    // appends batch b's W images (host memory) to the W files once every earlier batch has been written
+    auto write_batch = [&](int b, const char *img, std::vector<long long> off) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return next_write == b || first_rc != RP_OK; });
+        if (first_rc != RP_OK) return;
+        lk.unlock(); // only batch b may write now; keep the lock free for error reports
+        const double tw = now_ms();
+        std::string err = files_open.get();
+        if (err.empty()) {
+            std::atomic<int> werr{0};
+            parallel_for(W, 16, [&](int w) { // one writer per window file
+                const char *p = img + off[w];
+                long long left = off[w + 1] - off[w];
+                while (left > 0) {
+                    const ssize_t put = write(fds[w], p, (size_t)left);
+                    if (put <= 0) {
+                        werr = 1;
+                        break;
+                    }
+                    p += put;
+                    left -= put;
+                }
+            });
+            if (werr) err = "short write to the paint files";
+        }
+        lk.lock();
+        ms_write += now_ms() - tw;
+        if (!err.empty()) set_error(RP_EIO, err);
+        else {
+            next_write = b + 1;
+            cv.notify_all();
+        }
+    };
 
     auto worker = [&](int di) {
         rp_stats &st = dstats[di];
@@ -1028,80 +1202,56 @@ extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *
         rp_chunk *c = ws.shell;
         ws.shell = nullptr;
         int rc = chunk_from_host(devs[di], hc.N, hc.L, hc.hap, hc.r.data(), hc.wb.data(), (int)hc.wb.size(), hc.theta,
-                                 flags, &c, &st);
-        std::vector<float> lsa, lsb;
-        std::vector<int> sb, se;
-        if (rc == RP_OK) {
-            const size_t vb = (size_t)B * W * N * 4;
-            rc = ws.ha.ensure(vb);
-            if (rc == RP_OK) rc = ws.hb.ensure(vb);
-            lsa.resize((size_t)B * W);
-            lsb.resize((size_t)B * W);
-            sb.resize((size_t)B * W);
-            se.resize((size_t)B * W);
-        }
-        float *ha = static_cast<float *>(ws.ha.p), *hb = static_cast<float *>(ws.hb.p);
-        const int nblk_max = (B + TB - 1) / TB;
-        std::vector<std::vector<char>> blobs((size_t)W * nblk_max);
+                                 flags, &c, &st, &feed);
+        PinnedBuf *pin[2] = {&ws.ha, &ws.hb};
+        std::future<void> pending[2];
+        int slot = 0;
         while (rc == RP_OK) {
             const int b = next_batch.fetch_add(1);
             if (b >= nbatch) break;
-            const int k0 = b * B, k1 = std::min(N, k0 + B), nt = k1 - k0;
-            rc = rp_paint_targets(c, k0, k1, ha, hb, lsa.data(), lsb.data(), sb.data(), se.data(), &st);
+            const int k0 = b * B, k1 = std::min(N, k0 + B);
+            rc = paint_device(c, k0, k1, &st);
+            if (rc == RP_OK) rc = encode_device(c, k1 - k0, &st);
             if (rc != RP_OK) break;
-            const double te = now_ms();
-            const int nblk = (nt + TB - 1) / TB;
-            parallel_for(W * nblk, enc_threads, [&](int task) {
-                const int w = task / nblk, blk = task % nblk;
-                std::vector<char> &out = blobs[(size_t)w * nblk_max + blk];
-                out.clear();
-                std::vector<float> vals;
-                std::vector<int> lens;
-                const int a0 = hc.wb[w], b0 = hc.wb[w + 1] - 1;
-                const int kb = blk * TB, ke = std::min(nt, kb + TB);
-                for (int kk = kb; kk < ke; kk++) { // fast_painting.cpp:589-601
-                    const size_t at = out.size();
-                    out.resize(at + 8);
-                    memcpy(out.data() + at, &a0, 4);
-                    memcpy(out.data() + at + 4, &b0, 4);
-                    const size_t row = ((size_t)kk * W + w);
-                    rp::append_record(out, ha + row * N, N, sb[row], lsa[row], vals, lens);
-                    rp::append_record(out, hb + row * N, N, se[row], lsb[row], vals, lens);
-                }
-            });
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return next_write == b || first_rc != RP_OK; });
-                if (first_rc == RP_OK) {
-                    std::atomic<int> werr{0};
-                    parallel_for(W, std::min(enc_threads, 16), [&](int w) { // one writer per window file
-                        for (int blk = 0; blk < nblk; blk++) {
-                            const std::vector<char> &o = blobs[(size_t)w * nblk_max + blk];
-                            if (fwrite(o.data(), 1, o.size(), files[w]) != o.size()) werr = 1;
-                        }
-                    });
-                    if (werr) rc = fail(RP_EIO, "short write to the paint files");
-                    next_write = b + 1;
-                }
-                cv.notify_all();
+            if (pending[slot].valid()) pending[slot].get(); // this staging buffer's previous batch is on disk
+            const long long total = c->h_img_off[W];
+            rc = pin[slot]->ensure((size_t)(total + total / 8));
+            if (rc != RP_OK) break;
+            cudaError_t e = cudaEventRecord(c->ev[0], c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(pin[slot]->p, c->image.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(c->ev[1], c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) {
+                rc = fail(RP_ECUDA, std::string("copying the encoded records to the host: ") + cudaGetErrorString(e));
+                break;
             }
-            st.ms_encode += now_ms() - te;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+            st.ms_d2h += ms;
+            st.d2h_bytes += total;
+            pending[slot] = std::async(std::launch::async, write_batch, b, static_cast<const char *>(pin[slot]->p), c->h_img_off);
+            slot ^= 1;
         }
         if (rc != RP_OK) {
             std::unique_lock<std::mutex> lk(mu);
-            if (first_rc == RP_OK) {
-                first_rc = rc;
-                first_err = g_err;
-            }
-            cv.notify_all();
+            set_error(rc, g_err);
         }
+        for (auto &f : pending)
+            if (f.valid()) f.get();
         ws.shell = c; // park the workspace (may be nullptr if creation failed)
     };
     std::vector<std::thread> threads;
     for (int di = 1; di < (int)devs.size(); di++) threads.emplace_back(worker, di);
     worker(0);
     for (auto &t : threads) t.join();
-    close_all();
+    for (auto &t : readers) t.join();
+    close(hap_fd);
+    {
+        const std::string err = files_open.get();
+        for (int fd : fds)
+            if (fd >= 0) close(fd);
+        if (first_rc == RP_OK && !err.empty()) return fail(RP_EIO, err);
+    }
     if (first_rc != RP_OK) return fail(first_rc, first_err);
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -1110,7 +1260,7 @@ extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *
             stats->ms_prep = std::max(stats->ms_prep, s.ms_prep);
             stats->ms_paint = std::max(stats->ms_paint, s.ms_paint);
             stats->ms_d2h = std::max(stats->ms_d2h, s.ms_d2h);
-            stats->ms_encode = std::max(stats->ms_encode, s.ms_encode);
+            stats->ms_rle = std::max(stats->ms_rle, s.ms_rle);
             stats->sites += s.sites;
             stats->cells += s.cells;
             stats->h2d_bytes += s.h2d_bytes;
@@ -1121,6 +1271,7 @@ extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *
             stats->words_per_thread = s.words_per_thread;
             stats->ctas = s.ctas;
         }
+        stats->ms_write = ms_write;
         stats->ms_load = t_loaded - t0;
         stats->ms_total = now_ms() - t0;
     }

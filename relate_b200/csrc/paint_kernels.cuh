@@ -1178,4 +1178,133 @@ __global__ void __launch_bounds__(256) distance_kernel(const DistanceParams P)
     for (int j = t; j < N; j += blockDim.x) out[j] = (j == n) ? 0.0f : __fsub_rn(out[j], mn);
 }
 
+// =========================================================================================
+// Stepping-stone record codec on the device: CollapsedMatrix<float>::DumpToFile (src/collapsed_matrix.hpp:228-265).
+// A value joins the current run when fabs(head - v) < 1e-3 * min(head, v) (float difference, comparison in double);
+// otherwise it becomes the head of a new run.  The rule is sequential in the run heads only: a warp tests 32 values
+// against the current head at once, the first failing lane becomes the next head (ballot + ffs).
+// One warp per vector; `EMIT=false` counts runs, `EMIT=true` writes the record into the window's file image.
+// Record: size_t 1; size_t N; int site; float logscale; int K; float val[K]; int len[K]   (28 + 8K bytes)
+// File image of window w, per target: int wb[w]; int wb[w+1]-1; alpha record; beta record (fast_painting.cpp:589-601)
+struct RleParams {
+    const float *alpha, *beta;        // [T][W][N]
+    const float *ls_alpha, *ls_beta;  // [T][W]
+    const int *site_begin, *site_end; // [T][W]
+    const int *wb;                    // [W+1]
+    int T, W, N;
+    int *K;                           // [T][W][2] run counts
+    const long long *rec_off;         // [T][W] byte offset of the target's block within window w's image (EMIT)
+    const long long *img_off;         // [W] byte offset of window w's image within `image` (EMIT)
+    char *image;
+};
+
+// Byte layout of the W file images of one batch: rec_off[k*W+w] = offset of target k's block inside window w's image
+// (exclusive scan over targets of 64 + 8*(Ka+Kb)), win_bytes[w] = size of the image.  One CTA per window.
+__global__ void __launch_bounds__(256) rle_offsets_kernel(const int *__restrict__ K, int T, int W,
+                                                          long long *__restrict__ rec_off,
+                                                          long long *__restrict__ win_bytes)
+{
+    __shared__ long long wsum[8];
+    __shared__ long long base_s;
+    const int w = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (t == 0) base_s = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < T; k0 += 256) {
+        const int k = k0 + t;
+        long long sz = 0;
+        if (k < T) {
+            const size_t tw = (size_t)k * W + w;
+            sz = 64 + 8ll * (K[2 * tw] + K[2 * tw + 1]);
+        }
+        long long incl = sz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        long long pre = base_s;
+        for (int i = 0; i < wid; i++) pre += wsum[i];
+        if (k < T) rec_off[(size_t)k * W + w] = pre + incl - sz;
+        __syncthreads();
+        if (t == 255) base_s = pre + incl;
+        __syncthreads();
+    }
+    if (t == 0) win_bytes[w] = base_s;
+}
+
+// img_off[w] = exclusive scan of win_bytes (img_off[W] = total).  W <= a few hundred: one thread.
+__global__ void rle_image_scan_kernel(const long long *__restrict__ win_bytes, int W, long long *__restrict__ img_off)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        long long acc = 0;
+        for (int w = 0; w < W; w++) { img_off[w] = acc; acc += win_bytes[w]; }
+        img_off[W] = acc;
+    }
+}
+
+template <bool EMIT> __global__ void __launch_bounds__(256) rle_kernel(const RleParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int nvec = P.T * P.W * 2;
+    for (int vec = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; vec < nvec; vec += (gridDim.x * blockDim.x) >> 5) {
+        const int ab = vec & 1, tw = vec >> 1; // tw = k*W + w
+        const float *v = (ab ? P.beta : P.alpha) + (size_t)tw * P.N;
+        float *vals = nullptr;
+        int *lens = nullptr;
+        const int N = P.N;
+        if (EMIT) {
+            const int w = tw % P.W;
+            const int Ka = P.K[2 * tw], Kb = P.K[2 * tw + 1];
+            char *blk = P.image + P.img_off[w] + P.rec_off[tw];
+            char *rec = blk + 8 + (ab ? 28 + 8 * (size_t)Ka : 0);
+            const int K = ab ? Kb : Ka;
+            if (lane == 0) {
+                if (!ab) {
+                    reinterpret_cast<int *>(blk)[0] = P.wb[w];
+                    reinterpret_cast<int *>(blk)[1] = P.wb[w + 1] - 1;
+                }
+                // records are 4-byte aligned only: write the two size_t fields as 32-bit halves
+                int *h = reinterpret_cast<int *>(rec);
+                h[0] = 1; h[1] = 0; h[2] = N; h[3] = 0;
+                h[4] = (ab ? P.site_end : P.site_begin)[tw];
+                reinterpret_cast<float *>(rec)[5] = (ab ? P.ls_beta : P.ls_alpha)[tw];
+                h[6] = K;
+            }
+            vals = reinterpret_cast<float *>(rec + 28);
+            lens = reinterpret_cast<int *>(rec + 28 + 4 * (size_t)K);
+        }
+        float head = v[0];
+        int k = 0, runlen = 1;
+        if (EMIT && lane == 0) vals[0] = head;
+        for (int j0 = 1; j0 < N; j0 += 32) {
+            const int idx = j0 + lane;
+            const bool valid = idx < N;
+            const float x = valid ? v[idx] : 0.f;
+            const int nvalid = min(32, N - j0);
+            int cur = 0; // first lane not yet assigned to a run
+            for (;;) {
+                const float mn = fminf(head, x); // std::min for non-NaN inputs
+                const bool merge = (double)fabsf(head - x) < 1e-3 * (double)mn;
+                const unsigned mask = __ballot_sync(0xffffffffu, valid && lane >= cur && !merge);
+                if (mask == 0) {
+                    runlen += nvalid - cur;
+                    break;
+                }
+                const int f = __ffs(mask) - 1;
+                runlen += f - cur;
+                if (EMIT && lane == 0) lens[k] = runlen;
+                k++;
+                head = __shfl_sync(0xffffffffu, x, f);
+                runlen = 1;
+                if (EMIT && lane == 0) vals[k] = head;
+                cur = f + 1;
+            }
+        }
+        if (EMIT) { if (lane == 0) lens[k] = runlen; }
+        else if (lane == 0) P.K[vec] = k + 1;
+    }
+}
+
 } // namespace rp

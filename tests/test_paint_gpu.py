@@ -200,6 +200,53 @@ def test_target_range_invariance_and_determinism():
         assert np.array_equal(getattr(full, name), np.concatenate([getattr(a, name), getattr(b, name)])), name
 
 
+def host_records(g, wb, k_lo, k_hi, w):
+    """The bytes targets [k_lo,k_hi) add to relate_<w>.bin, built with the host codec from pre-RLE stepping stones."""
+    out = bytearray()
+    N = g.alpha.shape[2]
+    for k in range(k_lo, k_hi):
+        out += struct.pack("<ii", int(wb[w]), int(wb[w + 1]) - 1)
+        for vec, site, ls in ((g.alpha[k, w], g.site_begin[k, w], g.ls_alpha[k, w]), (g.beta[k, w], g.site_end[k, w], g.ls_beta[k, w])):
+            vals, lens = capi.rle_encode(vec)
+            out += struct.pack("<QQifi", 1, N, int(site), float(ls), len(vals)) + vals.tobytes() + lens.tobytes()
+    return bytes(out)
+
+
+@pytest.mark.parametrize("N,L,W,seed,nk", [(8, 2500, 4, 1, None), (100, 1500, 6, 4, None), (1000, 1500, 4, 5, 300),
+                                           (1056, 900, 3, 6, 77), (2100, 900, 3, 8, 40), (5000, 400, 2, 9, 20)])
+def test_device_record_encoder_is_byte_exact(N, L, W, seed, nk):
+    """rle_kernel (device DumpToFile) == the host codec on the same stepping stones, byte for byte; the host codec is
+    pinned to the reference's in tests/test_capi_cpu.py."""
+    hap, r, wb = make_case(N, L, W, seed)
+    nk = N if nk is None else nk
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        g = c.paint_targets(0, nk)
+        imgs, st = c.paint_records(0, nk)
+        assert len(imgs) == W
+        for w in range(W):
+            assert imgs[w] == host_records(g, wb, 0, nk, w), (w, len(imgs[w]))
+        # a sub-range gives the corresponding slice of every file
+        lo = nk // 3
+        sub, _ = c.paint_records(lo, nk)
+        for w in range(W):
+            assert sub[w] == host_records(g, wb, lo, nk, w)
+
+
+def test_device_record_encoder_run_rule_edges():
+    """Constant vectors (one run), strictly alternating vectors (N runs) and runs crossing 32-lane groups."""
+    N, L = 96, 40
+    hap = np.full((L, N), ord("0"), np.uint8)
+    hap[5:35:3, ::2] = ord("1")
+    hap[7:33:5, 1::7] = ord("1")
+    r = np.full(L, 1e-4)
+    wb = np.array([0, 13, 27, L], np.int32)
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        g = c.paint_targets(0, N)
+        imgs, _ = c.paint_records(0, N)
+    for w in range(3):
+        assert imgs[w] == host_records(g, wb, 0, N, w)
+
+
 def test_unsupported_sizes_fail_loudly():
     hap = np.full((40, 33000), ord("0"), np.uint8)
     with pytest.raises(capi.PaintError) as e:
