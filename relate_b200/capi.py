@@ -13,7 +13,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librelate_paint.so")
+LIB_PATH = os.environ.get("RELATE_PAINT_LIB") or os.path.join(_HERE, "librelate_paint.so")
 
 RP_FP64 = 1
 

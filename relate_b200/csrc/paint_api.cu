@@ -463,6 +463,13 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     P.cf.inv_ntheta = (float)P.cd.inv_ntheta;
     P.cf.lower = (float)P.cd.lower;
     P.cf.upper = (float)P.cd.upper;
+    {   // headroom of the fixed-point REDUX sum: S_new <= S_prev*(1 + N*c'), N*c' <= 2*99/(1-theta); S_prev < 2^(E+1)
+        const double growth = 2.0 * (1.0 + 2.0 * 99.0 / ntheta);
+        P.hshift = (int)ceil(log2(growth)) + 1;
+        if (P.hshift > 20) return fail(RP_EUNSUPPORTED, "theta too close to 1 for the fp32 painter (use RP_FP64)");
+        P.k1c = (277 - P.hshift) << 23;
+        P.k2c = (P.hshift - 23) * (1 << 23);
+    }
     int ctas = 0;
     RP_TRY(launch_paint(c, P, lp, c->scratch, ctas));
     launches += 1;

@@ -342,7 +342,7 @@ __global__ void tables_kernel(ENT *__restrict__ ent, const long long *__restrict
 
 // ---------------------------------------------------------------------------------------
 // Per-step table entries.
-struct EntF { // fp32 mode
+struct __align__(8) EntF { // fp32 mode
     int site;
     float c;
     __device__ __forceinline__ void set_c(double v) { c = (float)v; }
@@ -391,6 +391,8 @@ struct PaintParams {
     float *ls_alpha, *ls_beta; // [nt][W]
     int *queue;            // two job counters: [0] forward, [1] backward
     double *scratch;       // fp64 mode only: [gridDim.x][N] staging rows for backward stepping stones
+    int hshift;            // fixed-point headroom of the REDUX sum: S_new < 2^hshift * 2^floor(log2 S_prev) always
+    int k1c, k2c;          // (277-hshift)<<23 and (hshift-23)<<23: exponent arithmetic of the fixed-point scale
     PaintConsts<float> cf;
     PaintConsts<double> cd;
 };
@@ -442,11 +444,17 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int TT = blockDim.x, TW = TT >> 5;
     const PaintConsts<T> &K = paint_consts<T>(P);
-    const T tau = K.tau;
+    // loop constants live in registers (opaque to the compiler, which would otherwise re-read the constant bank
+    // every step)
+    T tau = K.tau, band_lo = K.lower, band_hi = K.upper;
+    opaque(tau);
+    opaque(band_lo);
+    opaque(band_hi);
     const Ent *ents = reinterpret_cast<const Ent *>(P.ent);
     T *scratch = reinterpret_cast<T *>(P.scratch) + (size_t)blockIdx.x * P.N; // dereferenced in fp64 mode only
     int *queue = P.queue + DIR;
-    const unsigned rowbytes = (unsigned)P.wps * 4u;
+    unsigned rowbytes = (unsigned)P.wps * 4u;
+    asm volatile("" : "+r"(rowbytes));
 
     // Long-lived per-thread facts are kept as multipliers / opaque registers rather than predicates: R2P
     // rewrites P0-P6 four times per word, so a predicate cannot survive a step, and ptxas would otherwise
@@ -519,6 +527,14 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             for (int e = 0; e < 16; e++) a[j][e] = RT::mk((T)0, (T)0);
         T tl = (T)0;
         double lsr = 0.0; // log-scale added by rescaling
+        // fixed-point scale of the REDUX sum (fp32 single-warp teams), from the exponent of the previous sum
+        float k1 = 0.f, k2 = 0.f;
+        auto set_scale = [&](float sprev) {
+            const int ebs = __float_as_int(sprev) & 0x7f800000;
+            k1 = __int_as_float(P.k1c - ebs);   // 2^(23 - hshift - E)
+            k2 = __int_as_float(ebs + P.k2c);   // 2^(E + hshift - 23)
+        };
+        if (!MULTI && sizeof(T) == 4) set_scale(DIR ? (float)P.N : 1.0f);
 
         // x <- (x + R) * (mis ? tau : 1);  returns the team-wide sum.  mis = target derived && reference
         // ancestral; tdm is all-ones when the target is derived at the site (always, except SNP 0 / L-1).
@@ -561,7 +577,27 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             return S;
         };
         // team-wide sum: warp butterfly, then (multi-warp teams) one bar.sync and a shared-memory exchange
-        auto reduce = [&](T S, int parity) -> T {
+        auto reduce = [&](T S, int parity, bool &lowprec) -> T {
+            if (!MULTI && sizeof(T) == 4) {
+                // Single-warp fp32 teams: the 32 lane sums are added as 46-bit fixed point with two integer REDUX
+                // (exact, order-free) instead of a 5-level shuffle butterfly (150 -> ~70 cycles of dependent latency).
+                // The scale comes from the previous step's sum: 0 <= S < 2^hshift * 2^floor(log2 S_prev), because
+                // S_new <= S_prev * (1 + N*c) and N*c <= 2*0.99/0.01 (rho cap) / (1-theta).  hi/lo are 23-bit halves
+                // taken with the 2^23 / 1.5*2^23 magic-number roundings; every operation up to the I2F is exact, the
+                // lanes' roundings to the 2^-46 grid add up to <= 16 units.  When the sum fell so far below the scale
+                // that fewer than 2^29 units are left (the vector lost > 2^(17-hshift) of its mass in one step),
+                // `lowprec` sends the step through the rare-path handler, which redoes the sum with the butterfly, so
+                // the result always carries fp32 precision.
+                const float sl = (float)S;
+                const float a = fmaf(sl, k1, 8388608.0f);
+                const float ah = a - 8388608.0f;
+                const float rem = fmaf(sl, k1, -ah);
+                const float b = fmaf(rem, 8388608.0f, 12582912.0f);
+                const int sa = __reduce_add_sync(0xffffffffu, __float_as_int(a)) - (int)(32u * 0x4B000000u);
+                const int sb = __reduce_add_sync(0xffffffffu, __float_as_int(b)) - (int)(32u * 0x4B400000u);
+                lowprec = sa < 64; // handled on the rare path (the step is redone with the butterfly)
+                return (T)(fmaf((float)sb, 1.0f / 8388608.0f, (float)sa) * k2);
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
             if (MULTI) {
@@ -620,7 +656,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         // ---- pipeline state ---------------------------------------------------------------------------
         // Two register sets (A/B) alternate between consecutive steps, so nothing is moved between steps:
         // while step p computes from set X, the genotype words of step p+1 are loaded into set Y (their site
-        // index was loaded during step p-1) together with c_{p+1} and the site index of step p+2.
+        // index was loaded during step p-1) together with entry p+2 (site index and c, one vector load).
         // Entries up to 2 past either end of the target's list are read and never used (the table is padded).
         uint32_t wA[WPT], wB[WPT], twA = 0, twB = 0;
         int sA, sB;   // site index whose words go INTO set A / B next
@@ -630,7 +666,8 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         cA = (T)pe[0].c;
         sB = pe[ES].site;  // step 1's words go into set B during step 0
         sA = 0;
-        cB = (T)0;
+        cB = (T)pe[ES].c;
+        const Ent *pnx = pe + 2 * ES; // entry p+2 while step p runs
 
         T R = DIR ? (T)1 : K.prior_n; // step 0 is x = (0 + R0) * m
         uint32_t tdm = td_first;
@@ -657,7 +694,14 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         int pev = 1; // the handler always runs after step 0 (it switches the allele mask to all-ones)
 
         // rare path, run between step p and step p+1
-        auto handler = [&](int p, T S, T cthis) {
+        auto handler = [&](int p, T S, T cthis, T Sl, bool lowprec) {
+            if (!MULTI && sizeof(T) == 4 && lowprec) { // the fixed-point sum ran out of bits: redo it in floating point
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) Sl += __shfl_xor_sync(0xffffffffu, Sl, o);
+                S = Sl;
+                R = S * cthis;
+                set_scale((float)S);
+            }
             const T B = chk * S;
             bool rescaled = false;
             if (p == 0) tdm = 0xffffffffu; // steps 1..m-1 visit sites where the target is derived
@@ -679,6 +723,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 }
                 lsr += DIR ? (double)fast_log_dev((float)B) : log((double)B);
                 R = resc_R * cthis;
+                if (!MULTI && sizeof(T) == 4) set_scale((float)resc_R); // the state now sums to 1 (forward) or 1/ntheta
             }
             if (DIR && post) { // finalise the backward stepping stone(s) of step p: divide by B if it rescaled
                 for (int qq = q; qq < q1; qq++) {
@@ -737,17 +782,26 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         // one step computing from set X while filling set Y
         auto do_step = [&](int p, uint32_t (&wX)[WPT], uint32_t &twX, T &cX, int &sX,
                            uint32_t (&wY)[WPT], uint32_t &twY, T &cY, int &sY) {
-            // loads for later steps first: words of step p+1 into Y, c_{p+1}, site of step p+2 (-> X's next fill)
+            // loads for later steps first: words of step p+1 into Y, entry p+2 (site -> X's next fill, c -> X's next step)
             load_words(wY, gthr + (size_t)(unsigned)sY * rowbytes);
             if (MULTI ? tail_warp : has_tail) twY = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)sY * rowbytes);
-            cY = (T)pe[(p + 1) * ES].c;
-            sX = pe[(p + 2) * ES].site;
-            const T Sl = step_local(wX, twX, tdm, R);
-            const T S = reduce(Sl, p & 1);
-            R = S * cX;
-            const T B = chk * S;
-            const bool oob = (B < K.lower) || (B > K.upper);
-            if (__builtin_expect(oob || (p + 1 == pev), 0)) handler(p, S, cX);
+            // one (vector) load of entry p+2: its site is needed next step (to fetch the words of step p+2), its c at
+            // the end of step p+2, which runs on this same register set
+            const Ent e2 = *pnx;
+            pnx += ES;
+            sX = e2.site;
+            T Sl = step_local(wX, twX, tdm, R);
+            bool lowprec = false;
+            const T S = reduce(Sl, p & 1, lowprec);
+            const T ccur = cX;
+            R = S * ccur;
+            cX = (T)e2.c;
+            if (!MULTI && sizeof(T) == 4) set_scale((float)S);
+            const T B = DIR ? chk * S : S;
+            const bool oob = (B < band_lo) || (B > band_hi);
+            // the rare path is taken by all threads or none (S is the team-wide sum): tell the compiler with a vote, so
+            // the branch needs no reconvergence bookkeeping
+            if (__builtin_expect(__any_sync(0xffffffffu, oob || lowprec || (p + 1 == pev)), 0)) handler(p, S, ccur, Sl, lowprec);
         };
 
         // steps 0..m, two per iteration (even steps compute from set A, odd ones from set B)
