@@ -10,6 +10,8 @@
  *   rp_chunk_load       <- Data::Data(6 files) + --painting handling          src/data.cpp:86-97, pipeline/Paint.cpp:21-61
  *   rp_chunk_create     <- the in-memory Data the painter is handed            src/data.hpp (sequence, r, theta)
  *   rp_paint_targets    <- for(hap) FastPainting::PaintSteppingStones(...)     pipeline/Paint.cpp:81-87, src/fast_painting.cpp:18-618
+ *   rp_make_chunks      <- int MakeChunks(cxxopts::Options&) + Data::MakeChunks pipeline/MakeChunks.cpp:14-117, src/data.cpp:117-518
+ *   rp_paint_records    <- fast_painting.cpp:589-601 + DumpToFile, on the device
  *   rp_rle_encode       <- CollapsedMatrix<float>::DumpToFile (stepping stone) src/collapsed_matrix.hpp:228-265
  *   rp_fast_log_device  <- fast_log                                            src/fast_log.hpp:6-22
  *
@@ -82,6 +84,16 @@ const char *rp_version(void);
 /* Pinned host memory for callers that want full-speed PCIe copies (cudaMallocHost / cudaFreeHost). */
 int rp_host_alloc(size_t bytes, void **out);
 void rp_host_free(void *p);
+
+/* ---- loader (SURVEY.md 8 "next" row f2) -------------------------------------------------------------
+ * `Relate --mode MakeChunks`: SHAPEIT haps/sample (plain or gzip) + genetic map -> <out_dir>/parameters.bin,
+ * props.bin, parameters_c<c>.bin and chunk_<c>.{hap,state,bp,dist,rpos,r}, byte-identical to the reference's
+ * (same chunk / window boundary rules, data.cpp:129-229).  dist may be NULL ("unspecified"); transversion != 0
+ * is the --transversion flag; memory_gb is --memory (reference default 5).  Like the reference it refuses an
+ * existing out_dir and creates it with mode 0700.  Host-only.  n_chunks / warnings (a caller-provided buffer
+ * for the lines the reference prints to stderr) may be NULL. */
+int rp_make_chunks(const char *haps, const char *sample, const char *map, const char *dist, const char *out_dir,
+                   int transversion, float memory_gb, int *n_chunks, char *warnings, size_t warnings_cap);
 
 /* ---- chunk lifetime ---------------------------------------------------------------- */
 /* hap: L*N chars '0'/'1', SNP-major (Data::sequence); r: L doubles, already multiplied by rho;

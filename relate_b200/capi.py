@@ -76,6 +76,8 @@ SYMBOLS = {
     "rp_window_distance": (C.c_int, [_P, C.c_int, _P]),
     "rp_window_rows": (C.c_longlong, [_P]),
     "rp_window_close": (None, [_P]),
+    "rp_make_chunks": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_float,
+                                 C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
     "rp_rle_encode": (C.c_int, [_P, C.c_int, _P, _P]),
     "rp_fast_log_device": (C.c_int, [C.c_int, _P, _P, C.c_int]),
     "rp_debug_pack": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int), _P, C.POINTER(C.c_int)]),
@@ -287,6 +289,16 @@ def paint_chunk(out_dir: str, chunk_index: int, painting: str | None = None, dev
     check(lib().rp_paint_chunk(out_dir.encode(), chunk_index, painting.encode() if painting is not None else None,
                                _ptr(dev), n, RP_FP64 if fp64 else 0, C.byref(st)))
     return st.as_dict()
+
+
+def make_chunks(haps: str, sample: str, gmap: str, out_dir: str, dist: str | None = None, transversion: bool = False,
+                memory_gb: float = 5.0):
+    """``Relate --mode MakeChunks`` (host-only): -> (number of chunks, the warnings the reference prints to stderr)."""
+    n = C.c_int(0)
+    buf = C.create_string_buffer(4096)
+    check(lib().rp_make_chunks(haps.encode(), sample.encode(), gmap.encode(), dist.encode() if dist else None,
+                               out_dir.encode(), int(transversion), memory_gb, C.byref(n), buf, len(buf)))
+    return n.value, buf.value.decode()
 
 
 def rle_encode(v: np.ndarray):

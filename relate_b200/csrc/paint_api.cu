@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "host_io.hpp"
+#include "make_chunks.hpp"
 #include "paint_kernels.cuh"
 
 namespace {
@@ -742,6 +743,27 @@ int rp_paint_from_host(int device, int N, int L, const char *hap, const double *
     g_err = keep;
     if (stats) stats->ms_total = now_ms() - t0;
     return rc;
+}
+
+int rp_make_chunks(const char *haps, const char *sample, const char *map, const char *dist, const char *out_dir,
+                   int transversion, float memory_gb, int *n_chunks, char *warnings, size_t warnings_cap)
+{
+    if (!haps || !sample || !map || !out_dir) return fail(RP_EINVAL, "Needed: haps, sample, map, output.");
+    const std::string out = out_dir;
+    struct stat sb;
+    if (stat((out + "/").c_str(), &sb) == 0) // pipeline/MakeChunks.cpp:38-43
+        return fail(RP_EINVAL, "Error: Directory " + out + " already exists. Relate will use this directory to store temporary files.");
+    if (mkdir(out.c_str(), 0700) != 0) return fail(RP_EIO, "could not create directory " + out);
+    rp::MakeChunksInfo info;
+    const std::string err = rp::make_chunks(haps, sample, map, dist ? dist : "unspecified", out, transversion == 0, memory_gb, &info);
+    if (!err.empty()) return fail(err.rfind("Failed to open", 0) == 0 || err.rfind("cannot", 0) == 0 ? RP_EIO : RP_EINVAL, err);
+    if (n_chunks) *n_chunks = info.num_chunks;
+    if (warnings && warnings_cap > 0) {
+        const size_t n = std::min(warnings_cap - 1, info.warnings.size());
+        memcpy(warnings, info.warnings.data(), n);
+        warnings[n] = 0;
+    }
+    return RP_OK;
 }
 
 int rp_rle_encode(const float *v, int n, float *vals, int *lens)

@@ -4,8 +4,9 @@
 //   * the same flag set (Relate.cpp:19-45) is accepted; unknown flags are an error, as with cxxopts;
 //   * `--mode Paint` (Relate.cpp:64-79 -> pipeline/Paint.cpp:17-108) runs natively on the GPUs through
 //     the C ABI in include/relate_paint.h;
-//   * `--mode All` (Relate.cpp:190-296) keeps the reference's stage order, with Paint native and every
-//     other stage delegated to the reference binary;
+//   * `--mode MakeChunks` (Relate.cpp:60-63 -> pipeline/MakeChunks.cpp:14-117) runs natively (host code, rp_make_chunks);
+//   * `--mode All` (Relate.cpp:190-296) keeps the reference's stage order, with MakeChunks and Paint native and
+//     every other stage delegated to the reference binary;
 //   * every other mode is handed to the reference binary unchanged (exec).
 // The reference binary is found via $RELATE_REFERENCE_BIN, else "<dir of this exe>/Relate.ref".
 // Extra flags of this build (stripped before delegating): --gpus a,b,c   --fp64
@@ -220,10 +221,45 @@ int paint(const Args &a, int chunk_index)
     rusage usage;
     getrusage(RUSAGE_SELF, &usage);
     std::cerr << "GPU Paint: " << devs.size() << " device(s), " << st.n_targets << " targets, kernel " << std::fixed
-              << std::setprecision(3) << st.ms_paint << " ms, prep " << st.ms_prep << " ms, encode+write " << st.ms_encode
+              << std::setprecision(3) << st.ms_paint << " ms, prep " << st.ms_prep << " ms, record encoder " << st.ms_rle << " ms, file writes " << st.ms_write
               << " ms, total " << st.ms_total << " ms." << std::endl;
     std::cerr << "CPU Time spent: " << usage.ru_utime.tv_sec << "." << std::setfill('0') << std::setw(6) << usage.ru_utime.tv_usec
               << "s; Max Memory usage: " << std::setprecision(6) << usage.ru_maxrss / 1000.0 << "Mb." << std::endl;
+    std::cerr << "---------------------------------------------------------" << std::endl << std::endl;
+    return 0;
+}
+
+// pipeline/MakeChunks.cpp:14-117 behind the C ABI
+int make_chunks(const Args &a)
+{
+    bool help = false;
+    if (!a.count("haps") || !a.count("sample") || !a.count("map") || !a.count("output")) {
+        std::cout << "Not enough arguments supplied." << std::endl;
+        std::cout << "Needed: haps, sample, map, output. Optional: memory, dist, transversion." << std::endl;
+        help = true;
+    }
+    if (a.count("help") || help) {
+        print_help();
+        std::cout << "Use to make smaller chunks from the data." << std::endl;
+        return 0;
+    }
+    std::cerr << "---------------------------------------------------------" << std::endl;
+    std::cerr << "Parsing data.." << std::endl;
+    char warnings[4096];
+    warnings[0] = 0;
+    const float mem = a.count("memory") ? strtof(a.get("memory").c_str(), nullptr) : 5.0f;
+    const int rc = rp_make_chunks(a.get("haps").c_str(), a.get("sample").c_str(), a.get("map").c_str(),
+                                  a.count("dist") ? a.get("dist").c_str() : nullptr, a.get("output").c_str(),
+                                  a.count("transversion") ? 1 : 0, mem, nullptr, warnings, sizeof warnings);
+    if (rc != RP_OK) {
+        std::cerr << rp_last_error() << std::endl;
+        return 1;
+    }
+    std::cerr << warnings;
+    rusage usage;
+    getrusage(RUSAGE_SELF, &usage);
+    std::cerr << "CPU Time spent: " << usage.ru_utime.tv_sec << "." << std::setfill('0') << std::setw(6) << usage.ru_utime.tv_usec
+              << "s; Max Memory usage: " << usage.ru_maxrss / 1000.0 << "Mb." << std::endl;
     std::cerr << "---------------------------------------------------------" << std::endl << std::endl;
     return 0;
 }
@@ -256,6 +292,8 @@ int main(int argc, char **argv)
     }
     const std::string ref = reference_binary(argv[0]);
 
+    if (mode == "MakeChunks") return make_chunks(a);
+
     if (mode == "Paint") {
         bool help = false;
         if (!a.count("chunk_index") || !a.count("output")) { // Relate.cpp:66-76
@@ -280,7 +318,7 @@ int main(int argc, char **argv)
         if (a.count("chunk_index")) {
             start_chunk = end_chunk = atoi(a.get("chunk_index").c_str());
         } else {
-            int rc = run_reference(ref, with_mode(a, "MakeChunks"));
+            int rc = make_chunks(a);
             if (rc != 0) return rc;
             int hdr[3];
             if (!read_ints(out + "/parameters.bin", hdr, 3)) {

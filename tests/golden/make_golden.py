@@ -12,6 +12,8 @@ Fixtures (all produced by the UNMODIFIED reference binary oracle/_ref/Relate):
                      painted by the reference with --painting 0.001,1 and without the flag; dlens_ref/ holds the
                      distance matrices the reference's DistanceMeasure::GetMatrix derives from those paint files
                      (windows 1 and 3, every 61st SNP), written by oracle/_ref/dlens.
+  makechunks_synth.json  md5 of every file the reference's MakeChunks writes for a 24 x 1200 synthetic text data set
+                     (one chunk, several windows; inputs regenerated from the seed by tests/test_makechunks_cpu.py).
 """
 import gzip
 import hashlib
@@ -116,5 +118,25 @@ def main():
     print("golden fixtures written,", total, "bytes")
 
 
+def make_makechunks_fixture():
+    """md5 of every file the reference's MakeChunks writes for a small synthetic text data set (the inputs are
+    regenerated by tests/test_makechunks_cpu.py's writers from the seed)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_makechunks_cpu as t
+    from relate_b200 import synth
+    N, L, seed, mem = 24, 1200, 9, 0.0002
+    tmp = tempfile.mkdtemp()
+    hap, bp = synth.block_kingman(N, L, seed)
+    hp, sp = t.write_haps(tmp, hap, bp)
+    mp = t.write_map(tmp, bp)
+    md5s = t.run_ref(tmp, ["--haps", hp, "--sample", sp, "--map", mp, "--memory", repr(mem)])
+    json.dump({"N": N, "L": L, "seed": seed, "memory": mem, "md5": md5s}, open(os.path.join(HERE, "makechunks_synth.json"), "w"), indent=1)
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "makechunks":  # only the MakeChunks fixture
+        make_makechunks_fixture()
+    else:
+        main()
+        make_makechunks_fixture()
