@@ -159,6 +159,10 @@ typedef struct rp_window rp_window;
  * 0..N-1; ls_alpha, ls_beta: float [N]; rpos: double [L+1] (chunk_<c>.rpos). */
 int rp_window_open(rp_chunk *c, int w, const float *alpha, const float *beta, const float *ls_alpha,
                    const float *ls_beta, const double *rpos, rp_window **out, rp_stats *stats);
+/* Same, from the stepping stones still resident in HBM: the last paint call on the chunk must have covered targets
+ * 0..N-1 (rp_paint_targets_device(c, 0, N, ...)).  The codec's lossy collapse (what a reader of the paint files
+ * sees) is applied on the device, so the result is bit-identical to writing the files and opening them. */
+int rp_window_open_resident(rp_chunk *c, int w, const double *rpos, rp_window **out, rp_stats *stats);
 /* Same, reading <out_dir>/chunk_<c>/paint/relate_<w>.bin and chunk_<c>.rpos. */
 int rp_window_open_files(rp_chunk *c, const char *out_dir, int chunk_index, int w, rp_window **out, rp_stats *stats);
 int rp_window_distance(rp_window *win, int snp, float *d);

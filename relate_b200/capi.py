@@ -72,6 +72,7 @@ SYMBOLS = {
     "rp_paint_chunk": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, _P, C.c_int, C.c_uint, C.POINTER(RpStats)]),
     "rp_release_cache": (None, []),
     "rp_window_open": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(RpStats)]),
+    "rp_window_open_resident": (C.c_int, [_P, C.c_int, _P, C.POINTER(_P), C.POINTER(RpStats)]),
     "rp_window_open_files": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(RpStats)]),
     "rp_window_distance": (C.c_int, [_P, C.c_int, _P]),
     "rp_window_rows": (C.c_longlong, [_P]),
@@ -226,6 +227,14 @@ class Window:
     def open_files(cls, chunk: DeviceChunk, out_dir: str, chunk_index: int, w: int) -> "Window":
         h, st = C.c_void_p(), RpStats()
         check(lib().rp_window_open_files(chunk._h, out_dir.encode(), chunk_index, w, C.byref(h), C.byref(st)))
+        return cls(chunk, h, st.as_dict())
+
+    @classmethod
+    def open_resident(cls, chunk: DeviceChunk, w: int, rpos) -> "Window":
+        """From the stepping stones of the last ``paint_targets_device(0, N)`` still in HBM (no paint files)."""
+        rpos = np.ascontiguousarray(rpos, np.float64)
+        h, st = C.c_void_p(), RpStats()
+        check(lib().rp_window_open_resident(chunk._h, w, _ptr(rpos), C.byref(h), C.byref(st)))
         return cls(chunk, h, st.as_dict())
 
     @classmethod

@@ -105,6 +105,7 @@ struct rp_chunk {
     DevBuf rleK, rec_off, win_bytes, img_off, image;
     std::vector<long long> h_img_off; // W+1 offsets of the last encoded batch
     int enc_targets = 0;              // targets in c->image (0: none)
+    bool resident_all = false;        // alpha/beta/lsa/lsb hold the stepping stones of ALL targets (last paint was 0..N)
     long long *h_total = nullptr; // pinned
     cudaStream_t stream = nullptr;       // the stream every copy and kernel of this chunk is issued on
     cudaStream_t own_stream = nullptr;   // created by the library; `stream` may be replaced by a caller's
@@ -472,7 +473,9 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
         P.k2c = (P.hshift - 23) * (1 << 23);
     }
     int ctas = 0;
+    c->resident_all = false;
     RP_TRY(launch_paint(c, P, lp, c->scratch, ctas));
+    c->resident_all = (k0 == 0 && k1 == N);
     launches += 1;
     RP_CUDA(cudaEventRecord(c->ev[2], s));
     RP_CUDA(cudaStreamSynchronize(s));
@@ -851,10 +854,16 @@ struct rp_window {
     DevBuf top, ls, rowoff, rpos, d, ab, be, lsa, lsb;
 };
 
-int rp_window_open(rp_chunk *c, int w, const float *alpha, const float *beta, const float *ls_alpha,
-                   const float *ls_beta, const double *rpos, rp_window **out, rp_stats *stats)
+// alpha == nullptr: take the stepping stones of window w from the chunk's HBM buffers (last paint covered all targets)
+// and apply the codec's collapse (every element becomes the head of its run) on the device.
+static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float *beta, const float *ls_alpha,
+                            const float *ls_beta, const double *rpos, rp_window **out, rp_stats *stats)
 {
-    if (!c || !alpha || !beta || !ls_alpha || !ls_beta || !rpos || !out) return fail(RP_EINVAL, "null argument");
+    const bool resident = alpha == nullptr;
+    if (!c || !rpos || !out) return fail(RP_EINVAL, "null argument");
+    if (!resident && (!beta || !ls_alpha || !ls_beta)) return fail(RP_EINVAL, "null argument");
+    if (resident && !c->resident_all)
+        return fail(RP_EINVAL, "the chunk does not hold the stepping stones of all targets (paint targets 0..N first)");
     if (w < 0 || w >= c->W) return fail(RP_EINVAL, "window index out of range");
     if (c->flags & RP_FP64) return fail(RP_EUNSUPPORTED, "window repaint runs with fp32 state");
     *out = nullptr;
@@ -900,10 +909,17 @@ int rp_window_open(rp_chunk *c, int w, const float *alpha, const float *beta, co
     RP_CUDAW(cudaEventRecord(c->ev[0], s));
     RP_CUDAW(cudaMemcpyAsync(win->rowoff.p, rowoff.data(), rowoff.size() * 8, cudaMemcpyHostToDevice, s));
     RP_CUDAW(cudaMemcpyAsync(win->rpos.p, rpos, ((size_t)L + 1) * 8, cudaMemcpyHostToDevice, s));
-    RP_CUDAW(cudaMemcpyAsync(win->ab.p, alpha, nn * 4, cudaMemcpyHostToDevice, s));
-    RP_CUDAW(cudaMemcpyAsync(win->be.p, beta, nn * 4, cudaMemcpyHostToDevice, s));
-    RP_CUDAW(cudaMemcpyAsync(win->lsa.p, ls_alpha, (size_t)N * 4, cudaMemcpyHostToDevice, s));
-    RP_CUDAW(cudaMemcpyAsync(win->lsb.p, ls_beta, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    if (!resident) {
+        RP_CUDAW(cudaMemcpyAsync(win->ab.p, alpha, nn * 4, cudaMemcpyHostToDevice, s));
+        RP_CUDAW(cudaMemcpyAsync(win->be.p, beta, nn * 4, cudaMemcpyHostToDevice, s));
+        RP_CUDAW(cudaMemcpyAsync(win->lsa.p, ls_alpha, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+        RP_CUDAW(cudaMemcpyAsync(win->lsb.p, ls_beta, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    } else {
+        const unsigned grid = (unsigned)std::min<long long>(((long long)2 * N + 7) / 8, (long long)c->sm_count * 64);
+        rp::collapse_kernel<<<grid, 256, 0, s>>>(c->alpha.as<float>(), c->beta.as<float>(), c->lsa.as<float>(), c->lsb.as<float>(), N, W, w,
+                                                 win->ab.as<float>(), win->be.as<float>(), win->lsa.as<float>(), win->lsb.as<float>());
+        RP_CUDAW(cudaGetLastError());
+    }
     RP_CUDAW(cudaMemsetAsync(c->queue.p, 0, 8, s));
     RP_CUDAW(cudaEventRecord(c->ev[1], s));
     rp::RepaintParams P{};
@@ -950,8 +966,8 @@ int rp_window_open(rp_chunk *c, int w, const float *alpha, const float *beta, co
         cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
         stats->ms_h2d += a;
         stats->ms_paint += b; // the repaint kernel
-        stats->h2d_bytes += (long long)(2 * nn * 4 + ((size_t)L + 1) * 8);
-        stats->launches += 1;
+        stats->h2d_bytes += (long long)((resident ? 0 : 2 * nn * 4) + ((size_t)L + 1) * 8);
+        stats->launches += resident ? 2 : 1;
         stats->n_targets = N;
         stats->team_threads = lp.threads;
         stats->words_per_thread = lp.wpt;
@@ -962,6 +978,18 @@ int rp_window_open(rp_chunk *c, int w, const float *alpha, const float *beta, co
     *out = win;
     return RP_OK;
 #undef RP_CUDAW
+}
+
+int rp_window_open(rp_chunk *c, int w, const float *alpha, const float *beta, const float *ls_alpha,
+                   const float *ls_beta, const double *rpos, rp_window **out, rp_stats *stats)
+{
+    if (!alpha) return fail(RP_EINVAL, "null argument");
+    return window_open_impl(c, w, alpha, beta, ls_alpha, ls_beta, rpos, out, stats);
+}
+
+int rp_window_open_resident(rp_chunk *c, int w, const double *rpos, rp_window **out, rp_stats *stats)
+{
+    return window_open_impl(c, w, nullptr, nullptr, nullptr, nullptr, rpos, out, stats);
 }
 
 int rp_window_open_files(rp_chunk *c, const char *out_dir, int chunk_index, int w, rp_window **out, rp_stats *stats)

@@ -1361,4 +1361,43 @@ template <bool EMIT> __global__ void __launch_bounds__(256) rle_kernel(const Rle
     }
 }
 
+// What a reader of the paint files sees (CollapsedMatrix<float>::ReadFromFile, collapsed_matrix.hpp:268-296): every
+// element replaced by the head of its run under DumpToFile's rule.  Applied here to the stepping stones of window w
+// while they are still in HBM (alpha/beta [T][W][N] of all T = N targets), so the window repaint can start from them
+// without the round trip through the paint files and yet from bit-identical inputs.  One warp per vector.
+__global__ void __launch_bounds__(256) collapse_kernel(const float *__restrict__ alpha, const float *__restrict__ beta,
+                                                       const float *__restrict__ lsa, const float *__restrict__ lsb, int N,
+                                                       int W, int w, float *__restrict__ oa, float *__restrict__ ob,
+                                                       float *__restrict__ olsa, float *__restrict__ olsb)
+{
+    const int lane = threadIdx.x & 31;
+    for (int vec = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; vec < 2 * N; vec += (gridDim.x * blockDim.x) >> 5) {
+        const int ab = vec & 1, k = vec >> 1;
+        const float *v = (ab ? beta : alpha) + ((size_t)k * W + w) * N;
+        float *o = (ab ? ob : oa) + (size_t)k * N;
+        if (lane == 0) (ab ? olsb : olsa)[k] = (ab ? lsb : lsa)[(size_t)k * W + w];
+        float head = v[0];
+        if (lane == 0) o[0] = head;
+        for (int j0 = 1; j0 < N; j0 += 32) {
+            const int idx = j0 + lane;
+            const bool valid = idx < N;
+            const float x = valid ? v[idx] : 0.f;
+            float mine = 0.f;
+            int cur = 0;
+            for (;;) {
+                const float mn = fminf(head, x);
+                const bool merge = (double)fabsf(head - x) < 1e-3 * (double)mn;
+                const unsigned mask = __ballot_sync(0xffffffffu, valid && lane >= cur && !merge);
+                const int f = mask ? __ffs(mask) - 1 : 32;
+                if (lane >= cur && lane < f) mine = head; // joins the current run
+                if (mask == 0) break;
+                head = __shfl_sync(0xffffffffu, x, f);
+                if (lane == f) mine = head;               // heads a new run
+                cur = f + 1;
+            }
+            if (valid) o[idx] = mine;
+        }
+    }
+}
+
 } // namespace rp

@@ -467,3 +467,32 @@ def test_window_distances_vs_oracle_on_gpu_painted_files(tmp_path, N, L, W):
             with capi.Window.open_files(c, d, 0, sec) as win:
                 worst = max(float(np.abs(win.distance(snp) - ref).max()) for snp, ref in want.items())
             assert worst <= tol, (sec, worst)
+
+
+@pytest.mark.parametrize("N,L,W", [(200, 3000, 3), (1000, 1500, 2), (2100, 700, 2)])
+def test_window_from_resident_stepping_stones_equals_file_round_trip(tmp_path, N, L, W):
+    """rp_window_open_resident (device collapse of the HBM-resident stepping stones) gives bit-identical distance
+    matrices to writing the paint files and reading them back (rp_window_open_files)."""
+    d = str(tmp_path / "o")
+    synth.make_chunk_dir(d, N, L, seed=52, n_windows=W)
+    capi.paint_chunk(d, 0, "0.001,1")
+    ch = chunkio.read_chunk(d, 0)
+    rpos = np.fromfile(os.path.join(d, "chunk_0.rpos"), dtype="<f8", offset=4)
+    assert len(rpos) == L + 1
+    with capi.DeviceChunk.load(d, 0, "0.001,1") as c:
+        snps = {}
+        for sec in range(W):
+            with capi.Window.open_files(c, d, 0, sec) as win:
+                lo, hi = int(ch.wb[sec]), int(ch.wb[sec + 1]) - 1
+                snps[sec] = {s: win.distance(s) for s in (lo, (lo + hi) // 2, hi)}
+                rows = win.rows
+        with pytest.raises(capi.PaintError):  # nothing painted on this handle yet
+            capi.Window.open_resident(c, 0, rpos)
+        c.paint_targets_device(0, N)
+        for sec in range(W):
+            with capi.Window.open_resident(c, sec, rpos) as win:
+                for s, want in snps[sec].items():
+                    assert np.array_equal(win.distance(s), want), (sec, s)
+        c.paint_targets_device(0, N // 2)
+        with pytest.raises(capi.PaintError):  # only half of the targets are resident now
+            capi.Window.open_resident(c, 0, rpos)
