@@ -197,6 +197,43 @@ def cpu_baseline_sample():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def window_repaint_measure(chunk, rpos, W, peaks):
+    """SURVEY.md 8 row f1 on the same chunk: RePaintSection for all N targets of one window (repaint_kernel, HBM-bound:
+    the forward sweep writes every alpha row, the backward sweep reads it back and writes the posterior row) and
+    GetMatrix for a few SNPs (distance_kernel), from the stepping stones still resident in HBM."""
+    import numpy as np
+    from relate_b200 import capi
+    chunk.set_stream(None)
+    chunk.paint_targets_device(0, N_HAP)
+    w = W // 2
+    times = []
+    for rep in range(3):  # the first call also pays for the window's HBM allocations
+        win = capi.Window.open_resident(chunk, w, rpos)
+        times.append(win.stats["ms_paint"])
+        rows = win.rows
+        if rep < 2:
+            win.close()
+    ms = sorted(times)[1]
+    lo = int(np.asarray(chunk_wb(chunk))[w])
+    t0 = time.perf_counter()
+    nd = 8
+    for i in range(nd):
+        win.distance(lo + 11 * i)
+    ms_d = 1e3 * (time.perf_counter() - t0) / nd
+    win.close()
+    bytes_alg = 3.0 * 4.0 * N_HAP * rows + 2.0 * 4.0 * N_HAP * N_HAP
+    peak = peaks.get("hbm_gbs") or 6500.0
+    return {"window": w, "posterior_rows": int(rows), "repaint_kernel_ms": ms, "algorithmic_bytes": bytes_alg,
+            "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9, "peak_gbs": peak, "frac": bytes_alg / (ms * 1e-3) / 1e9 / peak,
+            "bound": "hbm", "distance_call_ms": ms_d,
+            "distance_call": "rp_window_distance: distance_kernel + D2H of the N x N float matrix, host wall clock",
+            "source": "stepping stones resident in HBM (rp_window_open_resident), no paint-file round trip"}
+
+
+def chunk_wb(chunk):
+    return chunk._wb
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -243,6 +280,7 @@ def main():
         stream = torch.cuda.Stream(device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
         chunk = capi.DeviceChunk.from_arrays(hap, r, wb, theta, device=local_rank)
+        chunk._wb = wb
         chunk.set_tune(words_per_thread=args.words_per_thread, ctas_per_sm=args.ctas_per_sm)
         chunk.set_stream(stream.cuda_stream)
 
@@ -332,6 +370,8 @@ def main():
                 "clocks": clocks,
                 "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             }
+            if world == 1:
+                line["window_repaint"] = window_repaint_measure(chunk, rpos, W, peaks)
             if world == 1 and not args.no_cpu_baseline:
                 cb = cpu_baseline_sample()
                 line["cpu_baseline"] = cb
