@@ -524,9 +524,9 @@ int encode_device(rp_chunk *c, int nt, rp_stats *st)
     P.rec_off = c->rec_off.as<long long>();
     P.img_off = c->img_off.as<long long>();
     const long long nvec = (long long)nw * 2;
-    const unsigned grid = (unsigned)std::min<long long>((nvec + 7) / 8, (long long)c->sm_count * 64);
+    const unsigned grid = (unsigned)std::min<long long>((nvec + 127) / 128, (long long)c->sm_count * 12);
     RP_CUDA(cudaEventRecord(c->ev[0], s));
-    rp::rle_kernel<false><<<grid, 256, 0, s>>>(P);
+    rp::rle_kernel<false><<<grid, 128, 0, s>>>(P);
     rp::rle_offsets_kernel<<<W, 256, 0, s>>>(c->rleK.as<int>(), nt, W, c->rec_off.as<long long>(),
                                              c->win_bytes.as<long long>());
     rp::rle_image_scan_kernel<<<1, 32, 0, s>>>(c->win_bytes.as<long long>(), W, c->img_off.as<long long>());
@@ -537,7 +537,7 @@ int encode_device(rp_chunk *c, int nt, rp_stats *st)
     const long long total = c->h_img_off[W];
     RP_TRY(c->image.ensure((size_t)total));
     P.image = c->image.as<char>();
-    rp::rle_kernel<true><<<grid, 256, 0, s>>>(P);
+    rp::rle_kernel<true><<<grid, 128, 0, s>>>(P);
     RP_CUDA(cudaGetLastError());
     RP_CUDA(cudaEventRecord(c->ev[1], s));
     RP_CUDA(cudaStreamSynchronize(s));

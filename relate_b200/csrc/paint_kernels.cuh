@@ -1235,9 +1235,7 @@ __global__ void __launch_bounds__(256) distance_kernel(const DistanceParams P)
 // =========================================================================================
 // Stepping-stone record codec on the device: CollapsedMatrix<float>::DumpToFile (src/collapsed_matrix.hpp:228-265).
 // A value joins the current run when fabs(head - v) < 1e-3 * min(head, v) (float difference, comparison in double);
-// otherwise it becomes the head of a new run.  The rule is sequential in the run heads only: a warp tests 32 values
-// against the current head at once, the first failing lane becomes the next head (ballot + ffs).
-// One warp per vector; `EMIT=false` counts runs, `EMIT=true` writes the record into the window's file image.
+// otherwise it becomes the head of a new run (see rle_kernel below for the parallelisation).
 // Record: size_t 1; size_t N; int site; float logscale; int K; float val[K]; int len[K]   (28 + 8K bytes)
 // File image of window w, per target: int wb[w]; int wb[w+1]-1; alpha record; beta record (fast_painting.cpp:589-601)
 struct RleParams {
@@ -1298,66 +1296,85 @@ __global__ void rle_image_scan_kernel(const long long *__restrict__ win_bytes, i
     }
 }
 
-template <bool EMIT> __global__ void __launch_bounds__(256) rle_kernel(const RleParams P)
+// One THREAD per vector: the rule is sequential in the run heads and about half of all elements start a run, so a
+// warp-per-vector scan (ballot + ffs + shuffle per head) spends ~50 cycles per element.  Here a warp owns 32 vectors;
+// it stages 32 x 32 tiles through shared memory (coalesced 128-byte row segments in, conflict-free column reads out)
+// and every lane walks its own vector with a handful of instructions per element.  `EMIT=false` counts runs,
+// `EMIT=true` writes the records; each lane appends to its own record, consecutive addresses over time, so the L2
+// merges the 4-byte stores into full sectors.
+template <bool EMIT> __global__ void __launch_bounds__(128) rle_kernel(const RleParams P)
 {
-    const int lane = threadIdx.x & 31;
-    const int nvec = P.T * P.W * 2;
-    for (int vec = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; vec < nvec; vec += (gridDim.x * blockDim.x) >> 5) {
-        const int ab = vec & 1, tw = vec >> 1; // tw = k*W + w
-        const float *v = (ab ? P.beta : P.alpha) + (size_t)tw * P.N;
+    __shared__ float tile[4][32][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float(*T)[33] = tile[wid];
+    const long long nvec = (long long)P.T * P.W * 2;
+    const int N = P.N;
+    for (long long vec0 = ((long long)blockIdx.x * 4 + wid) * 32; vec0 < nvec; vec0 += (long long)gridDim.x * 128) {
+        const long long vec = vec0 + lane;
+        const bool live = vec < nvec;
+        const int nrows = (int)min(32ll, nvec - vec0);
         float *vals = nullptr;
         int *lens = nullptr;
-        const int N = P.N;
-        if (EMIT) {
-            const int w = tw % P.W;
+        if (EMIT && live) {
+            const int ab = (int)(vec & 1);
+            const long long tw = vec >> 1; // k*W + w
+            const int w = (int)(tw % P.W);
             const int Ka = P.K[2 * tw], Kb = P.K[2 * tw + 1];
             char *blk = P.image + P.img_off[w] + P.rec_off[tw];
             char *rec = blk + 8 + (ab ? 28 + 8 * (size_t)Ka : 0);
             const int K = ab ? Kb : Ka;
-            if (lane == 0) {
-                if (!ab) {
-                    reinterpret_cast<int *>(blk)[0] = P.wb[w];
-                    reinterpret_cast<int *>(blk)[1] = P.wb[w + 1] - 1;
-                }
-                // records are 4-byte aligned only: write the two size_t fields as 32-bit halves
-                int *h = reinterpret_cast<int *>(rec);
-                h[0] = 1; h[1] = 0; h[2] = N; h[3] = 0;
-                h[4] = (ab ? P.site_end : P.site_begin)[tw];
-                reinterpret_cast<float *>(rec)[5] = (ab ? P.ls_beta : P.ls_alpha)[tw];
-                h[6] = K;
+            if (!ab) {
+                reinterpret_cast<int *>(blk)[0] = P.wb[w];
+                reinterpret_cast<int *>(blk)[1] = P.wb[w + 1] - 1;
             }
+            // records are 4-byte aligned only: write the two size_t fields as 32-bit halves
+            int *h = reinterpret_cast<int *>(rec);
+            h[0] = 1; h[1] = 0; h[2] = N; h[3] = 0;
+            h[4] = (ab ? P.site_end : P.site_begin)[tw];
+            reinterpret_cast<float *>(rec)[5] = (ab ? P.ls_beta : P.ls_alpha)[tw];
+            h[6] = K;
             vals = reinterpret_cast<float *>(rec + 28);
             lens = reinterpret_cast<int *>(rec + 28 + 4 * (size_t)K);
         }
-        float head = v[0];
+        float head = 0.f;
         int k = 0, runlen = 1;
-        if (EMIT && lane == 0) vals[0] = head;
-        for (int j0 = 1; j0 < N; j0 += 32) {
-            const int idx = j0 + lane;
-            const bool valid = idx < N;
-            const float x = valid ? v[idx] : 0.f;
-            const int nvalid = min(32, N - j0);
-            int cur = 0; // first lane not yet assigned to a run
-            for (;;) {
-                const float mn = fminf(head, x); // std::min for non-NaN inputs
-                const bool merge = (double)fabsf(head - x) < 1e-3 * (double)mn;
-                const unsigned mask = __ballot_sync(0xffffffffu, valid && lane >= cur && !merge);
-                if (mask == 0) {
-                    runlen += nvalid - cur;
-                    break;
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const int cols = min(32, N - j0);
+            __syncwarp();
+#pragma unroll 8
+            for (int rr = 0; rr < nrows; rr++) { // row rr of the tile: 128 contiguous bytes of vector vec0 + rr
+                const long long v2 = vec0 + rr;
+                const float *src = ((v2 & 1) ? P.beta : P.alpha) + (size_t)(v2 >> 1) * N + j0;
+                if (lane < cols) T[rr][lane] = src[lane];
+            }
+            __syncwarp();
+            if (live) {
+                int c = 0;
+                if (j0 == 0) {
+                    head = T[lane][0];
+                    if (EMIT) vals[0] = head;
+                    c = 1;
                 }
-                const int f = __ffs(mask) - 1;
-                runlen += f - cur;
-                if (EMIT && lane == 0) lens[k] = runlen;
-                k++;
-                head = __shfl_sync(0xffffffffu, x, f);
-                runlen = 1;
-                if (EMIT && lane == 0) vals[k] = head;
-                cur = f + 1;
+#pragma unroll 4
+                for (; c < cols; c++) {
+                    const float x = T[lane][c];
+                    const float mn = fminf(head, x); // std::min for non-NaN inputs
+                    if ((double)fabsf(head - x) < 1e-3 * (double)mn) {
+                        runlen++;
+                    } else {
+                        if (EMIT) lens[k] = runlen;
+                        k++;
+                        if (EMIT) vals[k] = x;
+                        head = x;
+                        runlen = 1;
+                    }
+                }
             }
         }
-        if (EMIT) { if (lane == 0) lens[k] = runlen; }
-        else if (lane == 0) P.K[vec] = k + 1;
+        if (live) {
+            if (EMIT) lens[k] = runlen;
+            else P.K[vec] = k + 1;
+        }
     }
 }
 
