@@ -148,6 +148,12 @@ int rp_paint_from_host(int device, int N, int L, const char *hap, const double *
 int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
                    int n_devices, unsigned flags, rp_stats *stats);
 
+/* Several chunks of one data set: chunks first_chunk..last_chunk are distributed over the
+ * devices as whole chunks, largest first, one host thread per device, no collective.  What a maintainer would call
+ * instead of the per-chunk loop of RelateParallel.sh:221-225 when several GPUs are present. */
+int rp_paint_chunks(const char *out_dir, int first_chunk, int last_chunk, const char *painting, const int *devices,
+                    int n_devices, unsigned flags, rp_stats *stats);
+
 /* ---- window repaint + distance matrices (consumer side, SURVEY.md 8 "next" row f1) ------------------
  *   rp_window_open      <- FastPainting::RePaintSection for every target     src/fast_painting.cpp:620-1092
  *                          (as DistanceMeasure::GetTopologyWithRepaint drives it, src/anc_builder.cpp:48-106)

@@ -70,6 +70,7 @@ SYMBOLS = {
     "rp_paint_from_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_double, C.c_uint,
                                      C.POINTER(RpTune), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(RpStats)]),
     "rp_paint_chunk": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, _P, C.c_int, C.c_uint, C.POINTER(RpStats)]),
+    "rp_paint_chunks": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p, _P, C.c_int, C.c_uint, C.POINTER(RpStats)]),
     "rp_release_cache": (None, []),
     "rp_window_open": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(RpStats)]),
     "rp_window_open_resident": (C.c_int, [_P, C.c_int, _P, C.POINTER(_P), C.POINTER(RpStats)]),
@@ -297,6 +298,20 @@ def paint_chunk(out_dir: str, chunk_index: int, painting: str | None = None, dev
         n = len(dev)
     check(lib().rp_paint_chunk(out_dir.encode(), chunk_index, painting.encode() if painting is not None else None,
                                _ptr(dev), n, RP_FP64 if fp64 else 0, C.byref(st)))
+    return st.as_dict()
+
+
+def paint_chunks(out_dir: str, first_chunk: int, last_chunk: int, painting: str | None = None, devices=None,
+                 fp64: bool = False) -> dict:
+    """Paint chunks first_chunk..last_chunk, whole chunks per device (``rp_paint_chunks``)."""
+    st = RpStats()
+    dev = None
+    n = 0
+    if devices is not None:
+        dev = np.asarray(list(devices), dtype=np.int32)
+        n = len(dev)
+    check(lib().rp_paint_chunks(out_dir.encode(), first_chunk, last_chunk, painting.encode() if painting is not None else None,
+                                _ptr(dev), n, RP_FP64 if fp64 else 0, C.byref(st)))
     return st.as_dict()
 
 

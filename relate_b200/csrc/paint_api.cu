@@ -1082,11 +1082,11 @@ struct PinnedBuf {
 struct DeviceWorkspace { // parked between rp_paint_chunk calls
     rp_chunk *shell = nullptr; // keeps its DevBufs, stream and events
     PinnedBuf ha, hb;
+    PinnedBuf hap_in;          // genotype bytes of the chunk being painted with this device as devs[0]
 };
 
 std::mutex g_stage_mu; // rp_paint_chunk calls are serialised (they share the cache)
 std::map<int, DeviceWorkspace> g_ws;
-PinnedBuf g_hap_in;
 
 template <typename F> void parallel_for(int n, int nthreads, F f)
 {
@@ -1115,24 +1115,31 @@ extern "C" void rp_release_cache(void)
         if (kv.second.shell) rp_chunk_free(kv.second.shell);
         kv.second.ha.release();
         kv.second.hb.release();
+        kv.second.hap_in.release();
     }
     g_ws.clear();
-    g_hap_in.release();
 }
 
-extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
-                              int n_devices, unsigned flags, rp_stats *stats)
+namespace {
+
+int check_devices(const int *devices, int n_devices, std::vector<int> &devs)
 {
-    if (!out_dir) return fail(RP_EINVAL, "null out_dir");
-    const double t0 = now_ms();
     int ndev = rp_device_count();
     if (ndev < 1) return fail(RP_ENODEVICE, "no CUDA device (there is no CPU fallback)");
-    std::vector<int> devs;
+    devs.clear();
     if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
     else devs.push_back(0);
     for (int d : devs)
         if (d < 0 || d >= ndev) return fail(RP_EINVAL, "device index out of range");
-    std::lock_guard<std::mutex> stage_lock(g_stage_mu);
+    return RP_OK;
+}
+
+// One chunk on the given devices.  The caller holds g_stage_mu and has created the g_ws entries of `devs`; concurrent
+// calls must use disjoint device sets (rp_paint_chunks: one device each).
+int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting, const std::vector<int> &devs, unsigned flags,
+                      rp_stats *stats)
+{
+    const double t0 = now_ms();
 
     // ---- input: small files now, genotype bytes by reader threads while the devices already copy ----
     rp::HostChunk hc;
@@ -1143,11 +1150,12 @@ extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *
         if (!err.empty()) return fail(RP_EIO, err);
     }
     const size_t nchar = (size_t)hc.L * hc.N;
-    if (g_hap_in.ensure(nchar) != RP_OK) {
+    PinnedBuf &hap_in = g_ws.at(devs[0]).hap_in;
+    if (hap_in.ensure(nchar) != RP_OK) {
         close(hap_fd);
         return RP_ENOMEM;
     }
-    hc.hap = static_cast<char *>(g_hap_in.p);
+    hc.hap = static_cast<char *>(hap_in.p);
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     HapFeed feed;
     feed.slice = (size_t)4 << 20;
@@ -1255,7 +1263,7 @@ extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *
     auto worker = [&](int di) {
         rp_stats &st = dstats[di];
         memset(&st, 0, sizeof st);
-        DeviceWorkspace &ws = g_ws[devs[di]];
+        DeviceWorkspace &ws = g_ws.at(devs[di]);
         rp_chunk *c = ws.shell;
         ws.shell = nullptr;
         int rc = chunk_from_host(devs[di], hc.N, hc.L, hc.hap, hc.r.data(), hc.wb.data(), (int)hc.wb.size(), hc.theta,
@@ -1330,6 +1338,97 @@ extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *
         }
         stats->ms_write = ms_write;
         stats->ms_load = t_loaded - t0;
+        stats->ms_total = now_ms() - t0;
+    }
+    return RP_OK;
+}
+
+} // namespace
+
+extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
+                              int n_devices, unsigned flags, rp_stats *stats)
+{
+    if (!out_dir) return fail(RP_EINVAL, "null out_dir");
+    std::vector<int> devs;
+    RP_TRY(check_devices(devices, n_devices, devs));
+    std::lock_guard<std::mutex> stage_lock(g_stage_mu);
+    for (int d : devs) g_ws[d];
+    return paint_chunk_stage(out_dir, chunk_index, painting, devs, flags, stats);
+}
+
+// Chunks first_chunk..last_chunk, whole chunks per device, largest first: one host thread per device
+// pulls the next chunk from the sorted list and runs the single-device stage on it.  No collective; the only shared
+// state is the list cursor.
+extern "C" int rp_paint_chunks(const char *out_dir, int first_chunk, int last_chunk, const char *painting, const int *devices,
+                               int n_devices, unsigned flags, rp_stats *stats)
+{
+    if (!out_dir) return fail(RP_EINVAL, "null out_dir");
+    if (first_chunk < 0 || last_chunk < first_chunk) return fail(RP_EINVAL, "bad chunk range");
+    const double t0 = now_ms();
+    std::vector<int> devs;
+    RP_TRY(check_devices(devices, n_devices, devs));
+    std::vector<std::pair<long long, int>> order; // (-cost, chunk)
+    for (int c = first_chunk; c <= last_chunk; c++) {
+        const std::string p = std::string(out_dir) + "/parameters_c" + std::to_string(c) + ".bin";
+        FILE *fp = fopen(p.c_str(), "rb");
+        int hdr[2] = {0, 0};
+        const bool ok = fp && fread(hdr, 4, 2, fp) == 2;
+        if (fp) fclose(fp);
+        if (!ok) return fail(RP_EIO, "cannot read " + p);
+        order.emplace_back(-(long long)hdr[0] * hdr[0] * hdr[1], c); // painted cells N*N*L
+    }
+    std::sort(order.begin(), order.end());
+    std::lock_guard<std::mutex> stage_lock(g_stage_mu);
+    for (int d : devs) g_ws[d];
+    std::atomic<int> cursor{0};
+    std::mutex mu;
+    int first_rc = RP_OK;
+    std::string first_err;
+    std::vector<rp_stats> acc(devs.size());
+    auto worker = [&](int di) {
+        rp_stats &a = acc[di];
+        memset(&a, 0, sizeof a);
+        for (;;) {
+            const int i = cursor.fetch_add(1);
+            if (i >= (int)order.size()) break;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (first_rc != RP_OK) break;
+            }
+            rp_stats st;
+            memset(&st, 0, sizeof st);
+            const int rc = paint_chunk_stage(out_dir, order[i].second, painting, std::vector<int>{devs[di]}, flags, &st);
+            if (rc != RP_OK) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (first_rc == RP_OK) {
+                    first_rc = rc;
+                    first_err = "chunk " + std::to_string(order[i].second) + ": " + g_err;
+                }
+                break;
+            }
+            a.ms_h2d += st.ms_h2d; a.ms_prep += st.ms_prep; a.ms_paint += st.ms_paint; a.ms_d2h += st.ms_d2h;
+            a.ms_rle += st.ms_rle; a.ms_write += st.ms_write; a.ms_load += st.ms_load;
+            a.sites += st.sites; a.cells += st.cells; a.h2d_bytes += st.h2d_bytes; a.d2h_bytes += st.d2h_bytes;
+            a.launches += st.launches; a.n_targets += st.n_targets;
+            a.team_threads = st.team_threads; a.words_per_thread = st.words_per_thread; a.ctas = st.ctas;
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int di = 1; di < (int)devs.size(); di++) threads.emplace_back(worker, di);
+    worker(0);
+    for (auto &t : threads) t.join();
+    if (first_rc != RP_OK) return fail(first_rc, first_err);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (const rp_stats &a : acc) { // per-device times: the busiest device; counts: summed
+            stats->ms_h2d = std::max(stats->ms_h2d, a.ms_h2d); stats->ms_prep = std::max(stats->ms_prep, a.ms_prep);
+            stats->ms_paint = std::max(stats->ms_paint, a.ms_paint); stats->ms_d2h = std::max(stats->ms_d2h, a.ms_d2h);
+            stats->ms_rle = std::max(stats->ms_rle, a.ms_rle); stats->ms_write = std::max(stats->ms_write, a.ms_write);
+            stats->ms_load = std::max(stats->ms_load, a.ms_load);
+            stats->sites += a.sites; stats->cells += a.cells; stats->h2d_bytes += a.h2d_bytes; stats->d2h_bytes += a.d2h_bytes;
+            stats->launches += a.launches; stats->n_targets += a.n_targets;
+            if (a.n_targets) { stats->team_threads = a.team_threads; stats->words_per_thread = a.words_per_thread; stats->ctas = a.ctas; }
+        }
         stats->ms_total = now_ms() - t0;
     }
     return RP_OK;

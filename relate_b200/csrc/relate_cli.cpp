@@ -9,7 +9,7 @@
 //     every other stage delegated to the reference binary;
 //   * every other mode is handed to the reference binary unchanged (exec).
 // The reference binary is found via $RELATE_REFERENCE_BIN, else "<dir of this exe>/Relate.ref".
-// Extra flags of this build (stripped before delegating): --gpus a,b,c   --fp64
+// Extra flags of this build (stripped before delegating): --gpus a,b,c   --fp64   --chunks a-b
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -65,6 +65,7 @@ const Flag kFlags[] = {
     // this build only
     {"gpus", 0, true, "(relate_b200) Comma-separated CUDA device indices for --mode Paint. Default: all visible."},
     {"fp64", 0, false, "(relate_b200) fp64 state in the painting kernel (verification mode)."},
+    {"chunks", 0, true, "(relate_b200) --mode Paint: paint chunks a-b (instead of --chunk_index), whole chunks per GPU."},
 };
 
 void print_help()
@@ -132,7 +133,7 @@ bool parse(int argc, char **argv, Args &a, std::string &err)
         }
         a.present.insert(f->name);
         a.val[f->name] = value;
-        const bool ours = !strcmp(f->name, "gpus") || !strcmp(f->name, "fp64");
+        const bool ours = !strcmp(f->name, "gpus") || !strcmp(f->name, "fp64") || !strcmp(f->name, "chunks");
         if (!ours) {
             a.passthrough.push_back(std::string("--") + f->name);
             if (f->has_value) a.passthrough.push_back(value);
@@ -191,7 +192,7 @@ std::vector<std::string> with_mode(const Args &a, const std::string &mode, const
 }
 
 // pipeline/Paint.cpp:17-108 behind the C ABI
-int paint(const Args &a, int chunk_index)
+int paint(const Args &a, int chunk_index, int last_chunk = -1)
 {
     std::vector<int> devs;
     if (a.count("gpus")) {
@@ -212,8 +213,10 @@ int paint(const Args &a, int chunk_index)
     rp_stats st;
     memset(&st, 0, sizeof st);
     const char *painting = a.count("painting") ? a.get("painting").c_str() : nullptr;
-    int rc = rp_paint_chunk(a.get("output").c_str(), chunk_index, painting, devs.data(), (int)devs.size(),
-                            a.count("fp64") ? RP_FP64 : 0u, &st);
+    int rc = last_chunk < 0 ? rp_paint_chunk(a.get("output").c_str(), chunk_index, painting, devs.data(), (int)devs.size(),
+                                             a.count("fp64") ? RP_FP64 : 0u, &st)
+                            : rp_paint_chunks(a.get("output").c_str(), chunk_index, last_chunk, painting, devs.data(),
+                                              (int)devs.size(), a.count("fp64") ? RP_FP64 : 0u, &st);
     if (rc != RP_OK) {
         std::cerr << "relate: Paint failed: " << rp_last_error() << std::endl;
         return 1;
@@ -296,6 +299,14 @@ int main(int argc, char **argv)
 
     if (mode == "Paint") {
         bool help = false;
+        if (a.count("chunks") && a.count("output") && !a.count("help")) {
+            int c0 = 0, c1 = -1;
+            if (sscanf(a.get("chunks").c_str(), "%d-%d", &c0, &c1) != 2 || c0 < 0 || c1 < c0) {
+                std::cerr << "relate: --chunks expects a-b" << std::endl;
+                return 1;
+            }
+            return paint(a, c0, c1);
+        }
         if (!a.count("chunk_index") || !a.count("output")) { // Relate.cpp:66-76
             std::cout << "Not enough arguments supplied." << std::endl;
             std::cout << "Needed: chunk_index, output." << std::endl;

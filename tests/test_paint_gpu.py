@@ -496,3 +496,42 @@ def test_window_from_resident_stepping_stones_equals_file_round_trip(tmp_path, N
         c.paint_targets_device(0, N // 2)
         with pytest.raises(capi.PaintError):  # only half of the targets are resident now
             capi.Window.open_resident(c, 0, rpos)
+
+
+# ---- BASELINE.json configs[4] shape (scaled): multi-chunk data set, MakeChunks -> Paint over all GPUs -----------
+def test_config5_shape_multichunk_makechunks_then_paint_chunks(tmp_path):
+    """Text haps -> rp_make_chunks (3 overlapping chunks: the 20000-SNP overlap and per-chunk window plans) -> every chunk
+    painted (whole chunks per GPU, rp_paint_chunks, through the CLI) -> compared with the oracle chunk by chunk; the fp64
+    verification mode must give the oracle's bytes."""
+    from test_makechunks_cpu import write_haps, write_map
+    d = str(tmp_path)
+    N, L = 64, 60000
+    hap, bp = synth.block_kingman(N, L, 77)
+    hp, sp = write_haps(d, hap, bp)
+    mp = write_map(d, bp, rows=200)
+    n, _ = capi.make_chunks(hp, sp, mp, os.path.join(d, "o"), memory_gb=0.0065)
+    assert n == 3
+    ndev = capi.lib().rp_device_count()
+    r = subprocess.run([EXE, "--mode", "Paint", "--chunks", f"0-{n - 1}", "-o", "o", "--painting", "0.001,1",
+                        "--gpus", ",".join(str(i) for i in range(ndev))], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    shutil.copytree(os.path.join(d, "o"), os.path.join(d, "ora"), ignore=shutil.ignore_patterns("paint"))
+    for c in range(n):
+        ch = chunkio.read_chunk(os.path.join(d, "o"), c)
+        assert ch.N == N
+        oracle.paint_chunk(os.path.join(d, "ora"), c, "0.001,1")
+        flips = 0
+        for w in range(ch.W):
+            flips += decoded_close(os.path.join(d, "o", f"chunk_{c}", "paint", f"relate_{w}.bin"),
+                                   os.path.join(d, "ora", f"chunk_{c}", "paint", f"relate_{w}.bin"), N, 1.1e-3)
+        assert flips <= max(2, N * ch.W // 50)
+    # fp64 verification mode through the API, chunks spread over the devices again
+    for c in range(n):
+        shutil.rmtree(os.path.join(d, "o", f"chunk_{c}"))
+    st = capi.paint_chunks(os.path.join(d, "o"), 0, n - 1, "0.001,1", devices=list(range(ndev)), fp64=True)
+    assert st["n_targets"] == n * N
+    for c in range(n):
+        W = chunkio.read_chunk(os.path.join(d, "o"), c).W
+        same = [filecmp.cmp(os.path.join(d, "o", f"chunk_{c}", "paint", f"relate_{w}.bin"),
+                            os.path.join(d, "ora", f"chunk_{c}", "paint", f"relate_{w}.bin"), shallow=False) for w in range(W)]
+        assert sum(same) >= W - 1, (c, same)
