@@ -387,7 +387,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     RP_CUDA(cudaMemsetAsync(c->ent.as<char>() + (pad + (size_t)U) * entsz, 0, pad * entsz, s));
     double *nor_out = nullptr;
     if (want_nor) {
-        RP_TRY(c->nor.ensure((size_t)U * 8));
+        RP_TRY(c->nor.ensure(((size_t)U + 8) * 8)); // the window repaint reads up to 2 entries past a slice
         nor_out = c->nor.as<double>();
     }
 
@@ -851,6 +851,7 @@ struct rp_window {
     rp_chunk *c = nullptr;
     int w = 0, start = 0, end = 0;
     long long rows = 0;
+    int pitch = 0, tt = 0, wpt = 0; // row layout of `top` (RepaintParams::pitch)
     DevBuf top, ls, rowoff, rpos, d, ab, be, lsa, lsb;
 };
 
@@ -896,7 +897,10 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     };
     int rc = RP_OK;
     const size_t nn = (size_t)N * N;
-    if ((rc = win->top.ensure((size_t)win->rows * N * 4)) || (rc = win->ls.ensure((size_t)win->rows * 4)) ||
+    win->tt = lp.threads;
+    win->wpt = lp.wpt;
+    win->pitch = lp.threads * lp.wpt * 32 + 32;
+    if ((rc = win->top.ensure((size_t)win->rows * win->pitch * 4)) || (rc = win->ls.ensure((size_t)win->rows * 4)) ||
         (rc = win->rowoff.ensure(((size_t)N + 1) * 8)) || (rc = win->rpos.ensure(((size_t)L + 1) * 8)) ||
         (rc = win->d.ensure(nn * 4)) || (rc = win->ab.ensure(nn * 4)) || (rc = win->be.ensure(nn * 4)) ||
         (rc = win->lsa.ensure((size_t)N * 4)) || (rc = win->lsb.ensure((size_t)N * 4)))
@@ -934,6 +938,7 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     P.alpha_begin = win->ab.as<float>(); P.beta_end = win->be.as<float>();
     P.ls_alpha = win->lsa.as<float>(); P.ls_beta = win->lsb.as<float>();
     P.top = win->top.as<float>(); P.ls = win->ls.as<float>();
+    P.pitch = win->pitch;
     P.rowoff = win->rowoff.as<long long>();
     P.queue = c->queue.as<int>();
     const double ntheta = 1.0 - c->theta;
@@ -946,16 +951,20 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     P.cf.upper = (float)(1.0 / 1e-10);
     P.log_ntheta = log(ntheta); P.log_small = log(0.01); P.Nm1 = N - 1.0;
     int occ = 0, ctas = 0;
-    auto launch = [&](auto kern) -> int {
-        RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, lp.threads, 0));
+    auto launch = [&](auto kern, int ring_rows) -> int {
+        const size_t smem = (size_t)ring_rows * lp.threads * lp.wpt * 128; // shared-memory ring of alpha rows
+        RP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, lp.threads, smem));
         if (occ < 1) return fail(RP_ECUDA, "repaint kernel does not fit on an SM");
         ctas = std::min(N, occ * c->sm_count);
-        kern<<<ctas, lp.threads, 0, s>>>(P);
+        kern<<<ctas, lp.threads, smem, s>>>(P);
         RP_CUDA(cudaGetLastError());
         return RP_OK;
     };
-    if (lp.wpt == 1) rc = lp.multi ? launch(rp::repaint_kernel<1, true>) : launch(rp::repaint_kernel<1, false>);
-    else rc = lp.multi ? launch(rp::repaint_kernel<2, true>) : launch(rp::repaint_kernel<2, false>);
+    if (lp.wpt == 1) rc = lp.multi ? launch(rp::repaint_kernel<1, true>, rp::RepaintRing<1, true>::kRows)
+                                   : launch(rp::repaint_kernel<1, false>, rp::RepaintRing<1, false>::kRows);
+    else rc = lp.multi ? launch(rp::repaint_kernel<2, true>, rp::RepaintRing<2, true>::kRows)
+                       : launch(rp::repaint_kernel<2, false>, rp::RepaintRing<2, false>::kRows);
     if (rc != RP_OK) return bail(rc);
     RP_CUDAW(cudaEventRecord(c->ev[2], s));
     RP_CUDAW(cudaStreamSynchronize(s));
@@ -1027,6 +1036,7 @@ int rp_window_distance(rp_window *win, int snp, float *d)
     P.top = win->top.as<float>(); P.ls = win->ls.as<float>();
     P.rowoff = win->rowoff.as<long long>();
     P.d = win->d.as<float>();
+    P.pitch = win->pitch; P.tt = win->tt; P.wpt = win->wpt;
     rp::distance_kernel<<<c->N, 256, 0, c->stream>>>(P);
     RP_CUDA(cudaGetLastError());
     RP_CUDA(cudaMemcpyAsync(d, win->d.p, (size_t)c->N * c->N * 4, cudaMemcpyDeviceToHost, c->stream));

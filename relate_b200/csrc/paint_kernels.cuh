@@ -846,9 +846,14 @@ paint_kernel(const PaintParams P)
 // per-row log-scales.  The window's entries are the slice ia[k][w]..ib[k][w] of the chunk-level site table; only
 // the last entry's recombination term differs (x_m = r[eS], :700-709).
 //
-// Rows are stored in the painter's register order: word-wise, each word rotated by k & 31 (reference haplotype j of
-// target k sits at (j & ~31) | ((j - k) & 31)); the tail haplotypes (N % 32) are stored unrotated.  This kernel
-// is HBM-bound: 3 * 4 * N * (sites in window) bytes per target against 6 FP32 ops per element.
+// Row layout in HBM (`pitch` = T*WPT*32 + 32 floats for a team of T threads): the painter's register order, transposed
+// so that one warp instruction touches contiguous memory.  Word w = t*WPT + j of a row belongs to thread t; its 32
+// haplotypes, rotated by k & 31 (haplotype n of target k has slot s = (n - k) & 31), form 8 float4 pieces; piece e of
+// (t, j) sits at float4 index (j*8 + e)*T + t, so the T threads' pieces e are adjacent (a 16-byte-per-lane access is
+// 512 contiguous bytes per warp; with a thread's 128 bytes contiguous instead, every instruction touched 32 different
+// lines and the kernel ran at 2.9 TB/s, bound by the load/store unit's tag rate).  The tail haplotypes (N % 32) are
+// stored unrotated at float index T*WPT*32 + lane.  HBM-bound: 3 * 4 * N * (sites in window) bytes per target against
+// 6 FP32 ops per element.
 struct RepaintParams {
     const uint32_t *G;
     int wps, N, L, W, nfw, tailn;
@@ -861,7 +866,8 @@ struct RepaintParams {
     const int *ia, *ib;      // [N][W]
     const float *alpha_begin, *beta_end; // [N][N] decoded stepping stones of window w (natural order)
     const float *ls_alpha, *ls_beta;     // [N]
-    float *top;              // posterior rows, target k at row offset rowoff[k]
+    float *top;              // posterior rows, target k at row offset rowoff[k]; `pitch` floats per row
+    int pitch;               // T*WPT*32 + 32 for the launch's team size T (see the row layout below)
     float *ls;               // per-row log-scales, same row indexing
     const long long *rowoff; // [N+1] prefix of (ib-ia+1)
     int *queue;
@@ -869,8 +875,15 @@ struct RepaintParams {
     double log_ntheta, log_small, Nm1;
 };
 
+extern __shared__ __align__(16) unsigned char rp_dyn_smem[];
+// rows of the shared-memory ring per team: bytes = kRows * (threads * WPT * 128)
+template <int WPT, bool MULTI> struct RepaintRing { static constexpr int kRows = MULTI ? 3 : (WPT == 1 ? 6 : 3); };
+
 template <int WPT, bool MULTI>
-__global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1 : 8) repaint_kernel(const RepaintParams P)
+#ifndef RP_REPAINT_MINB
+#define RP_REPAINT_MINB 8
+#endif
+__global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1 : (WPT == 1 ? RP_REPAINT_MINB : 8)) repaint_kernel(const RepaintParams P)
 {
     using T = float;
     using RT = Real<T>;
@@ -934,7 +947,9 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
         const int m = i1 - i0;                      // rows 0..m
         const EntF *pe = ents + P.off[k] + i0;      // entry of row i is pe[i]
         const double *pnor = P.nor + P.off[k] + i0;
-        float *top = P.top + (size_t)P.rowoff[k] * N;
+        float *top = P.top + (size_t)P.rowoff[k] * P.pitch;
+        const size_t pitch = (size_t)P.pitch;
+        const int tail_off = TT * WPT * 32;
         float *lsrow = P.ls + P.rowoff[k];
         const int rot = k & 31, wk = k >> 5;
         T ownmul[WPT];
@@ -952,21 +967,25 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             if (rho > 0.99) { rho = 0.99; nor_last = P.log_small + P.log_ntheta; }
             c_last = rho / ((1.0 - rho) * P.Nm1);
         }
-        // mis bits of row i for this thread's words, rotated; td = target's own allele mask
-        auto mask_words = [&](int site, uint32_t (&mw)[WPT], uint32_t &tmw) {
-            uint32_t w[WPT];
-            load_words(w, gthr + (size_t)(unsigned)site * rowbytes);
-            const uint32_t kw = P.G[(size_t)site * P.wps + wk];
-            const uint32_t td = ((kw >> rot) & 1u) ? 0xffffffffu : 0u;
+        // Inputs of a row, fetched one row ahead of their use (the site index two rows ahead): this thread's genotype
+        // words, the word holding the target's own allele, the tail word.  expand() turns them into the rotated
+        // mismatch bits; td = target's own allele mask.
+        struct RowIn { uint32_t w[WPT]; uint32_t kw, tw; };
+        auto fetch = [&](int site, RowIn &in) {
+            load_words(in.w, gthr + (size_t)(unsigned)site * rowbytes);
+            in.kw = P.G[(size_t)site * P.wps + wk];
+            in.tw = 0;
+            if (tail_warp) in.tw = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)site * rowbytes);
+        };
+        auto expand = [&](const RowIn &in, uint32_t (&mw)[WPT], uint32_t &tmw) {
+            const uint32_t td = ((in.kw >> rot) & 1u) ? 0xffffffffu : 0u;
 #pragma unroll
             for (int j = 0; j < WPT; j++) {
-                const uint32_t nb = ~w[j] & td;
+                const uint32_t nb = ~in.w[j] & td;
                 mw[j] = __funnelshift_r(nb, nb, rot);
             }
-            tmw = 0;
-            if (tail_warp) tmw = ~*reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)site * rowbytes) & td;
+            tmw = ~in.tw & td;
         };
-        const size_t slot0 = (size_t)t * WPT * 32; // this thread's first element within a row
 
         // ---------------- forward: alpha rows -> top ----------------
         V2 a[WPT][16];
@@ -989,11 +1008,11 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
 #pragma unroll
             for (int j = 0; j < WPT; j++)
                 if (valid[j]) {
-                    float4 *o = reinterpret_cast<float4 *>(row + slot0 + j * 32);
+                    float4 *o = reinterpret_cast<float4 *>(row) + (size_t)(j * 8) * TT + t;
 #pragma unroll
-                    for (int e = 0; e < 8; e++) o[e] = make_float4(a[j][2 * e].x, a[j][2 * e].y, a[j][2 * e + 1].x, a[j][2 * e + 1].y);
+                    for (int e = 0; e < 8; e++) o[(size_t)e * TT] = make_float4(a[j][2 * e].x, a[j][2 * e].y, a[j][2 * e + 1].x, a[j][2 * e + 1].y);
                 }
-            if (tail_lane) row[P.nfw * 32 + lane] = tl;
+            if (tail_lane) row[tail_off + lane] = tl;
         };
         auto local_sum = [&]() -> T {
             V2 S0 = make_float2(0.f, 0.f), S1 = S0;
@@ -1010,9 +1029,22 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
         double prev_ls = (double)P.ls_alpha[k];
         if (t == 0) lsrow[0] = P.ls_alpha[k];
         T R = S * pe[0].c;
+        RowIn nin;                    // inputs of row i+1 while row i is computed
+        fetch(pe[1].site, nin);       // entries past the window's slice belong to the chunk-level table or its padding
+        EntF e2 = pe[2];
+        T cnext = pe[1].c;
+        double nor1 = pnor[0], nor2 = pnor[1]; // nor of rows i-1 and i while row i runs (the table is padded past U)
         for (int i = 1; i <= m; i++) {
+            const RowIn cin = nin;
+            const T ccur = cnext;
+            const double nor_cur = nor1;
+            nor1 = nor2;
+            nor2 = pnor[i + 1];
+            fetch(e2.site, nin);
+            cnext = e2.c;
+            e2 = pe[i + 2];
             uint32_t mw[WPT], tmw;
-            mask_words(pe[i].site, mw, tmw);
+            expand(cin, mw, tmw);
             V2 S0 = make_float2(0.f, 0.f), S1 = S0;
 #pragma unroll
             for (int j = 0; j < WPT; j++) {
@@ -1037,7 +1069,7 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
                 Sl += tl;
             }
             S = reduce(Sl, par ^= 1);
-            prev_ls += pnor[i - 1];
+            prev_ls += nor_cur;
             float lsi = (float)prev_ls;
             if (S < K.lower || S > K.upper) { // :865-876
                 const T inv = 1.f / S;
@@ -1053,8 +1085,8 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             } else {
                 R = S;
             }
-            R *= (i == m) ? (T)c_last : pe[i].c;
-            store_row(top + (size_t)i * N);
+            R *= (i == m) ? (T)c_last : ccur;
+            store_row(top + (size_t)i * pitch);
             if (t == 0) lsrow[i] = lsi;
         }
 
@@ -1066,10 +1098,56 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
         T gt = 0.f;
         T Rp = 0.f;
         double prevb = (double)P.ls_beta[k];
+        // alpha rows of the backward sweep come through a ring of RING rows in shared memory, filled by cp.async RING
+        // rows ahead of their use (the kernel has one row-sized load per step and one team per target, so bytes in
+        // flight = teams x rows ahead; with a single row in registers it ran at the latency-bound 2.6 TB/s).  Every
+        // thread copies and later reads only its own 16-byte pieces (piece e of thread t sits at [e][t]: conflict-free),
+        // so the ring needs no barrier, only cp.async.wait_group.
+        float4 *ring = reinterpret_cast<float4 *>(rp_dyn_smem);
+        constexpr int RING = RepaintRing<WPT, MULTI>::kRows;
+        auto ring_issue = [&](int i, int rslot) { // request row i (nothing if i < 0); always closes one group
+            if (i >= 0) {
+                const float4 *src = reinterpret_cast<const float4 *>(top + (size_t)i * pitch) + t;
+#pragma unroll
+                for (int j = 0; j < WPT; j++)
+                    if (valid[j]) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + ((size_t)(rslot * WPT + j) * 8 + e) * TT + t);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)(j * 8 + e) * TT) : "memory");
+                        }
+                    }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int d = 0; d < RING; d++) ring_issue(m - d, d);
+        int rslot = 0;
+        float tail_a_next = tail_lane ? top[(size_t)m * pitch + tail_off + lane] : 0.f; // the tail element's alpha, one row ahead
+        fetch(pe[m].site, nin);
+        e2 = pe[m - 1];
+        cnext = pe[m].c;
+        float ls_next = lsrow[m];                 // log-scale of row i (written by the forward sweep), one row ahead
+        double norb_next = m >= 1 ? pnor[m - 1] : 0.0, norb_next2 = m >= 2 ? pnor[m - 2] : 0.0; // pnor[i+1] for rows m-2, m-3
         for (int i = m; i >= 0; i--) {
-            float *row = top + (size_t)i * N;
+            float *row = top + (size_t)i * pitch;
+            const RowIn cin = nin;
+            const T ccur = cnext;
+            const float ls_cur = ls_next;
+            if (i > 0) ls_next = lsrow[i - 1];
+            const float tail_a = tail_a_next;
+            if (tail_lane && i > 0) tail_a_next = (row - pitch)[tail_off + lane];
+            double norb_cur = 0.0; // pnor[i+1], needed for rows i <= m-2
+            if (i <= m - 2) {
+                norb_cur = norb_next;
+                norb_next = norb_next2;
+                if (i >= 2) norb_next2 = pnor[i - 1];
+            }
+            fetch(e2.site, nin);
+            cnext = e2.c;
+            e2 = pe[i - 2];
             uint32_t mw[WPT], tmw;
-            mask_words(pe[i].site, mw, tmw);
+            expand(cin, mw, tmw);
             V2 S0 = make_float2(0.f, 0.f), S1 = S0;
             if (i == m) { // b_m = beta_end (:895-909)
                 const float *be = P.beta_end + (size_t)k * N;
@@ -1083,17 +1161,18 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
                     }
                 if (tail_lane) gt = be[P.nfw * 32 + lane];
             }
+            asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory"); // row i has landed
 #pragma unroll
             for (int j = 0; j < WPT; j++) {
                 const T Rj = (i == m) ? 0.f : Rp * vmul[j];
                 const V2 R2 = make_float2(Rj, Rj);
-                float4 *o = reinterpret_cast<float4 *>(row + slot0 + j * 32);
+                float4 *o = reinterpret_cast<float4 *>(row) + (size_t)(j * 8) * TT + t;
 #pragma unroll
                 for (int e2 = 0; e2 < 8; e2++) {
-                    float4 av = valid[j] ? o[e2] : make_float4(0.f, 0.f, 0.f, 0.f); // alpha_i
+                    const float4 av = valid[j] ? ring[((size_t)(rslot * WPT + j) * 8 + e2) * TT + t] : make_float4(0.f, 0.f, 0.f, 0.f); // alpha_i
                     V2 b0 = RT::add2(g[j][2 * e2], R2), b1 = RT::add2(g[j][2 * e2 + 1], R2);
                     if (e2 == 0) b0.x *= ownmul[j]; // b[k] = 0
-                    if (valid[j]) o[e2] = make_float4(av.x * b0.x, av.y * b0.y, av.z * b1.x, av.w * b1.y);
+                    if (valid[j]) o[(size_t)e2 * TT] = make_float4(av.x * b0.x, av.y * b0.y, av.z * b1.x, av.w * b1.y);
                     if (mw[j] & (1u << (4 * e2))) b0.x *= tau;
                     if (mw[j] & (2u << (4 * e2))) b0.y *= tau;
                     if (mw[j] & (4u << (4 * e2))) b1.x *= tau;
@@ -1104,11 +1183,13 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
                     S1 = RT::add2(S1, b1);
                 }
             }
+            ring_issue(i - RING, rslot); // the slot just consumed receives row i-RING
+            rslot = (rslot + 1 == RING) ? 0 : rslot + 1;
             S0 = RT::add2(S0, S1);
             T Sl = S0.x + S0.y;
             if (tail_warp) {
                 T b = ((i == m) ? gt : gt + Rp) * tailmul;
-                if (tail_lane) row[P.nfw * 32 + lane] = row[P.nfw * 32 + lane] * b;
+                if (tail_lane) row[tail_off + lane] = tail_a * b;
                 if (tmw & lanebit) b *= tau;
                 gt = b;
                 Sl += b;
@@ -1118,10 +1199,10 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             // log-scale of the row (thread 0): float accumulations exactly as the reference orders them
             float lsi = 0.f;
             if (t == 0) {
-                lsi = lsrow[i];
+                lsi = ls_cur;
                 if (i == m) lsi = lsi + P.ls_beta[k];
                 else {
-                    prevb += (i + 1 == m) ? nor_last : pnor[i + 1];
+                    prevb += (i + 1 == m) ? nor_last : norb_cur;
                     lsi = (float)((double)lsi + prevb);
                 }
             }
@@ -1139,7 +1220,7 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             } else {
                 Rp = G;
             }
-            Rp *= (i == m) ? (T)c_last : pe[i].c;
+            Rp *= (i == m) ? (T)c_last : ccur;
             if (t == 0) lsrow[i] = lsi;
         }
     }
@@ -1156,6 +1237,7 @@ struct DistanceParams {
     const float *top, *ls;
     const long long *rowoff;
     float *d;            // [N][N]
+    int pitch, tt, wpt;  // row layout of `top`: the repaint launch's pitch, team size and words per thread
 };
 
 __global__ void __launch_bounds__(256) distance_kernel(const DistanceParams P)
@@ -1186,14 +1268,18 @@ __global__ void __launch_bounds__(256) distance_kernel(const DistanceParams P)
     __syncthreads();
     const int v = s_v, rot = n & 31;
     const int nfw32 = (N >> 5) << 5;
-    const float *top_n = P.top + (size_t)P.rowoff[n] * N;
+    const float *top_n = P.top + (size_t)P.rowoff[n] * P.pitch;
     const float *ls_n = P.ls + P.rowoff[n];
-    auto slot = [&](int j) { return j < nfw32 ? ((j & ~31) | ((j - rot) & 31)) : j; }; // painter's register order
+    auto slot = [&](int j) -> int { // the repaint kernel's row layout (see there)
+        if (j >= nfw32) return P.tt * P.wpt * 32 + (j - nfw32);
+        const int w = j >> 5, s = (j - rot) & 31;
+        return (((w % P.wpt) * 8 + (s >> 2)) * P.tt + w / P.wpt) * 4 + (s & 3);
+    };
     float *out = P.d + (size_t)n * N;
     const float scale = -1.0f;
     float mn = INFINITY;
     if (s_der || P.snp == 0 || P.snp == P.L - 1) {
-        const float *tr = top_n + (size_t)v * N;
+        const float *tr = top_n + (size_t)v * P.pitch;
         const float lsp = ls_n[v];
         for (int j = t; j < N; j += blockDim.x) {
             const float m = __fmul_rn(__fadd_rn(fast_log_dev(tr[slot(j)]), lsp), scale);
@@ -1205,7 +1291,7 @@ __global__ void __launch_bounds__(256) distance_kernel(const DistanceParams P)
         double wl, wr;
         if (rp == rn) { wl = 0.5; wr = 0.5; }
         else { const double den = rn - rp; wl = (rn - rs) / den; wr = (rs - rp) / den; }
-        const float *tp = top_n + (size_t)v * N, *tn = top_n + (size_t)(v + 1) * N;
+        const float *tp = top_n + (size_t)v * P.pitch, *tn = top_n + (size_t)(v + 1) * P.pitch;
         const float lsp = ls_n[v], lsn = ls_n[v + 1];
         const float e_pn = expf(lsp - lsn), e_np = expf(lsn - lsp);
         for (int j = t; j < N; j += blockDim.x) {
