@@ -875,6 +875,19 @@ struct RepaintParams {
     double log_ntheta, log_small, Nm1;
 };
 
+// A value stream requested D rows ahead of its use: D registers that shift by one per row.
+template <typename V, int D> struct Ahead {
+    V q[D];
+    __device__ __forceinline__ V pop_push(const V &nv)
+    {
+        const V r = q[0];
+#pragma unroll
+        for (int d = 0; d + 1 < D; d++) q[d] = q[d + 1];
+        q[D - 1] = nv;
+        return r;
+    }
+};
+
 extern __shared__ __align__(16) unsigned char rp_dyn_smem[];
 // rows of the shared-memory ring per team: bytes = kRows * (threads * WPT * 128)
 template <int WPT, bool MULTI> struct RepaintRing { static constexpr int kRows = MULTI ? 3 : (WPT == 1 ? 6 : 3); };
@@ -967,15 +980,18 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             if (rho > 0.99) { rho = 0.99; nor_last = P.log_small + P.log_ntheta; }
             c_last = rho / ((1.0 - rho) * P.Nm1);
         }
-        // Inputs of a row, fetched one row ahead of their use (the site index two rows ahead): this thread's genotype
-        // words, the word holding the target's own allele, the tail word.  expand() turns them into the rotated
+        // Inputs of a row, fetched two rows ahead of their use (their table entry four rows ahead; one row was not
+        // enough once the row traffic itself ran near the HBM rate): this thread's genotype words, the word holding
+        // the target's own allele, the tail word.  expand() turns them into the rotated
         // mismatch bits; td = target's own allele mask.
         struct RowIn { uint32_t w[WPT]; uint32_t kw, tw; };
-        auto fetch = [&](int site, RowIn &in) {
+        auto fetch = [&](int site) -> RowIn {
+            RowIn in;
             load_words(in.w, gthr + (size_t)(unsigned)site * rowbytes);
             in.kw = P.G[(size_t)site * P.wps + wk];
             in.tw = 0;
             if (tail_warp) in.tw = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)site * rowbytes);
+            return in;
         };
         auto expand = [&](const RowIn &in, uint32_t (&mw)[WPT], uint32_t &tmw) {
             const uint32_t td = ((in.kw >> rot) & 1u) ? 0xffffffffu : 0u;
@@ -1029,20 +1045,20 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
         double prev_ls = (double)P.ls_alpha[k];
         if (t == 0) lsrow[0] = P.ls_alpha[k];
         T R = S * pe[0].c;
-        RowIn nin;                    // inputs of row i+1 while row i is computed
-        fetch(pe[1].site, nin);       // entries past the window's slice belong to the chunk-level table or its padding
-        EntF e2 = pe[2];
-        T cnext = pe[1].c;
-        double nor1 = pnor[0], nor2 = pnor[1]; // nor of rows i-1 and i while row i runs (the table is padded past U)
+        // entries past the window's slice belong to the chunk-level table or its 4-entry padding; nor is padded too
+        Ahead<EntF, 2> entq;
+        Ahead<RowIn, 2> inq;
+        Ahead<T, 2> cq;
+        Ahead<double, 3> norq;
+        entq.q[0] = pe[3]; entq.q[1] = pe[4];
+        inq.q[0] = fetch(pe[1].site); inq.q[1] = fetch(pe[2].site);
+        cq.q[0] = pe[1].c; cq.q[1] = pe[2].c;
+        norq.q[0] = pnor[0]; norq.q[1] = pnor[1]; norq.q[2] = pnor[2];
         for (int i = 1; i <= m; i++) {
-            const RowIn cin = nin;
-            const T ccur = cnext;
-            const double nor_cur = nor1;
-            nor1 = nor2;
-            nor2 = pnor[i + 1];
-            fetch(e2.site, nin);
-            cnext = e2.c;
-            e2 = pe[i + 2];
+            const EntF ent = entq.pop_push(pe[i + 4]);       // = pe[i+2]
+            const RowIn cin = inq.pop_push(fetch(ent.site)); // inputs of row i; row i+2's are requested
+            const T ccur = cq.pop_push(ent.c);               // c of row i
+            const double nor_cur = norq.pop_push(pnor[i + 2]); // pnor[i-1]
             uint32_t mw[WPT], tmw;
             expand(cin, mw, tmw);
             V2 S0 = make_float2(0.f, 0.f), S1 = S0;
@@ -1123,29 +1139,28 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
 #pragma unroll
         for (int d = 0; d < RING; d++) ring_issue(m - d, d);
         int rslot = 0;
-        float tail_a_next = tail_lane ? top[(size_t)m * pitch + tail_off + lane] : 0.f; // the tail element's alpha, one row ahead
-        fetch(pe[m].site, nin);
-        e2 = pe[m - 1];
-        cnext = pe[m].c;
-        float ls_next = lsrow[m];                 // log-scale of row i (written by the forward sweep), one row ahead
-        double norb_next = m >= 1 ? pnor[m - 1] : 0.0, norb_next2 = m >= 2 ? pnor[m - 2] : 0.0; // pnor[i+1] for rows m-2, m-3
+        // the same streams walking down; plus the row's log-scale (written by the forward sweep), the tail element's
+        // alpha and pnor[i+1] (used for rows i <= m-2), three rows ahead, row indices clamped at 0
+        Ahead<float, 3> lsq, tailq;
+        Ahead<double, 3> norbq;
+        auto tail_at = [&](int i) -> float { return tail_lane ? top[(size_t)max(i, 0) * pitch + tail_off + lane] : 0.f; };
+        entq.q[0] = pe[m - 2]; entq.q[1] = pe[m - 3];
+        inq.q[0] = fetch(pe[m].site); inq.q[1] = fetch(pe[m - 1].site);
+        cq.q[0] = pe[m].c; cq.q[1] = pe[m - 1].c;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            lsq.q[d] = lsrow[max(m - d, 0)];
+            tailq.q[d] = tail_at(m - d);
+            norbq.q[d] = pnor[max(m - d + 1, 0)];
+        }
         for (int i = m; i >= 0; i--) {
             float *row = top + (size_t)i * pitch;
-            const RowIn cin = nin;
-            const T ccur = cnext;
-            const float ls_cur = ls_next;
-            if (i > 0) ls_next = lsrow[i - 1];
-            const float tail_a = tail_a_next;
-            if (tail_lane && i > 0) tail_a_next = (row - pitch)[tail_off + lane];
-            double norb_cur = 0.0; // pnor[i+1], needed for rows i <= m-2
-            if (i <= m - 2) {
-                norb_cur = norb_next;
-                norb_next = norb_next2;
-                if (i >= 2) norb_next2 = pnor[i - 1];
-            }
-            fetch(e2.site, nin);
-            cnext = e2.c;
-            e2 = pe[i - 2];
+            const EntF ent = entq.pop_push(pe[i - 4]);       // = pe[i-2]
+            const RowIn cin = inq.pop_push(fetch(ent.site)); // inputs of row i; row i-2's are requested
+            const T ccur = cq.pop_push(ent.c);
+            const float ls_cur = lsq.pop_push(lsrow[max(i - 3, 0)]);
+            const float tail_a = tailq.pop_push(tail_at(i - 3));
+            const double norb_cur = norbq.pop_push(pnor[max(i - 2, 0)]); // pnor[i+1]
             uint32_t mw[WPT], tmw;
             expand(cin, mw, tmw);
             V2 S0 = make_float2(0.f, 0.f), S1 = S0;
