@@ -157,8 +157,10 @@ class DeviceChunk:
                                   RP_FP64 if fp64 else 0, C.byref(h)))
         return cls(h)
 
-    def set_tune(self, words_per_thread: int = 0, ctas_per_sm: int = 0) -> None:
+    def set_tune(self, words_per_thread: int = 0, ctas_per_sm: int = 0, cluster: int = 0) -> None:
+        """cluster > 1 forces teams of that many CTAs (thread-block cluster) where a single CTA would do (tests)."""
         t = RpTune(words_per_thread, ctas_per_sm)
+        t.reserved[3] = cluster
         check(lib().rp_chunk_set_tune(self._h, C.byref(t)))
 
     def set_stream(self, cuda_stream: int | None) -> None:

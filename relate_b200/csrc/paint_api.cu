@@ -118,6 +118,7 @@ struct LaunchPlan {
     int wpt = 1;
     bool multi = false;
     int threads = 32;
+    int cluster = 1; // CTAs per team (thread-block cluster with distributed shared memory when > 1)
 };
 
 int plan_launch(const rp_chunk *c, LaunchPlan &lp)
@@ -134,10 +135,19 @@ int plan_launch(const rp_chunk *c, LaunchPlan &lp)
     lp.multi = need > 32;
     lp.threads = ((need + 31) / 32) * 32;
     const int maxt = (fp64 || wpt == 1) ? 384 : 512; // PaintCfg::kMaxThreads
+    const int forced = c->tune.reserved[3];          // tests: force a cluster of this many CTAs per team
+    if (!fp64 && lp.multi && wpt == 2 && (lp.threads > maxt || forced > 1)) {
+        // a team of several CTAs: thread-block cluster, sums combined through distributed shared memory
+        int cs = std::max(forced, (need + 511) / 512);
+        if (cs > 16) return fail(RP_EUNSUPPORTED, "N=" + std::to_string(c->N) + " is beyond a 16-CTA cluster (524288 haplotypes)");
+        lp.cluster = cs;
+        lp.threads = (((need + cs - 1) / cs + 31) / 32) * 32;
+        return RP_OK;
+    }
     if (lp.threads > maxt)
         return fail(RP_EUNSUPPORTED, "N=" + std::to_string(c->N) + " needs " + std::to_string(lp.threads) +
                                          " threads per team; one CTA owns at most " + std::to_string(maxt * wpt * 32) +
-                                         " haplotypes in this mode (cluster/DSMEM variant not built yet)");
+                                         " haplotypes in this mode (fp64 verification mode has no cluster variant)");
     return RP_OK;
 }
 
@@ -179,6 +189,30 @@ int launch_paint(const rp_chunk *c, rp::PaintParams &P, const LaunchPlan &lp, De
                         : launch_paint_t<double, 1, false>(c, P, lp.threads, ctas);
     }
     P.scratch = nullptr;
+    if (lp.cluster > 1) {
+        auto kern = rp::paint_cluster_kernel;
+        if (lp.cluster > 8) RP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)lp.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3((unsigned)lp.threads);
+        cfg.gridDim = dim3((unsigned)lp.cluster); // provisional, for the occupancy query
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = c->stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int max_clusters = 0;
+        RP_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+        if (max_clusters < 1) return fail(RP_EUNSUPPORTED, "a cluster of " + std::to_string(lp.cluster) + " CTAs cannot be co-scheduled on this device");
+        const int teams = 2 * std::min(P.nt, std::max(1, max_clusters / 2)); // even teams paint forwards, odd ones backwards
+        ctas = teams * lp.cluster;
+        cfg.gridDim = dim3((unsigned)ctas);
+        RP_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+        return RP_OK;
+    }
     if (lp.wpt == 1)
         return lp.multi ? launch_paint_t<float, 1, true>(c, P, lp.threads, ctas)
                         : launch_paint_t<float, 1, false>(c, P, lp.threads, ctas);
@@ -874,7 +908,8 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     RP_TRY(paint_device(c, 0, N, stats, /*run_paint=*/false, /*want_nor=*/true));
     LaunchPlan lp;
     RP_TRY(plan_launch(c, lp));
-    if (lp.multi && lp.threads > (lp.wpt == 1 ? 512 : 256)) return fail(RP_EUNSUPPORTED, "N too large for the window repaint kernel");
+    if (lp.cluster > 1 || (lp.multi && lp.threads > (lp.wpt == 1 ? 512 : 256)))
+        return fail(RP_EUNSUPPORTED, "N too large for the window repaint kernel");
     cudaStream_t s = c->stream;
     // rows per target = ib - ia + 1; prefix on the host (N ints each way)
     std::vector<int> ia((size_t)N * W), ib((size_t)N * W);

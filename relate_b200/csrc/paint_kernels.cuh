@@ -21,6 +21,8 @@
 
 #include <type_traits>
 
+#include <cooperative_groups.h>
+
 namespace rp {
 
 // ---------------------------------------------------------------------------------------
@@ -433,9 +435,16 @@ template <int WPT> __device__ __forceinline__ void load_words(uint32_t (&w)[WPT]
 __device__ __forceinline__ void opaque(float &x) { asm volatile("" : "+f"(x)); }
 __device__ __forceinline__ void opaque(double &x) { asm volatile("" : "+d"(x)); }
 
-template <typename T, int WPT, bool MULTI, int DIR>
-__device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (*s_part)[32])
+// CLUSTER: the team is a thread-block cluster (N beyond one CTA's reach: up to 16 x 512 threads x 2 words).  CTA r
+// owns the words of team threads r*T .. r*T+T-1; the per-step sum adds the CTAs' sums through distributed shared
+// memory (one cluster barrier per step, partial sums double-buffered), the job index is fetched by CTA 0.
+template <typename T, int WPT, bool MULTI, int DIR, bool CLUSTER = false>
+__device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (*s_part)[32], float *s_cpart = nullptr)
 {
+    static_assert(!CLUSTER || (MULTI && sizeof(T) == 4), "cluster teams are multi-warp fp32 teams");
+    namespace cg = cooperative_groups;
+    const int crank = CLUSTER ? (int)cg::this_cluster().block_rank() : 0;
+    const int csize = CLUSTER ? (int)cg::this_cluster().num_blocks() : 1;
     using RT = Real<T>;
     using V2 = typename RT::V2;
     using Ent = typename RT::Ent;
@@ -443,6 +452,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int TT = blockDim.x, TW = TT >> 5;
+    const int gt = crank * TT + t; // index of this thread within the team
     const PaintConsts<T> &K = paint_consts<T>(P);
     // loop constants live in registers (opaque to the compiler, which would otherwise re-read the constant bank
     // every step)
@@ -463,17 +473,17 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
     T vmul[WPT];           // 1 for words this thread owns, 0 otherwise: R*vmul keeps an unused slot at exactly 0
 #pragma unroll
     for (int j = 0; j < WPT; j++) {
-        valid[j] = (t * WPT + j) < P.nfw;
+        valid[j] = (gt * WPT + j) < P.nfw;
         vmul[j] = valid[j] ? (T)1 : (T)0;
         opaque(vmul[j]);
     }
     // this thread's WPT adjacent words within a row: one (vector) load per visited site, 4*WPT bytes per lane,
     // coalesced across the warp.  Rows are padded to 16 bytes and a word past the last full one is either the tail
     // word or padding, so threads beyond the row's end read word 0 and ignore it.
-    const char *gthr = reinterpret_cast<const char *>(P.G + ((t * WPT + WPT - 1) < P.wps ? t * WPT : 0));
+    const char *gthr = reinterpret_cast<const char *>(P.G + ((gt * WPT + WPT - 1) < P.wps ? gt * WPT : 0));
     asm volatile("" : "+l"(gthr));
     const bool has_tail = P.tailn > 0;                 // kernel-uniform
-    const bool tail_warp = has_tail && (warp == 0);
+    const bool tail_warp = has_tail && (gt < 32);
     const bool tail_lane = tail_warp && (lane < P.tailn);
     const char *gtail = reinterpret_cast<const char *>(P.G + (has_tail ? P.nfw : 0));
     uint32_t lanebit = 1u << lane;
@@ -485,7 +495,16 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 
     for (;;) {
         int kk;
-        if (MULTI) {
+        if (CLUSTER) {
+            cg::cluster_group cl = cg::this_cluster();
+            cl.sync(); // every CTA is done with the previous job (and with s_job)
+            if (gt == 0) {
+                const int v = atomicAdd(queue, 1);
+                for (int r = 0; r < csize; r++) *cl.map_shared_rank(s_job, r) = v;
+            }
+            cl.sync();
+            kk = *s_job;
+        } else if (MULTI) {
             __syncthreads();
             if (t == 0) *s_job = atomicAdd(queue, 1);
             __syncthreads();
@@ -503,7 +522,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         const int rot = k & 31, wk = k >> 5;
         bool own[WPT];
 #pragma unroll
-        for (int j = 0; j < WPT; j++) own[j] = (wk < P.nfw) && (t * WPT + j == wk);
+        for (int j = 0; j < WPT; j++) own[j] = (wk < P.nfw) && (gt * WPT + j == wk);
         const bool tail_live = tail_lane && !((wk == P.nfw) && (lane == rot)); // valid tail slot that is not the target
         T ownmul[WPT]; // 0 on the thread/word holding the target (slot 0 after rotation), else 1
 #pragma unroll
@@ -620,6 +639,14 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                     S = part[0];
                     for (int ww = 1; ww < TW; ww++) S += part[ww];
                 }
+                if (CLUSTER) { // add the CTAs' sums, in rank order, through distributed shared memory
+                    cg::cluster_group cl = cg::this_cluster();
+                    if (t == 0) s_cpart[parity] = (float)S;
+                    cl.sync();
+                    float acc = *cl.map_shared_rank(s_cpart + parity, 0);
+                    for (int r = 1; r < csize; r++) acc += *cl.map_shared_rank(s_cpart + parity, r);
+                    S = (T)acc;
+                }
             }
             return S;
         };
@@ -630,7 +657,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 #pragma unroll
             for (int j = 0; j < WPT; j++) {
                 if (valid[j]) {
-                    const int n0 = (t * WPT + j) * 32;
+                    const int n0 = (gt * WPT + j) * 32;
 #pragma unroll
                     for (int e = 0; e < 16; e++) {
                         T vx = a[j][e].x + addR, vy = a[j][e].y + addR;
@@ -680,7 +707,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             for (int qq = q; qq < qe; qq++) {
                 const int w = P.W - 1 - qq;
                 store_vec(outv + (size_t)w * P.N, (T)0, true);
-                if (t == 0) outl[w] = (float)lsb[w];
+                if (gt == 0) outl[w] = (float)lsb[w];
             }
             q = qe;
         }
@@ -734,7 +761,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 #pragma unroll
                         for (int j = 0; j < WPT; j++) {
                             if (valid[j]) {
-                                const int n0 = (t * WPT + j) * 32;
+                                const int n0 = (gt * WPT + j) * 32;
                                 for (int e = 0; e < 32; e++) {
                                     T v = src[n0 + e];
                                     if (rescaled) v /= B;
@@ -748,7 +775,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                             o[P.nfw * 32 + lane] = (float)v;
                         }
                     }
-                    if (t == 0) outl[w] = (float)(lsb[w] + lsr);
+                    if (gt == 0) outl[w] = (float)(lsb[w] + lsr);
                 }
                 q = q1;
                 post = false;
@@ -765,7 +792,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                     if (!DIR) { // alpha after step p, post-rescale (:354-374)
                         for (int qq = q; qq < q1; qq++) {
                             store_vec(outv + (size_t)qq * P.N, (T)0, false);
-                            if (t == 0) outl[qq] = (float)(lsb[qq] + lsr);
+                            if (gt == 0) outl[qq] = (float)(lsb[qq] + lsr);
                         }
                         q = q1;
                     } else { // beta of step pn is b = g_old + R' before the emission multiply (:481-488)
@@ -814,7 +841,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         if (!DIR) { // alpha stepping stones at the last visited site
             while (q < P.W) {
                 store_vec(outv + (size_t)q * P.N, (T)0, false);
-                if (t == 0) outl[q] = (float)(lsb[q] + lsr);
+                if (gt == 0) outl[q] = (float)(lsb[q] + lsr);
                 q++;
             }
         }
@@ -834,6 +861,20 @@ paint_kernel(const PaintParams P)
     // even CTAs walk the site lists forwards (alpha), odd CTAs backwards (beta): two instantiations of one loop
     if (blockIdx.x & 1) paint_jobs<T, WPT, MULTI, 1>(P, &s_job, s_part);
     else paint_jobs<T, WPT, MULTI, 0>(P, &s_job, s_part);
+}
+
+// Cluster teams: 512 threads x 2 words per CTA, 2..16 CTAs per team (cluster dims set at launch).
+__global__ void __launch_bounds__(512, 1) paint_cluster_kernel(const PaintParams P)
+{
+    __shared__ int s_job;
+    __shared__ __align__(16) float s_part[2][32];
+    __shared__ float s_cpart[2];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) (&s_part[0][0])[i] = 0.f; // a CTA of a cluster may be one warp
+    __syncthreads();
+    const unsigned team = blockIdx.x / cooperative_groups::this_cluster().num_blocks();
+    if (team & 1) paint_jobs<float, 2, true, 1, true>(P, &s_job, s_part, s_cpart);
+    else paint_jobs<float, 2, true, 0, true>(P, &s_job, s_part, s_cpart);
+    cooperative_groups::this_cluster().sync(); // no CTA may exit while another still reads its shared memory
 }
 
 // =========================================================================================

@@ -248,10 +248,34 @@ def test_device_record_encoder_run_rule_edges():
 
 
 def test_unsupported_sizes_fail_loudly():
-    hap = np.full((40, 33000), ord("0"), np.uint8)
+    # fp64 verification mode has no cluster variant: one CTA of 384 threads x 1 word
+    hap = np.full((40, 12320), ord("0"), np.uint8)
     with pytest.raises(capi.PaintError) as e:
-        capi.DeviceChunk.from_arrays(hap, np.full(40, 1e-3), np.array([0, 40], np.int32))
+        capi.DeviceChunk.from_arrays(hap, np.full(40, 1e-3), np.array([0, 40], np.int32), fp64=True)
     assert e.value.code == -6
+
+
+# ---- teams of several CTAs: thread-block clusters, sums through distributed shared memory ---------------------
+@pytest.mark.parametrize("N,L,W,seed,cluster,nk", [(2100, 900, 3, 8, 2, 40), (2100, 900, 3, 8, 4, 40), (5000, 500, 2, 9, 2, 24),
+                                                  (5000, 500, 2, 9, 3, 24)])
+def test_forced_cluster_teams_match_oracle(N, L, W, seed, cluster, nk):
+    hap, r, wb = make_case(N, L, W, seed)
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        c.set_tune(cluster=cluster)
+        g = c.paint_targets(0, nk)
+        assert g.stats["ctas"] % (2 * cluster) == 0
+    compare(g, oracle.paint_targets(hap, r, wb, THETA, 0, nk))
+
+
+@pytest.mark.parametrize("N,L,nk", [(40000, 160, 6), (70001, 120, 4)])
+def test_more_haplotypes_than_one_cta_can_own(N, L, nk):
+    """N > 32768: the team is a cluster of 2 (N=40000) or 3 (N=70001, with a tail) CTAs of 512 / 384 threads."""
+    hap, r, wb = make_case(N, L, 2, 31)
+    ks = [0, N // 3, N - 1 - nk]
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        for k0 in ks:
+            g = c.paint_targets(k0, k0 + nk)
+            compare(g, oracle.paint_targets(hap, r, wb, THETA, k0, k0 + nk))
 
 
 # ---- golden fixtures and the reference binary ---------------------------------------------------
