@@ -10,13 +10,14 @@ cps = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 nk = int(sys.argv[6]) if len(sys.argv) > 6 else N
 nodense = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 fsel = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+cluster = int(sys.argv[9]) if len(sys.argv) > 9 else 0
 hap, bp = synth.block_kingman(N, L, 1)
 r = chunkio.r_from_rpos(chunkio.uniform_map_rpos(bp))
 mem = 5.0 if N <= 1000 else (50.0 if N <= 5000 else 100.0)
 wb = chunkio.window_boundaries(hap, mem)
 with capi.DeviceChunk.from_arrays(hap, r, wb, 0.001) as c:
     import ctypes as C
-    t = capi.RpTune(wpt, cps); t.reserved[0] = nodense; t.reserved[1] = fsel
+    t = capi.RpTune(wpt, cps); t.reserved[0] = nodense; t.reserved[1] = fsel; t.reserved[3] = cluster
     capi.check(capi.lib().rp_chunk_set_tune(c._h, C.byref(t)))
     for it in range(reps):
         st = c.paint_targets_device(0, nk)
