@@ -36,7 +36,7 @@ extern "C" {
 #define RP_ECUDA (-3)     /* CUDA runtime error (message has the details)  */
 #define RP_ENODEVICE (-4) /* no usable CUDA device                         */
 #define RP_ENOMEM (-5)
-#define RP_EUNSUPPORTED (-6) /* e.g. N beyond what one CTA can own        */
+#define RP_EUNSUPPORTED (-6) /* e.g. N beyond a 16-CTA cluster (524288), fp64 mode beyond one CTA */
 
 /* flags */
 #define RP_FP64 1u /* verification mode: fp64 state and sums (default fp32 state, as north_star) */

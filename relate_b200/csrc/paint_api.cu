@@ -1203,14 +1203,15 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     hc.hap = static_cast<char *>(hap_in.p);
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     HapFeed feed;
-    feed.slice = (size_t)4 << 20;
+    feed.slice = (size_t)(getenv("RP_SLICE_KB") ? atoi(getenv("RP_SLICE_KB")) : 1024) << 10;
     feed.nsl = (int)((nchar + feed.slice - 1) / feed.slice);
     feed.ready.reset(new std::atomic<int>[feed.nsl]);
     for (int i = 0; i < feed.nsl; i++) feed.ready[i].store(0);
     std::atomic<int> next_slice{0}, readers_left{0};
     double t_loaded = t0;
     std::vector<std::thread> readers;
-    const int nread = (int)std::max(1u, std::min<unsigned>({8u, hw, (unsigned)feed.nsl}));
+    const unsigned want_readers = getenv("RP_READERS") ? (unsigned)atoi(getenv("RP_READERS")) : 8u;
+    const int nread = (int)std::max(1u, std::min<unsigned>({want_readers, hw, (unsigned)feed.nsl}));
     readers_left = nread;
     for (int t = 0; t < nread; t++)
         readers.emplace_back([&]() {
