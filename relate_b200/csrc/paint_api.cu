@@ -441,12 +441,12 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
                                             c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>(), nor_out);
     } else {
         auto *e = c->ent.as<rp::EntF>() + pad;
-        rp::fill_sites_kernel<<<gw, th, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->off.as<long long>(), e);
+        rp::fill_sites_cta_kernel<rp::EntF, 8><<<nt, 256, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->off.as<long long>(), e);
         rp::boundaries_kernel<<<gb, th, 0, s>>>(e, c->off.as<long long>(), nt, W, c->wbdev.as<int>(), c->ia.as<int>(),
                                                 c->ib.as<int>(), c->sb.as<int>(), c->se.as<int>());
-        rp::tables_kernel<rp::EntF, 0><<<gw, th, 0, s>>>(e, c->off.as<long long>(), nt, c->L, W, c->r.as<double>(),
-                                            c->Phi.as<double>(), c->Plo.as<double>(), tc, c->ia.as<int>(),
-                                            c->ib.as<int>(), c->lsA.as<double>(), c->lsB.as<double>(), nor_out);
+        rp::tables_cta_kernel<rp::EntF, 8><<<nt, 256, 0, s>>>(e, c->off.as<long long>(), nt, c->L, W, c->Phi.as<double>(),
+                                                             c->Plo.as<double>(), tc, c->ia.as<int>(), c->ib.as<int>(),
+                                                             c->lsA.as<double>(), c->lsB.as<double>(), nor_out);
     }
     RP_CUDA(cudaGetLastError());
     launches += 3;

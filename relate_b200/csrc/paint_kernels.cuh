@@ -217,6 +217,48 @@ __global__ void fill_sites_kernel(const uint32_t *__restrict__ GT, int lw, int L
     if (lane == 0) e[base].site = L - 1;
 }
 
+// The same with one CTA of NW warps per target: warp s counts, then fills, the contiguous share s of the row's words.
+template <typename ENT, int NW>
+__global__ void __launch_bounds__(32 * NW) fill_sites_cta_kernel(const uint32_t *__restrict__ GT, int lw, int L, int k0, int nt,
+                                                                 const long long *__restrict__ off, ENT *__restrict__ ent)
+{
+    __shared__ int s_cnt[NW];
+    const int kk = blockIdx.x, lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    if (kk >= nt) return;
+    const uint32_t *row = GT + (size_t)(k0 + kk) * lw;
+    ENT *e = ent + off[kk];
+    const int groups = (lw + 31) >> 5; // groups of 32 words
+    const int w_lo = (int)(((long long)groups * seg / NW) << 5), w_hi = min(lw, (int)(((long long)groups * (seg + 1) / NW) << 5));
+    int c = 0;
+    for (int w = w_lo + lane; w < w_hi; w += 32) c += __popc(interior_mask(row[w], w, L));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_cnt[seg] = c;
+    __syncthreads();
+    int base = 1;
+    for (int sgm = 0; sgm < seg; sgm++) base += s_cnt[sgm];
+    if (threadIdx.x == 0) e[0].site = 0;
+    for (int w0 = w_lo; w0 < w_hi; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t word = (w < w_hi) ? interior_mask(row[w], w, L) : 0u;
+        const int cw = __popc(word);
+        int incl = cw;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int pos = base + incl - cw;
+        while (word) {
+            const int b = __ffs(word) - 1;
+            word &= word - 1;
+            e[pos++].site = w * 32 + b;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (seg == NW - 1 && lane == 0) e[base].site = L - 1;
+}
+
 // ---------------------------------------------------------------------------------------
 // Window boundary sites (fast_painting.cpp:60-69,98-107,150):
 //   begin[0] = 0;  begin[w] = last visited site < wb[w];  end[w] = first visited site >= wb[w+1];  end[W-1] = L-1.
@@ -340,6 +382,99 @@ __global__ void tables_kernel(ENT *__restrict__ ent, const long long *__restrict
     const double norm = log(tc.Nm1) - (double)D * tc.log_ntheta;
     __syncwarp();
     for (int w = lane; w < W; w += 32) ob[w] = norm + (carry - ob[w]);
+}
+
+// The same tables with one CTA (NW warps) per target: warp s owns the contiguous segment [D*s/NW, D*(s+1)/NW) rounded to
+// 32-entry tiles, scans it locally, and the segments' totals are combined through shared memory afterwards.  Eight
+// times the parallelism of the warp-per-target kernel (one warp per target left the kernel latency-bound: 0.22 ms at
+// config 2), at the price of a different association of the fp64 sums (relative 1e-16): used by the fp32 painter; the
+// fp64 verification mode keeps the sequential order of tables_kernel.
+template <typename ENT, int NW>
+__global__ void __launch_bounds__(32 * NW) tables_cta_kernel(ENT *__restrict__ ent, const long long *__restrict__ off, int nt, int L,
+                                                             int W, const double *__restrict__ Phi, const double *__restrict__ Plo,
+                                                             TableConsts tc, const int *__restrict__ ia, const int *__restrict__ ib,
+                                                             double *__restrict__ lsA, double *__restrict__ lsB,
+                                                             double *__restrict__ nor_out)
+{
+    __shared__ double s_tot[NW];
+    const int kk = blockIdx.x, lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    if (kk >= nt) return;
+    ENT *e = ent + off[kk];
+    double *no = nor_out ? nor_out + off[kk] : nullptr;
+    const int D = (int)(off[kk + 1] - off[kk]);
+    const int *ja = ia + (size_t)kk * W, *jb = ib + (size_t)kk * W;
+    double *oa = lsA + (size_t)kk * W, *ob = lsB + (size_t)kk * W;
+    const int tiles = (D + 31) >> 5;
+    auto seg_begin = [&](int sgm) { return (int)(((long long)tiles * sgm / NW) << 5); }; // first entry of segment sgm
+    const int i_lo = seg_begin(seg), i_hi = min(D, seg_begin(seg + 1));
+    // boundaries inside this segment, in window order: forward ones need cum_{ia-1} (index ia-1), backward ones cum_{ib}
+    int qa = 0, qb = 0;
+    while (qa < W && ja[qa] - 1 < i_lo) qa++; // includes ia == 0 (empty sum, written below)
+    while (qb < W && jb[qb] < i_lo) qb++;
+    int nexta = qa < W ? ja[qa] - 1 : 0x7fffffff, nextb = qb < W ? jb[qb] : 0x7fffffff;
+    double carry = 0.0;
+    constexpr int TILES = 2;
+    for (int i0 = i_lo; i0 < i_hi; i0 += 32 * TILES) {
+        double nor[TILES];
+#pragma unroll
+        for (int u = 0; u < TILES; u++) {
+            const int i = i0 + 32 * u + lane;
+            nor[u] = 0.0;
+            if (i < i_hi) {
+                const int a = e[i].site;
+                const int b = (i + 1 < D) ? e[i + 1].site : L;
+                const double x = (Phi[b] - Phi[a]) + (Plo[b] - Plo[a]);
+                nor[u] = -x + tc.log_ntheta;
+                double rho = 1.0 - exp(-x);
+                if (rho > 0.99) {
+                    rho = 0.99;
+                    nor[u] = tc.log_small + tc.log_ntheta;
+                }
+                e[i].set_c(rho / ((1.0 - rho) * tc.Nm1));
+                if (no) no[i] = nor[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TILES; u++) {
+            const int t0 = i0 + 32 * u;
+            double incl = nor[u];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                double v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            incl += carry; // sum of nor over [i_lo, i]
+            while (nexta < min(t0 + 32, i_hi)) {
+                double v = __shfl_sync(0xffffffffu, incl, nexta - t0);
+                if (lane == 0) oa[qa] = v; // provisional: without the earlier segments
+                qa++;
+                nexta = qa < W ? ja[qa] - 1 : 0x7fffffff;
+            }
+            while (nextb < min(t0 + 32, i_hi)) {
+                double v = __shfl_sync(0xffffffffu, incl, nextb - t0);
+                if (lane == 0) ob[qb] = v;
+                qb++;
+                nextb = qb < W ? jb[qb] : 0x7fffffff;
+            }
+            carry = __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    if (lane == 0) s_tot[seg] = carry;
+    __syncthreads();
+    // segment of an entry index, and the sum of the segments before it
+    auto prefix_before = [&](int idx) {
+        double p = 0.0;
+        for (int sgm = 0; sgm < NW; sgm++)
+            if (seg_begin(sgm + 1) <= idx) p += s_tot[sgm];
+        return p;
+    };
+    double total = 0.0;
+    for (int sgm = 0; sgm < NW; sgm++) total += s_tot[sgm];
+    const double norm = log(tc.Nm1) - (double)D * tc.log_ntheta;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        oa[w] = (ja[w] == 0) ? 0.0 : oa[w] + prefix_before(ja[w] - 1);
+        ob[w] = norm + (total - (ob[w] + prefix_before(jb[w])));
+    }
 }
 
 // ---------------------------------------------------------------------------------------
