@@ -558,9 +558,11 @@ int encode_device(rp_chunk *c, int nt, rp_stats *st)
     P.rec_off = c->rec_off.as<long long>();
     P.img_off = c->img_off.as<long long>();
     const long long nvec = (long long)nw * 2;
-    const unsigned grid = (unsigned)std::min<long long>((nvec + 127) / 128, (long long)c->sm_count * 12);
+    const unsigned grid = (unsigned)std::min<long long>((nvec + 3) / 4, (long long)c->sm_count * 16); // 4 vectors (warps) per CTA
     RP_CUDA(cudaEventRecord(c->ev[0], s));
-    rp::rle_kernel<false><<<grid, 128, 0, s>>>(P);
+    const bool short_vec = N <= 4096; // 32 x 32-element blocks keep all lanes busy on short vectors
+    if (short_vec) rp::rle_kernel<false, 32><<<grid, 128, 0, s>>>(P);
+    else rp::rle_kernel<false, 64><<<grid, 128, 0, s>>>(P);
     rp::rle_offsets_kernel<<<W, 256, 0, s>>>(c->rleK.as<int>(), nt, W, c->rec_off.as<long long>(),
                                              c->win_bytes.as<long long>());
     rp::rle_image_scan_kernel<<<1, 32, 0, s>>>(c->win_bytes.as<long long>(), W, c->img_off.as<long long>());
@@ -571,7 +573,8 @@ int encode_device(rp_chunk *c, int nt, rp_stats *st)
     const long long total = c->h_img_off[W];
     RP_TRY(c->image.ensure((size_t)total));
     P.image = c->image.as<char>();
-    rp::rle_kernel<true><<<grid, 128, 0, s>>>(P);
+    if (short_vec) rp::rle_kernel<true, 32><<<grid, 128, 0, s>>>(P);
+    else rp::rle_kernel<true, 64><<<grid, 128, 0, s>>>(P);
     RP_CUDA(cudaGetLastError());
     RP_CUDA(cudaEventRecord(c->ev[1], s));
     RP_CUDA(cudaStreamSynchronize(s));

@@ -1573,84 +1573,155 @@ __global__ void rle_image_scan_kernel(const long long *__restrict__ win_bytes, i
     }
 }
 
-// One THREAD per vector: the rule is sequential in the run heads and about half of all elements start a run, so a
-// warp-per-vector scan (ballot + ffs + shuffle per head) spends ~50 cycles per element.  Here a warp owns 32 vectors;
-// it stages 32 x 32 tiles through shared memory (coalesced 128-byte row segments in, conflict-free column reads out)
-// and every lane walks its own vector with a handful of instructions per element.  `EMIT=false` counts runs,
-// `EMIT=true` writes the records; each lane appends to its own record, consecutive addresses over time, so the L2
-// merges the 4-byte stores into full sectors.
-template <bool EMIT> __global__ void __launch_bounds__(128) rle_kernel(const RleParams P)
+// One WARP per vector, 32 segments scanned at once.  The rule is sequential only through the current run head, and a
+// scan that starts from a wrong head falls into step with the true one at the first position where both start a run
+// (about every other element does).  Per block of 32 x SEG elements (staged in shared memory, segment stride SEG+1 floats:
+// conflict-free both ways): (A) every lane scans its SEG-element segment assuming its first element starts a run
+// (lane 0 starts from the true head carried over from the previous block) and keeps a 64-bit mask of run heads and its
+// final head; (B) lanes 1..31 take the final head of the lane before them and rescan from their segment's start until
+// they meet a head of their own speculative scan, correcting the mask on the way; repeated while any lane's final head
+// changed (normally once); (C) popcounts and a warp scan turn the masks into run indices; `EMIT` writes each head's
+// value and closes the previous run's length.  A warp-per-vector scan with ballot/ffs/shuffle per head spent ~50
+// cycles per element; a thread per vector is fine at config 2 (12 000 vectors) but leaves 420 warps for the 13 000
+// vectors of a batch at N = 10 000.
+__device__ __forceinline__ bool rle_joins(float head, float x)
 {
-    __shared__ float tile[4][32][33];
+    const float mn = fminf(head, x); // std::min for non-NaN inputs
+    return (double)fabsf(head - x) < 1e-3 * (double)mn;
+}
+
+template <bool EMIT, int SEG> __global__ void __launch_bounds__(128) rle_kernel(const RleParams P)
+{
+    static_assert(SEG == 32 || SEG == 64, "segments of 32 (short vectors) or 64 elements");
+    constexpr int STRIDE = SEG + 1, BLK = 32 * SEG, SHIFT = SEG == 64 ? 6 : 5;
+    __shared__ float tile[4][32 * STRIDE];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float(*T)[33] = tile[wid];
+    float *T = tile[wid];
     const long long nvec = (long long)P.T * P.W * 2;
     const int N = P.N;
-    for (long long vec0 = ((long long)blockIdx.x * 4 + wid) * 32; vec0 < nvec; vec0 += (long long)gridDim.x * 128) {
-        const long long vec = vec0 + lane;
-        const bool live = vec < nvec;
-        const int nrows = (int)min(32ll, nvec - vec0);
+    for (long long vec = (long long)blockIdx.x * 4 + wid; vec < nvec; vec += (long long)gridDim.x * 4) {
+        const int ab = (int)(vec & 1);
+        const long long tw = vec >> 1; // k*W + w
+        const float *v = (ab ? P.beta : P.alpha) + (size_t)tw * N;
         float *vals = nullptr;
         int *lens = nullptr;
-        if (EMIT && live) {
-            const int ab = (int)(vec & 1);
-            const long long tw = vec >> 1; // k*W + w
+        if (EMIT) {
             const int w = (int)(tw % P.W);
             const int Ka = P.K[2 * tw], Kb = P.K[2 * tw + 1];
             char *blk = P.image + P.img_off[w] + P.rec_off[tw];
             char *rec = blk + 8 + (ab ? 28 + 8 * (size_t)Ka : 0);
             const int K = ab ? Kb : Ka;
-            if (!ab) {
-                reinterpret_cast<int *>(blk)[0] = P.wb[w];
-                reinterpret_cast<int *>(blk)[1] = P.wb[w + 1] - 1;
+            if (lane == 0) {
+                if (!ab) {
+                    reinterpret_cast<int *>(blk)[0] = P.wb[w];
+                    reinterpret_cast<int *>(blk)[1] = P.wb[w + 1] - 1;
+                }
+                // records are 4-byte aligned only: write the two size_t fields as 32-bit halves
+                int *h = reinterpret_cast<int *>(rec);
+                h[0] = 1; h[1] = 0; h[2] = N; h[3] = 0;
+                h[4] = (ab ? P.site_end : P.site_begin)[tw];
+                reinterpret_cast<float *>(rec)[5] = (ab ? P.ls_beta : P.ls_alpha)[tw];
+                h[6] = K;
             }
-            // records are 4-byte aligned only: write the two size_t fields as 32-bit halves
-            int *h = reinterpret_cast<int *>(rec);
-            h[0] = 1; h[1] = 0; h[2] = N; h[3] = 0;
-            h[4] = (ab ? P.site_end : P.site_begin)[tw];
-            reinterpret_cast<float *>(rec)[5] = (ab ? P.ls_beta : P.ls_alpha)[tw];
-            h[6] = K;
             vals = reinterpret_cast<float *>(rec + 28);
             lens = reinterpret_cast<int *>(rec + 28 + 4 * (size_t)K);
         }
-        float head = 0.f;
-        int k = 0, runlen = 1;
-        for (int j0 = 0; j0 < N; j0 += 32) {
-            const int cols = min(32, N - j0);
+        float head_in = 0.f; // true head entering the block (block 0: element 0 is a head by definition)
+        int kbase = 0;       // runs started before this block
+        int last_head = 0;   // position of the latest head before this block
+        for (int b0 = 0; b0 < N; b0 += BLK) {
+            const int nblk = min(BLK, N - b0);
             __syncwarp();
-#pragma unroll 8
-            for (int rr = 0; rr < nrows; rr++) { // row rr of the tile: 128 contiguous bytes of vector vec0 + rr
-                const long long v2 = vec0 + rr;
-                const float *src = ((v2 & 1) ? P.beta : P.alpha) + (size_t)(v2 >> 1) * N + j0;
-                if (lane < cols) T[rr][lane] = src[lane];
-            }
+            for (int g = lane; g < nblk; g += 32) T[(g >> SHIFT) * STRIDE + (g & (SEG - 1))] = v[b0 + g];
             __syncwarp();
-            if (live) {
-                int c = 0;
-                if (j0 == 0) {
-                    head = T[lane][0];
-                    if (EMIT) vals[0] = head;
-                    c = 1;
+            const int s0 = lane * SEG;                      // segment start within the block
+            const int sn = max(0, min(SEG, nblk - s0));     // elements in this lane's segment
+            const float *seg = T + lane * STRIDE;
+            // ---- A: speculative scan ----
+            unsigned long long heads = 0ull;
+            float head = head_in;
+            const bool first_is_head = (lane > 0) || (b0 == 0);
+            if (sn > 0) {
+                int i = 0;
+                if (first_is_head) { head = seg[0]; heads = 1ull; i = 1; }
+                for (; i < sn; i++) {
+                    const float x = seg[i];
+                    if (!rle_joins(head, x)) { head = x; heads |= 1ull << i; }
                 }
-#pragma unroll 4
-                for (; c < cols; c++) {
-                    const float x = T[lane][c];
-                    const float mn = fminf(head, x); // std::min for non-NaN inputs
-                    if ((double)fabsf(head - x) < 1e-3 * (double)mn) {
-                        runlen++;
+            }
+            float hout = head; // for empty segments: passes the incoming head through (fixed up below)
+            // ---- B: replace the speculation by the true incoming head, until nothing changes ----
+            for (;;) {
+                float hin = __shfl_up_sync(0xffffffffu, hout, 1);
+                bool changed = false;
+                if (lane > 0) {
+                    if (sn == 0) {
+                        changed = hout != hin;
+                        hout = hin;
                     } else {
-                        if (EMIT) lens[k] = runlen;
-                        k++;
-                        if (EMIT) vals[k] = x;
-                        head = x;
-                        runlen = 1;
+                        float h = hin;
+                        unsigned long long nh = heads;
+                        bool met = false;
+                        for (int i = 0; i < sn; i++) {
+                            const float x = seg[i];
+                            const bool is_head = !rle_joins(h, x);
+                            const bool was_head = (heads >> i) & 1ull;
+                            if (is_head) {
+                                h = x;
+                                nh |= 1ull << i;
+                                if (was_head) { met = true; break; } // both scans restart here: identical from now on
+                            } else {
+                                nh &= ~(1ull << i);
+                            }
+                        }
+                        heads = nh;
+                        if (!met) { // the whole segment was rescanned: its final head may have changed
+                            changed = hout != h;
+                            hout = h;
+                        }
                     }
                 }
+                if (!__any_sync(0xffffffffu, changed)) break;
             }
+            // ---- C: run indices, output ----
+            const int cnt = __popcll(heads);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t2 = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t2;
+            }
+            if (EMIT) {
+                // position of the latest head before this lane's segment
+                int mylast = heads ? b0 + s0 + (63 - __clzll(heads)) : -1;
+                int prevlast = mylast;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t2 = __shfl_up_sync(0xffffffffu, prevlast, o);
+                    if (lane >= o) prevlast = max(prevlast, t2);
+                }
+                int before = __shfl_up_sync(0xffffffffu, prevlast, 1);
+                if (lane == 0) before = -1;
+                int prevpos = max(before, last_head);
+                int k = kbase + incl - cnt;
+                unsigned long long hm = heads;
+                while (hm) {
+                    const int i = __ffsll((long long)hm) - 1;
+                    hm &= hm - 1;
+                    const int pos = b0 + s0 + i;
+                    vals[k] = seg[i];
+                    if (k > 0) lens[k - 1] = pos - prevpos;
+                    prevpos = pos;
+                    k++;
+                }
+                last_head = max(last_head, __shfl_sync(0xffffffffu, prevlast, 31));
+            }
+            kbase += __shfl_sync(0xffffffffu, incl, 31);
+            head_in = __shfl_sync(0xffffffffu, hout, 31);
         }
-        if (live) {
-            if (EMIT) lens[k] = runlen;
-            else P.K[vec] = k + 1;
+        if (lane == 0) {
+            if (EMIT) lens[kbase - 1] = N - last_head;
+            else P.K[vec] = kbase;
         }
     }
 }
