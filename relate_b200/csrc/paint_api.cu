@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <future>
 #include <map>
 #include <memory>
@@ -51,6 +52,14 @@ double now_ms()
 {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// RP_TRACE=1: wall-clock marks of the stage driver on stderr (cold-start analysis)
+void trace(const char *what, int dev = -1)
+{
+    static const bool on = getenv("RP_TRACE") != nullptr;
+    static const double t_first = now_ms();
+    if (on) fprintf(stderr, "[rp %9.2f ms] dev %d: %s\n", now_ms() - t_first, dev, what);
 }
 
 struct DevBuf {
@@ -102,13 +111,14 @@ struct rp_chunk {
     // per-paint work buffers (grown on demand, reused)
     DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch, nor;
     // record encoder (device RLE): run counts, byte offsets, the W file images of the last batch
-    DevBuf rleK, rec_off, win_bytes, img_off, image;
+    DevBuf rleK, rec_off, win_bytes, img_off, image, image_alt; // image_alt: the stage driver alternates the two
     std::vector<long long> h_img_off; // W+1 offsets of the last encoded batch
     int enc_targets = 0;              // targets in c->image (0: none)
     bool resident_all = false;        // alpha/beta/lsa/lsb hold the stepping stones of ALL targets (last paint was 0..N)
     long long *h_total = nullptr; // pinned
     cudaStream_t stream = nullptr;       // the stream every copy and kernel of this chunk is issued on
     cudaStream_t own_stream = nullptr;   // created by the library; `stream` may be replaced by a caller's
+    cudaStream_t copy_stream = nullptr;  // device->host copies of encoded records (stage driver), overlapping the next batch
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -306,6 +316,7 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
         c->sm_count = sms;
         if (major < 10) return bail(fail(RP_ENODEVICE, "device is not sm_100-class; this library ships sm_100a code only"));
         RP_CUDAB(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        RP_CUDAB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (auto &e : c->ev) RP_CUDAB(cudaEventCreate(&e));
         RP_CUDAB(cudaMallocHost(&c->h_total, sizeof(long long)));
     }
@@ -701,12 +712,13 @@ void rp_chunk_free(rp_chunk *c)
     cudaSetDevice(c->device);
     for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
                       &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch, &c->nor,
-                      &c->rleK, &c->rec_off, &c->win_bytes, &c->img_off, &c->image})
+                      &c->rleK, &c->rec_off, &c->win_bytes, &c->img_off, &c->image, &c->image_alt})
         b->release();
     if (c->h_total) cudaFreeHost(c->h_total);
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -1129,9 +1141,136 @@ struct PinnedBuf {
 
 struct DeviceWorkspace { // parked between rp_paint_chunk calls
     rp_chunk *shell = nullptr; // keeps its DevBufs, stream and events
-    PinnedBuf ha, hb;
+    PinnedBuf out;             // ring of pinned pieces the encoded records pass through on their way to the files
     PinnedBuf hap_in;          // genotype bytes of the chunk being painted with this device as devs[0]
 };
+
+// Pinned output staging is a small ring of pieces (pinning costs ~0.5 s/GB, which dominated a one-shot
+// `relate --mode Paint`): a batch's W file images are copied in pieces taken round-robin from the W windows (buffered
+// writes to one file serialise on its inode lock, so the pieces in flight should belong to different files), every
+// piece is one pwrite task at an absolute file offset (the order in which pieces, batches and devices reach the disk
+// does not matter), and a piece returns to the ring when its task is done.
+constexpr size_t kOutPiece = (size_t)4 << 20;
+constexpr int kOutPieces = 24;
+
+struct OutRing {
+    char *base = nullptr;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> free_slots;
+    std::atomic<int> pending[kOutPieces];
+    void init(char *p)
+    {
+        base = p;
+        free_slots.clear();
+        for (int i = 0; i < kOutPieces; i++) {
+            free_slots.push_back(i);
+            pending[i].store(0);
+        }
+    }
+    int acquire()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !free_slots.empty(); });
+        const int sl = free_slots.back();
+        free_slots.pop_back();
+        return sl;
+    }
+    void task_done(int sl)
+    {
+        if (pending[sl].fetch_sub(1) == 1) {
+            std::lock_guard<std::mutex> lk(mu);
+            free_slots.push_back(sl);
+            cv.notify_one();
+        }
+    }
+    void wait_all()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return (int)free_slots.size() == kOutPieces; });
+    }
+};
+
+struct WriteTask {
+    const char *src;
+    size_t len;
+    int fd;
+    long long off;
+    OutRing *ring;
+    int slot;
+};
+
+class WritePool {
+  public:
+    explicit WritePool(int nthreads)
+    {
+        for (int i = 0; i < nthreads; i++) th_.emplace_back([this] { run(); });
+    }
+    ~WritePool() { finish(); }
+    void push(const WriteTask &t)
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            if (t_first_ == 0) t_first_ = now_ms();
+            q_.push_back(t);
+        }
+        cv_.notify_one();
+    }
+    void finish()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_)
+            if (t.joinable()) t.join();
+        th_.clear();
+    }
+    bool failed() const { return err_.load() != 0; }
+    double span_ms() const { return t_first_ == 0 ? 0.0 : t_last_ - t_first_; }
+
+  private:
+    void run()
+    {
+        for (;;) {
+            WriteTask t;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                t = q_.front();
+                q_.pop_front();
+            }
+            const char *p = t.src;
+            size_t left = t.len;
+            long long off = t.off;
+            while (left > 0) {
+                const ssize_t put = pwrite(t.fd, p, left, (off_t)off);
+                if (put <= 0) {
+                    err_ = 1;
+                    break;
+                }
+                p += put;
+                off += put;
+                left -= (size_t)put;
+            }
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                t_last_ = now_ms();
+            }
+            t.ring->task_done(t.slot);
+        }
+    }
+    std::vector<std::thread> th_;
+    std::deque<WriteTask> q_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+    std::atomic<int> err_{0};
+    double t_first_ = 0, t_last_ = 0;
+};
+
 
 std::mutex g_stage_mu; // rp_paint_chunk calls are serialised (they share the cache)
 std::map<int, DeviceWorkspace> g_ws;
@@ -1161,8 +1300,7 @@ extern "C" void rp_release_cache(void)
     for (auto &kv : g_ws) {
         cudaSetDevice(kv.first);
         if (kv.second.shell) rp_chunk_free(kv.second.shell);
-        kv.second.ha.release();
-        kv.second.hb.release();
+        kv.second.out.release();
         kv.second.hap_in.release();
     }
     g_ws.clear();
@@ -1192,7 +1330,9 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     // ---- input: small files now, genotype bytes by reader threads while the devices already copy ----
     rp::HostChunk hc;
     int hap_fd = -1;
+    trace("stage begin");
     RP_CUDA(cudaSetDevice(devs[0]));
+    trace("cudaSetDevice done", devs[0]);
     {
         std::string err = rp::load_chunk_small(out_dir, chunk_index, painting, hc, &hap_fd);
         if (!err.empty()) return fail(RP_EIO, err);
@@ -1204,6 +1344,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         return RP_ENOMEM;
     }
     hc.hap = static_cast<char *>(hap_in.p);
+    trace("input staging pinned", devs[0]);
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     HapFeed feed;
     feed.slice = (size_t)(getenv("RP_SLICE_KB") ? atoi(getenv("RP_SLICE_KB")) : 1024) << 10;
@@ -1256,16 +1397,15 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     bsz = std::min<long long>(bsz, N);
     if ((int)devs.size() > 1)
         bsz = std::min<long long>(bsz, std::max<long long>(64, (N + 2 * (long long)devs.size() - 1) / (2 * (long long)devs.size())));
+    if (const char *fb = getenv("RP_BATCH_TARGETS")) bsz = std::max(1, std::min(N, atoi(fb))); // tests: force small batches
     const int B = (int)bsz;
     const int nbatch = (N + B - 1) / B;
 
     std::atomic<int> next_batch{0};
     std::mutex mu;
     std::condition_variable cv;
-    int next_write = 0;
     int first_rc = RP_OK;
     std::string first_err;
-    double ms_write = 0;
     std::vector<rp_stats> dstats(devs.size());
     auto set_error = [&](int rc, const std::string &msg) { // call with mu held
         if (first_rc == RP_OK) {
@@ -1274,40 +1414,28 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         }
         cv.notify_all();
     };
-
-    // appends batch b's W images (host memory) to the W files once every earlier batch has been written
-    auto write_batch = [&](int b, const char *img, std::vector<long long> off) {
+    // Where batch b's records start in file w = the sizes of all earlier batches' records: published as soon as a batch
+    // has been encoded, so the data itself can travel in any order.
+    std::vector<std::vector<long long>> bsize(nbatch), bbase(nbatch);
+    std::vector<char> have(nbatch, 0);
+    std::vector<long long> running(W, 0);
+    int upto = 0;
+    auto publish_sizes = [&](int b, const std::vector<long long> &off) -> bool { // false if the stage has failed
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return next_write == b || first_rc != RP_OK; });
-        if (first_rc != RP_OK) return;
-        lk.unlock(); // only batch b may write now; keep the lock free for error reports
-        const double tw = now_ms();
-        std::string err = files_open.get();
-        if (err.empty()) {
-            std::atomic<int> werr{0};
-            parallel_for(W, 16, [&](int w) { // one writer per window file
-                const char *p = img + off[w];
-                long long left = off[w + 1] - off[w];
-                while (left > 0) {
-                    const ssize_t put = write(fds[w], p, (size_t)left);
-                    if (put <= 0) {
-                        werr = 1;
-                        break;
-                    }
-                    p += put;
-                    left -= put;
-                }
-            });
-            if (werr) err = "short write to the paint files";
+        bsize[b].resize(W);
+        for (int w = 0; w < W; w++) bsize[b][w] = off[w + 1] - off[w];
+        have[b] = 1;
+        while (upto < nbatch && have[upto]) {
+            bbase[upto] = running;
+            for (int w = 0; w < W; w++) running[w] += bsize[upto][w];
+            upto++;
         }
-        lk.lock();
-        ms_write += now_ms() - tw;
-        if (!err.empty()) set_error(RP_EIO, err);
-        else {
-            next_write = b + 1;
-            cv.notify_all();
-        }
+        cv.notify_all();
+        cv.wait(lk, [&] { return upto > b || first_rc != RP_OK; });
+        return first_rc == RP_OK;
     };
+    WritePool pool((int)std::max(4u, std::min(16u, hw)));
+    std::vector<std::unique_ptr<OutRing>> rings(devs.size());
 
     auto worker = [&](int di) {
         rp_stats &st = dstats[di];
@@ -1315,43 +1443,111 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         DeviceWorkspace &ws = g_ws.at(devs[di]);
         rp_chunk *c = ws.shell;
         ws.shell = nullptr;
+        trace("worker start", devs[di]);
         int rc = chunk_from_host(devs[di], hc.N, hc.L, hc.hap, hc.r.data(), hc.wb.data(), (int)hc.wb.size(), hc.theta,
                                  flags, &c, &st, &feed);
-        PinnedBuf *pin[2] = {&ws.ha, &ws.hb};
-        std::future<void> pending[2];
-        int slot = 0;
+        trace("chunk resident (H2D + bit-pack)", devs[di]);
+        if (rc == RP_OK) rc = ws.out.ensure(kOutPiece * kOutPieces);
+        rings[di].reset(new OutRing());
+        OutRing &ring = *rings[di];
+        ring.init(static_cast<char *>(ws.out.p)); // (a null base is never used: rc != RP_OK skips the batches)
+        cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // one per copy kept in flight (+1)
+        for (auto &ev : pev)
+            if (rc == RP_OK && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) rc = fail(RP_ECUDA, "cudaEventCreate failed");
+        trace("output ring pinned", devs[di]);
+        cudaEvent_t tev[2] = {nullptr, nullptr}; // timing of a batch's copies (on the copy stream)
+        for (auto &ev : tev)
+            if (rc == RP_OK && cudaEventCreate(&ev) != cudaSuccess) rc = fail(RP_ECUDA, "cudaEventCreate failed");
+        // Drains one encoded batch: device image -> pinned pieces -> write tasks.  Runs on its own thread and the copy
+        // stream while this worker already paints the next batch into the other image buffer.
+        auto drain = [&, di](int b, const char *img, std::vector<long long> off) {
+            if (!publish_sizes(b, off)) return;
+            const std::string oerr = files_open.get();
+            if (!oerr.empty()) {
+                std::unique_lock<std::mutex> lk(mu);
+                set_error(RP_EIO, oerr);
+                return;
+            }
+            cudaSetDevice(devs[di]);
+            cudaStream_t cs = c->copy_stream;
+            // a few copies are kept queued on the stream (one event each); a piece goes to the writers as soon as its
+            // event has fired, so the copy engine never waits for this thread
+            std::vector<long long> cur(off.begin(), off.end() - 1); // next byte of every window's image to be copied
+            std::deque<std::pair<int, WriteTask>> inflight;         // (event index, task), in stream order
+            constexpr int kDepth = 4;
+            int evn = 0;
+            long long bytes = 0;
+            cudaError_t e = cudaEventRecord(tev[0], cs);
+            auto retire = [&](size_t keep) {
+                while (inflight.size() > keep && e == cudaSuccess) {
+                    e = cudaEventSynchronize(pev[inflight.front().first]);
+                    pool.push(inflight.front().second);
+                    inflight.pop_front();
+                }
+            };
+            for (bool more = true; more && e == cudaSuccess;) {
+                more = false;
+                for (int w = 0; w < W && e == cudaSuccess; w++) {
+                    if (cur[w] >= off[w + 1]) continue;
+                    const long long lo = cur[w], n = std::min<long long>((long long)kOutPiece, off[w + 1] - lo);
+                    cur[w] += n;
+                    more = true;
+                    const int sl = ring.acquire();
+                    char *dst = ring.base + (size_t)sl * kOutPiece;
+                    ring.pending[sl].store(1);
+                    e = cudaMemcpyAsync(dst, img + lo, (size_t)n, cudaMemcpyDeviceToHost, cs);
+                    if (e == cudaSuccess) e = cudaEventRecord(pev[evn], cs);
+                    inflight.emplace_back(evn, WriteTask{dst, (size_t)n, fds[w], bbase[b][w] + (lo - off[w]), &ring, sl});
+                    evn = (evn + 1) % (kDepth + 1);
+                    bytes += n;
+                    retire(kDepth);
+                }
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(tev[1], cs);
+            retire(0);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+            if (e != cudaSuccess) {
+                cudaStreamSynchronize(cs);
+                for (auto &it : inflight) ring.task_done(it.second.slot); // pieces that never reached the writers
+                std::unique_lock<std::mutex> lk(mu);
+                set_error(RP_ECUDA, std::string("copying the encoded records to the host: ") + cudaGetErrorString(e));
+                return;
+            }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, tev[0], tev[1]);
+            st.ms_d2h += ms;
+            st.d2h_bytes += bytes;
+            trace("batch copied to host", devs[di]);
+        };
+        std::thread copier;
         while (rc == RP_OK) {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (first_rc != RP_OK) break;
+            }
             const int b = next_batch.fetch_add(1);
             if (b >= nbatch) break;
             const int k0 = b * B, k1 = std::min(N, k0 + B);
             rc = paint_device(c, k0, k1, &st);
+            trace("batch painted", devs[di]);
             if (rc == RP_OK) rc = encode_device(c, k1 - k0, &st);
+            trace("batch encoded", devs[di]);
             if (rc != RP_OK) break;
-            if (pending[slot].valid()) pending[slot].get(); // this staging buffer's previous batch is on disk
-            const long long total = c->h_img_off[W];
-            rc = pin[slot]->ensure((size_t)(total + total / 8));
-            if (rc != RP_OK) break;
-            cudaError_t e = cudaEventRecord(c->ev[0], c->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(pin[slot]->p, c->image.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream);
-            if (e == cudaSuccess) e = cudaEventRecord(c->ev[1], c->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-            if (e != cudaSuccess) {
-                rc = fail(RP_ECUDA, std::string("copying the encoded records to the host: ") + cudaGetErrorString(e));
-                break;
-            }
-            float ms = 0;
-            cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-            st.ms_d2h += ms;
-            st.d2h_bytes += total;
-            pending[slot] = std::async(std::launch::async, write_batch, b, static_cast<const char *>(pin[slot]->p), c->h_img_off);
-            slot ^= 1;
+            if (copier.joinable()) copier.join(); // the previous batch has left the other image buffer
+            const char *img = c->image.as<char>();
+            std::swap(c->image, c->image_alt);    // the next batch is encoded into the other buffer
+            copier = std::thread(drain, b, img, c->h_img_off);
         }
+        if (copier.joinable()) copier.join();
         if (rc != RP_OK) {
             std::unique_lock<std::mutex> lk(mu);
             set_error(rc, g_err);
         }
-        for (auto &f : pending)
-            if (f.valid()) f.get();
+        ring.wait_all(); // every piece of this device has reached its file
+        for (auto &ev : pev)
+            if (ev) cudaEventDestroy(ev);
+        for (auto &ev : tev)
+            if (ev) cudaEventDestroy(ev);
         ws.shell = c; // park the workspace (may be nullptr if creation failed)
     };
     std::vector<std::thread> threads;
@@ -1360,6 +1556,12 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     for (auto &t : threads) t.join();
     for (auto &t : readers) t.join();
     close(hap_fd);
+    pool.finish();
+    if (pool.failed() && first_rc == RP_OK) {
+        first_rc = RP_EIO;
+        first_err = "short write to the paint files";
+    }
+    const double ms_write = pool.span_ms();
     {
         const std::string err = files_open.get();
         for (int fd : fds)

@@ -559,3 +559,17 @@ def test_config5_shape_multichunk_makechunks_then_paint_chunks(tmp_path):
         same = [filecmp.cmp(os.path.join(d, "o", f"chunk_{c}", "paint", f"relate_{w}.bin"),
                             os.path.join(d, "ora", f"chunk_{c}", "paint", f"relate_{w}.bin"), shallow=False) for w in range(W)]
         assert sum(same) >= W - 1, (c, same)
+
+
+def test_small_batches_and_the_copy_pipeline_give_the_same_files(tmp_path, monkeypatch):
+    """The stage driver with forced 37-target batches (several batches per device, alternating image buffers, pieces
+    of many batches in flight) writes byte-identical files to the single-batch run."""
+    for tag in ("one", "many"):
+        synth.make_chunk_dir(str(tmp_path / tag), 300, 2500, seed=43, n_windows=5)
+    capi.paint_chunk(str(tmp_path / "one"), 0, "0.001,1", devices=[0])
+    monkeypatch.setenv("RP_BATCH_TARGETS", "37")
+    st = capi.paint_chunk(str(tmp_path / "many"), 0, "0.001,1", devices=list(range(capi.lib().rp_device_count())))
+    assert st["n_targets"] == 300
+    for w in range(5):
+        assert filecmp.cmp(str(tmp_path / "one" / "chunk_0" / "paint" / f"relate_{w}.bin"),
+                           str(tmp_path / "many" / "chunk_0" / "paint" / f"relate_{w}.bin"), shallow=False)
