@@ -254,14 +254,21 @@ void dd_prefix(const double *r, int L, std::vector<double> &hi, std::vector<doub
 
 // Genotype bytes that are still being read from disk: slice i of `slice` bytes may be copied once ready[i] != 0
 // (1 = read, -1 = read failed).  Lets the host->device copy run behind the file reads.
+// The slices pass through a ring of `nslots` pinned slots (slice i sits in slot i % nslots): pinning the whole chunk
+// cost ~0.3 s per 0.5 GB at every cold start.  When the ring is shorter than the chunk, a slot is refilled only after
+// every device has copied the slice it held (consumed[i] == ndev).
 struct HapFeed {
     size_t slice = 0;
-    int nsl = 0;
-    std::unique_ptr<std::atomic<int>[]> ready;
+    int nsl = 0, nslots = 0, ndev = 1;
+    const char *ring = nullptr;
+    std::unique_ptr<std::atomic<int>[]> ready, consumed;
+    std::atomic<int> abort{0};
+    const char *src(int i) const { return ring + (size_t)(i % nslots) * slice; }
+    bool wraps() const { return nsl > nslots; }
 };
 
 int chunk_from_host(int device, int N, int L, const char *hap, const double *r, const int *wb, int n_wb,
-                    double theta, unsigned flags, rp_chunk **out, rp_stats *st, const HapFeed *feed = nullptr)
+                    double theta, unsigned flags, rp_chunk **out, rp_stats *st, HapFeed *feed = nullptr)
 {
     if (!out || !hap || !r || !wb) return fail(RP_EINVAL, "null argument");
     if (N < 2 || L < 2 || n_wb < 2) return fail(RP_EINVAL, "need N>=2, L>=2 and at least one window");
@@ -346,7 +353,11 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
             while ((state = feed->ready[i].load(std::memory_order_acquire)) == 0) std::this_thread::yield();
             if (state < 0) return bail(fail(RP_EIO, "short read in the chunk's .hap file"));
             const size_t at = (size_t)i * feed->slice, n = std::min(feed->slice, nchar - at);
-            RP_CUDAB(cudaMemcpyAsync(chars.as<char>() + at, hap + at, n, cudaMemcpyHostToDevice, c->stream));
+            RP_CUDAB(cudaMemcpyAsync(chars.as<char>() + at, feed->src(i), n, cudaMemcpyHostToDevice, c->stream));
+            if (feed->wraps()) { // the slot is reused: tell the readers once this device has its copy
+                RP_CUDAB(cudaStreamSynchronize(c->stream));
+                feed->consumed[i].fetch_add(1, std::memory_order_release);
+            }
         }
     }
     RP_CUDAB(cudaMemcpyAsync(c->r.p, r, (size_t)L * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1338,32 +1349,46 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         if (!err.empty()) return fail(RP_EIO, err);
     }
     const size_t nchar = (size_t)hc.L * hc.N;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    HapFeed feed;
+    const size_t ring_cap = (size_t)(getenv("RP_RING_KB") ? atoi(getenv("RP_RING_KB")) : 65536) << 10; // tests shrink it
+    feed.slice = (size_t)(getenv("RP_SLICE_KB") ? atoi(getenv("RP_SLICE_KB")) : (nchar <= ring_cap ? 1024 : 4096)) << 10;
+    feed.nsl = (int)((nchar + feed.slice - 1) / feed.slice);
+    feed.nslots = (int)std::min<size_t>((size_t)feed.nsl, std::max<size_t>(2, ring_cap / feed.slice));
+    feed.ndev = (int)devs.size();
     PinnedBuf &hap_in = g_ws.at(devs[0]).hap_in;
-    if (hap_in.ensure(nchar) != RP_OK) {
+    if (hap_in.ensure((size_t)feed.nslots * feed.slice) != RP_OK) {
         close(hap_fd);
         return RP_ENOMEM;
     }
-    hc.hap = static_cast<char *>(hap_in.p);
-    trace("input staging pinned", devs[0]);
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    HapFeed feed;
-    feed.slice = (size_t)(getenv("RP_SLICE_KB") ? atoi(getenv("RP_SLICE_KB")) : 1024) << 10;
-    feed.nsl = (int)((nchar + feed.slice - 1) / feed.slice);
+    feed.ring = static_cast<const char *>(hap_in.p);
+    hc.hap = static_cast<char *>(hap_in.p); // (only slices in the ring are addressable through it)
+    trace("input ring pinned", devs[0]);
     feed.ready.reset(new std::atomic<int>[feed.nsl]);
-    for (int i = 0; i < feed.nsl; i++) feed.ready[i].store(0);
+    feed.consumed.reset(new std::atomic<int>[feed.nsl]);
+    for (int i = 0; i < feed.nsl; i++) {
+        feed.ready[i].store(0);
+        feed.consumed[i].store(0);
+    }
     std::atomic<int> next_slice{0}, readers_left{0};
     double t_loaded = t0;
     std::vector<std::thread> readers;
     const unsigned want_readers = getenv("RP_READERS") ? (unsigned)atoi(getenv("RP_READERS")) : 8u;
-    const int nread = (int)std::max(1u, std::min<unsigned>({want_readers, hw, (unsigned)feed.nsl}));
+    const int nread = (int)std::max(1u, std::min<unsigned>({want_readers, hw, (unsigned)feed.nslots}));
     readers_left = nread;
     for (int t = 0; t < nread; t++)
         readers.emplace_back([&]() {
             for (;;) {
                 const int i = next_slice.fetch_add(1);
                 if (i >= feed.nsl) break;
+                bool ok = true;
+                if (i >= feed.nslots) // wait until every device has copied the slice that occupies the slot
+                    while (feed.consumed[i - feed.nslots].load(std::memory_order_acquire) < feed.ndev) {
+                        if (feed.abort.load()) { ok = false; break; }
+                        std::this_thread::yield();
+                    }
                 const size_t at = (size_t)i * feed.slice, n = std::min(feed.slice, nchar - at);
-                const bool ok = rp::read_hap_range(hap_fd, at, n, hc.hap + at);
+                ok = ok && rp::read_hap_range(hap_fd, at, n, const_cast<char *>(feed.src(i)));
                 feed.ready[i].store(ok ? 1 : -1, std::memory_order_release);
             }
             if (readers_left.fetch_sub(1) == 1) t_loaded = now_ms();
@@ -1447,6 +1472,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         int rc = chunk_from_host(devs[di], hc.N, hc.L, hc.hap, hc.r.data(), hc.wb.data(), (int)hc.wb.size(), hc.theta,
                                  flags, &c, &st, &feed);
         trace("chunk resident (H2D + bit-pack)", devs[di]);
+        if (rc != RP_OK) feed.abort.store(1); // readers must not wait for this device's copies
         if (rc == RP_OK) rc = ws.out.ensure(kOutPiece * kOutPieces);
         rings[di].reset(new OutRing());
         OutRing &ring = *rings[di];
