@@ -262,6 +262,10 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the painting path has no CPU fallback")
+    # stdout carries exactly one JSON line: native libraries that print to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -375,7 +379,10 @@ def main():
             if world == 1 and not args.no_cpu_baseline:
                 cb = cpu_baseline_sample()
                 line["cpu_baseline"] = cb
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
             print(json.dumps(line), flush=True)
+            os.dup2(2, 1)
         chunk.close()
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
