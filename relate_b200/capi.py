@@ -249,8 +249,11 @@ class Window:
         check(lib().rp_window_open(chunk._h, w, *[_ptr(a) for a in arrs], C.byref(h), C.byref(st)))
         return cls(chunk, h, st.as_dict())
 
-    def distance(self, snp: int) -> np.ndarray:
-        d = np.empty((self._c.N, self._c.N), np.float32)
+    def distance(self, snp: int, out: np.ndarray | None = None) -> np.ndarray:
+        """N x N distance matrix for one SNP.  ``out`` may be a preallocated float32 array; pinned memory
+        (:func:`pinned_empty`) lets the device->host copy run at PCIe speed instead of through a staging buffer."""
+        d = np.empty((self._c.N, self._c.N), np.float32) if out is None else out
+        assert d.dtype == np.float32 and d.shape == (self._c.N, self._c.N) and d.flags.c_contiguous
         check(lib().rp_window_distance(self._h, snp, _ptr(d)))
         return d
 
