@@ -109,11 +109,12 @@ struct rp_chunk {
     // resident
     DevBuf G, GT, r, Phi, Plo, wbdev, chars;
     // per-paint work buffers (grown on demand, reused)
-    DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch, nor;
+    DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch, nor, segstate, segdone;
     // record encoder (device RLE): run counts, byte offsets, the W file images of the last batch
     DevBuf rleK, rec_off, win_bytes, img_off, image, image_alt; // image_alt: the stage driver alternates the two
     std::vector<long long> h_img_off; // W+1 offsets of the last encoded batch
     int enc_targets = 0;              // targets in c->image (0: none)
+    long long last_sites = 0;         // visited sites (sum of chain lengths) of the batch being painted
     bool resident_all = false;        // alpha/beta/lsa/lsb hold the stepping stones of ALL targets (last paint was 0..N)
     long long *h_total = nullptr; // pinned
     cudaStream_t stream = nullptr;       // the stream every copy and kernel of this chunk is issued on
@@ -162,14 +163,44 @@ int plan_launch(const rp_chunk *c, LaunchPlan &lp)
 }
 
 template <typename T, int WPT, bool MULTI, bool DENSE = false>
-int launch_paint_t(const rp_chunk *c, const rp::PaintParams &P, int threads, int &ctas)
+int launch_paint_t(rp_chunk *c, rp::PaintParams &P, int threads, int &ctas)
 {
     auto kern = rp::paint_kernel<T, WPT, MULTI, DENSE>;
     int occ = 0;
     RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
     if (occ < 1) return fail(RP_ECUDA, "paint kernel does not fit on an SM");
     if (c->tune.ctas_per_sm > 0) occ = std::min(occ, c->tune.ctas_per_sm);
-    ctas = 2 * std::min(P.nt, std::max(1, occ * c->sm_count / 2)); // even CTAs paint forwards, odd ones backwards
+    const int slots = std::max(1, occ * c->sm_count / 2); // resident teams per direction
+    // Chain segments: with whole chains as jobs, a kernel whose 2*nt chains do not fill the SM sub-partitions evenly
+    // (config 2: 2000 chains on 592 schedulers = 3 or 4 each) ends when the fullest sub-partitions do.  Cut into
+    // segments whose state is parked in HBM in between, chains migrate to whichever team is free, so lightly loaded
+    // sub-partitions get through more segments; the same cut shortens the tail of multi-wave launches.
+    // Off for a launch that cannot fill half the slots (nothing to balance) and in the fp64 verification mode
+    // (its backward stepping-stone staging rows are per CTA).
+    int nseg = 1;
+    if (sizeof(T) == 4) {
+        const int want = c->tune.reserved[1];
+        if (want > 0) nseg = want;
+        else if (2 * P.nt > slots) // a park/resume costs a few microseconds: keep segments at >= ~512 steps
+            nseg = (int)std::max<long long>(1, std::min<long long>(8, c->last_sites / std::max(1, P.nt) / 512));
+    }
+    P.nseg = nseg;
+    P.segready = nullptr;
+    P.segstate = nullptr;
+    P.segstride = 0;
+    if (nseg > 1) {
+        P.segstride = (((size_t)threads * WPT * 32 + 32) * sizeof(T) + 64 + 15) & ~(size_t)15;
+        RP_TRY(c->segstate.ensure(2 * (size_t)P.nt * P.segstride));
+        const size_t rq = 2 * (size_t)P.nt * (nseg - 1) * 4;
+        RP_TRY(c->segdone.ensure(rq));
+        RP_CUDA(cudaMemsetAsync(c->segdone.p, 0, rq, c->stream));
+        P.segready = c->segdone.as<int>();
+        P.segstate = c->segstate.as<char>();
+    }
+#ifndef RP_FULLGRID
+#define RP_FULLGRID 1
+#endif
+    ctas = 2 * (int)std::min<long long>((long long)P.nt * (RP_FULLGRID ? nseg : 1), slots); // even CTAs paint forwards, odd ones backwards
     kern<<<ctas, threads, 0, c->stream>>>(P);
     RP_CUDA(cudaGetLastError());
     return RP_OK;
@@ -187,7 +218,7 @@ template <typename T, int WPT, bool MULTI> int grid_for(const rp_chunk *c, int n
     return RP_OK;
 }
 
-int launch_paint(const rp_chunk *c, rp::PaintParams &P, const LaunchPlan &lp, DevBuf &scratch, int &ctas)
+int launch_paint(rp_chunk *c, rp::PaintParams &P, const LaunchPlan &lp, DevBuf &scratch, int &ctas)
 {
     const bool fp64 = (c->flags & RP_FP64) != 0;
     if (fp64) {
@@ -420,7 +451,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
         RP_TRY(c->alpha.ensure(nw * N * 4));
         RP_TRY(c->beta.ensure(nw * N * 4));
     }
-    RP_TRY(c->queue.ensure(8));
+    RP_TRY(c->queue.ensure(16));
 
     cudaStream_t s = c->stream;
     int launches = 0;
@@ -435,6 +466,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     RP_CUDA(cudaMemcpyAsync(c->h_total, c->off.as<long long>() + nt, 8, cudaMemcpyDeviceToHost, s));
     RP_CUDA(cudaStreamSynchronize(s));
     const long long U = *c->h_total;
+    c->last_sites = U;
     // the paint kernel's prefetch reads up to 3 entries past either end of a target's list: pad both ends
     const size_t entsz = fp64 ? sizeof(rp::EntD) : sizeof(rp::EntF);
     const size_t pad = 4;
@@ -472,7 +504,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     }
     RP_CUDA(cudaGetLastError());
     launches += 3;
-    RP_CUDA(cudaMemsetAsync(c->queue.p, 0, 8, s));
+    RP_CUDA(cudaMemsetAsync(c->queue.p, 0, 16, s));
     RP_CUDA(cudaEventRecord(c->ev[1], s));
     if (!run_paint) { // site tables only (the window repaint builds on them)
         RP_CUDA(cudaStreamSynchronize(s));
@@ -722,7 +754,7 @@ void rp_chunk_free(rp_chunk *c)
     if (!c) return;
     cudaSetDevice(c->device);
     for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
-                      &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch, &c->nor,
+                      &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch, &c->nor, &c->segstate, &c->segdone,
                       &c->rleK, &c->rec_off, &c->win_bytes, &c->img_off, &c->image, &c->image_alt})
         b->release();
     if (c->h_total) cudaFreeHost(c->h_total);
@@ -985,7 +1017,7 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
                                                  win->ab.as<float>(), win->be.as<float>(), win->lsa.as<float>(), win->lsb.as<float>());
         RP_CUDAW(cudaGetLastError());
     }
-    RP_CUDAW(cudaMemsetAsync(c->queue.p, 0, 8, s));
+    RP_CUDAW(cudaMemsetAsync(c->queue.p, 0, 16, s));
     RP_CUDAW(cudaEventRecord(c->ev[1], s));
     rp::RepaintParams P{};
     P.G = c->G.as<uint32_t>();

@@ -513,6 +513,10 @@ template <typename T> struct PaintConsts { // fast_painting.hpp:26-39, already i
     T lower, upper; // rescaling band (1e-10, 1e10)
 };
 
+#ifndef RP_SPIN_NS
+#define RP_SPIN_NS 64 // poll interval of a team waiting for a parked chain
+#endif
+
 struct PaintParams {
     const uint32_t *G;     // SNP-major bits
     int wps;               // words per SNP row
@@ -526,7 +530,13 @@ struct PaintParams {
     const double *lsA, *lsB; // [nt][W] log-scale bases
     float *alpha, *beta;   // [nt][W][N]
     float *ls_alpha, *ls_beta; // [nt][W]
-    int *queue;            // two job counters: [0] forward, [1] backward
+    int *queue;            // job counters: [0] forward, [1] backward pops; [2], [3] pushes onto the ready queues
+    // Chain segments (load balance): a job is (segment, chain), segment-major; a chain's state is parked in HBM between
+    // its segments, so whichever team is free continues it.  nseg == 1: a job is a whole chain, nothing is parked.
+    int nseg;
+    int *segready;         // [2][nt*(nseg-1)] ready queue of parked chains (job+1 once pushed), zeroed before the launch
+    char *segstate;        // [2][nt] parked states of segstride bytes: team vector, tail elements, scalars
+    size_t segstride;
     double *scratch;       // fp64 mode only: [gridDim.x][N] staging rows for backward stepping stones
     int hshift;            // fixed-point headroom of the REDUX sum: S_new < 2^hshift * 2^floor(log2 S_prev) always
     int k1c, k2c;          // (277-hshift)<<23 and (hshift-23)<<23: exponent arithmetic of the fixed-point scale
@@ -628,8 +638,9 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
     const T chk = DIR ? K.ntheta : (T)1;        // the band is tested on chk*S  (B = ntheta*G backward)
     const T resc_R = DIR ? K.inv_ntheta : (T)1; // R after a rescale, before *c_i
 
+    const int nseg = CLUSTER ? 1 : P.nseg;
     for (;;) {
-        int kk;
+        int kk = 0;
         if (CLUSTER) {
             cg::cluster_group cl = cg::this_cluster();
             cl.sync(); // every CTA is done with the previous job (and with s_job)
@@ -639,20 +650,51 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             }
             cl.sync();
             kk = *s_job;
-        } else if (MULTI) {
-            __syncthreads();
-            if (t == 0) *s_job = atomicAdd(queue, 1);
-            __syncthreads();
-            kk = *s_job;
         } else {
-            kk = 0;
-            if (lane == 0) kk = atomicAdd(queue, 1);
-            kk = __shfl_sync(0xffffffffu, kk, 0);
+            // Ready queue.  Pop position `pos` of this direction: the first nt positions are the chains' first segments
+            // (ready from the start); position nt+i is the i-th chain segment that gets parked and pushed (`ready[i]`
+            // = job+1, 0 while nobody has pushed it yet).  Every lane of the polling warp polls, so the warp stays
+            // converged (a lone polling lane leaves the warp split for the whole job: 2x slower).
+            const int njobs = P.nt * nseg;
+            if (!MULTI || warp == 0) {
+                kk = 0;
+                if (lane == 0) kk = atomicAdd(queue, 1);
+                kk = __shfl_sync(0xffffffffu, kk, 0);
+                if (nseg > 1 && kk >= P.nt && kk < njobs) {
+                    const volatile int *slot = P.segready + (size_t)DIR * (njobs - P.nt) + (kk - P.nt);
+                    int v;
+                    while ((v = *slot) == 0) __nanosleep(RP_SPIN_NS);
+                    __threadfence(); // the parked state was written before the push
+                    kk = v - 1;
+                }
+            }
+            if (MULTI) {
+                __syncthreads(); // everyone is done with the previous job (and has read s_job)
+                if (t == 0) *s_job = kk;
+                __syncthreads();
+                kk = *s_job;
+            }
+            if (kk >= njobs) break;
         }
-        if (kk >= P.nt) break;
+        // job = segment * nt + chain.  A chain is cut into nseg segments; between segments its state is parked in HBM
+        // and the chain is pushed onto the ready queue, so whichever team is free continues it: teams on lightly
+        // loaded SM sub-partitions get through more segments, and all chains finish together.
+        int seg = 0;
+        if (CLUSTER) {
+            if (kk >= P.nt) break;
+        } else if (nseg > 1) {
+            seg = kk / P.nt;
+            kk -= seg * P.nt;
+        }
         const int k = P.k0 + kk;
         const long long base = P.off[kk];
         const int m = (int)(P.off[kk + 1] - base) - 1;
+        // steps [pbeg, pend) of 0..m belong to this segment (cuts at even steps: the pipeline alternates two register sets)
+        int pbeg = 0, pend = m + 1;
+        if (!CLUSTER && nseg > 1) {
+            if (seg > 0) pbeg = (int)(((long long)(m + 1) * seg / nseg) & ~1LL);
+            if (seg < nseg - 1) pend = (int)(((long long)(m + 1) * (seg + 1) / nseg) & ~1LL);
+        }
         const Ent *pe = ents + base + (DIR ? m : 0); // entry of step p is pe[p*ES]
         const int rot = k & 31, wk = k >> 5;
         bool own[WPT];
@@ -823,20 +865,21 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         uint32_t wA[WPT], wB[WPT], twA = 0, twB = 0;
         int sA, sB;   // site index whose words go INTO set A / B next
         T cA, cB;     // c of the step that computes from set A / B
-        load_words(wA, gthr + (size_t)(unsigned)site_first * rowbytes);
-        if (MULTI ? tail_warp : has_tail) twA = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)site_first * rowbytes);
-        cA = (T)pe[0].c;
-        sB = pe[ES].site;  // step 1's words go into set B during step 0
+        const int site_pbeg = pe[pbeg * ES].site; // == site_first unless this job continues a parked chain
+        load_words(wA, gthr + (size_t)(unsigned)site_pbeg * rowbytes);
+        if (MULTI ? tail_warp : has_tail) twA = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)site_pbeg * rowbytes);
+        cA = (T)pe[pbeg * ES].c;
+        sB = pe[(pbeg + 1) * ES].site;  // step pbeg+1's words go into set B during step pbeg
         sA = 0;
-        cB = (T)pe[ES].c;
-        const Ent *pnx = pe + 2 * ES; // entry p+2 while step p runs
+        cB = (T)pe[(pbeg + 1) * ES].c;
+        const Ent *pnx = pe + (pbeg + 2) * ES; // entry p+2 while step p runs
 
         T R = DIR ? (T)1 : K.prior_n; // step 0 is x = (0 + R0) * m
         uint32_t tdm = td_first;
         int q1 = q;
         bool post = false;
 
-        if (DIR) { // beta at SNP L-1 is all ones, the target included (:413-418, :433-448)
+        if (DIR && seg == 0) { // beta at SNP L-1 is all ones, the target included (:413-418, :433-448)
             int qe = q;
             while (qe < P.W && bpos(qe) == 0) qe++;
             for (int qq = q; qq < qe; qq++) {
@@ -941,6 +984,56 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             }
         };
 
+        // parks / resumes the chain's state between segments: the team vector (coalesced, L1-bypassing: the next segment
+        // usually runs on another SM), the tail elements and the team-uniform scalars
+        auto park_io = [&](bool save) {
+            char *park = P.segstate + ((size_t)DIR * P.nt + kk) * P.segstride;
+            V2 *pv = reinterpret_cast<V2 *>(park);
+            T *pt = reinterpret_cast<T *>(park + (size_t)TT * WPT * 16 * sizeof(V2));
+            double *pd = reinterpret_cast<double *>(park + (size_t)TT * WPT * 16 * sizeof(V2) + 32 * sizeof(T));
+            int *pi = reinterpret_cast<int *>(pd + 2);
+            if (save) {
+#pragma unroll
+                for (int j = 0; j < WPT; j++)
+#pragma unroll
+                    for (int e = 0; e < 16; e++) __stcg(&pv[(size_t)(j * 16 + e) * TT + t], a[j][e]);
+                if (tail_warp) __stcg(&pt[lane], tl);
+                if (t == 0) {
+                    __stcg(&pd[0], lsr);
+                    __stcg(&pd[1], (double)R);
+                    __stcg(&pi[0], (int)tdm);
+                    __stcg(&pi[1], q);
+                    __stcg(&pi[2], q1);
+                    __stcg(&pi[3], post ? 1 : 0);
+                    __stcg(&pi[4], pev);
+                    __stcg(&pi[5], __float_as_int(k1));
+                    __stcg(&pi[6], __float_as_int(k2));
+                }
+                __threadfence();
+                if (MULTI) __syncthreads(); else __syncwarp();
+                if (t == 0) { // push the chain's next segment onto the ready queue
+                    const int tp = atomicAdd(queue + 2, 1);
+                    atomicExch(P.segready + (size_t)DIR * (P.nt * (nseg - 1)) + tp, (seg + 1) * P.nt + kk + 1);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < WPT; j++)
+#pragma unroll
+                    for (int e = 0; e < 16; e++) a[j][e] = __ldcg(&pv[(size_t)(j * 16 + e) * TT + t]);
+                if (tail_warp) tl = __ldcg(&pt[lane]);
+                lsr = __ldcg(&pd[0]);
+                R = (T)__ldcg(&pd[1]);
+                tdm = (uint32_t)__ldcg(&pi[0]);
+                q = __ldcg(&pi[1]);
+                q1 = __ldcg(&pi[2]);
+                post = __ldcg(&pi[3]) != 0;
+                pev = __ldcg(&pi[4]);
+                k1 = __int_as_float(__ldcg(&pi[5]));
+                k2 = __int_as_float(__ldcg(&pi[6]));
+            }
+        };
+        if (!CLUSTER && seg > 0) park_io(false);
+
         // one step computing from set X while filling set Y
         auto do_step = [&](int p, uint32_t (&wX)[WPT], uint32_t &twX, T &cX, int &sX,
                            uint32_t (&wY)[WPT], uint32_t &twY, T &cY, int &sY) {
@@ -967,10 +1060,14 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         };
 
         // steps 0..m, two per iteration (even steps compute from set A, odd ones from set B)
-        for (int p = 0; p <= m; p += 2) {
+        for (int p = pbeg; p < pend; p += 2) {
             do_step(p, wA, twA, cA, sA, wB, twB, cB, sB);
-            if (p + 1 > m) break;
+            if (p + 1 >= pend) break;
             do_step(p + 1, wB, twB, cB, sB, wA, twA, cA, sA);
+        }
+        if (!CLUSTER && seg != nseg - 1) { // park the chain; whichever team takes job (seg+1, chain) continues it
+            park_io(true);
+            continue;
         }
 
         if (!DIR) { // alpha stepping stones at the last visited site

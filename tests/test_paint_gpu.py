@@ -267,6 +267,27 @@ def test_forced_cluster_teams_match_oracle(N, L, W, seed, cluster, nk):
     compare(g, oracle.paint_targets(hap, r, wb, THETA, 0, nk))
 
 
+@pytest.mark.parametrize("N,L,W,seed,segs,nk", [(200, 3000, 4, 21, 5, None), (1000, 1500, 5, 22, 8, None), (1000, 1500, 5, 22, 64, 80),
+                                                 (37, 90, 3, 23, 16, None), (2100, 900, 3, 8, 3, 60), (5000, 500, 2, 9, 7, 30)])
+def test_parked_chain_segments_are_bit_identical_to_whole_chains(N, L, W, seed, segs, nk):
+    """Load balance by chain segments (a chain's state is parked in HBM between segments and continued by whichever
+    team is free) must not change a single bit: same arithmetic, same order.  Covers single-warp teams with and without
+    a tail word, multi-warp teams, more segments than steps, and (second case) the automatic choice."""
+    hap, r, wb = make_case(N, L, W, seed)
+    nk = N if nk is None else nk
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        c.set_tune(segments=1)
+        a = c.paint_targets(0, nk)
+        c.set_tune(segments=segs)
+        b = c.paint_targets(0, nk)
+        c.set_tune()
+        d = c.paint_targets(0, nk)
+    for x in (b, d):
+        assert np.array_equal(a.alpha, x.alpha) and np.array_equal(a.beta, x.beta)
+        assert np.array_equal(a.ls_alpha, x.ls_alpha) and np.array_equal(a.ls_beta, x.ls_beta)
+        assert np.array_equal(a.site_begin, x.site_begin) and np.array_equal(a.site_end, x.site_end)
+
+
 @pytest.mark.parametrize("N,L,nk", [(40000, 160, 6), (70001, 120, 4)])
 def test_more_haplotypes_than_one_cta_can_own(N, L, nk):
     """N > 32768: the team is a cluster of 2 (N=40000) or 3 (N=70001, with a tail) CTAs of 512 / 384 threads."""
