@@ -559,6 +559,17 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
         if (P.hshift > 20) return fail(RP_EUNSUPPORTED, "theta too close to 1 for the fp32 painter (use RP_FP64)");
         P.k1c = (277 - P.hshift) << 23;
         P.k2c = (P.hshift - 23) * (1 << 23);
+        // band edges in fixed-point units of the REDUX sum, as float bit patterns to which the kernel adds the exponent of
+        // the previous sum: forward B = S, backward B = ntheta*S
+        for (int dir = 0; dir < 2; dir++) {
+            const float chk = dir ? P.cf.ntheta : 1.0f;
+            const float lo = P.cf.lower / chk * 1.000002f, hi = P.cf.upper / chk * 0.999998f;
+            int lob, hib;
+            memcpy(&lob, &lo, 4);
+            memcpy(&hib, &hi, 4);
+            P.xlo[dir] = lob + P.k1c - (127 << 23);
+            P.xhi[dir] = hib + P.k1c - (127 << 23);
+        }
     }
     int ctas = 0;
     c->resident_all = false;

@@ -540,6 +540,8 @@ struct PaintParams {
     double *scratch;       // fp64 mode only: [gridDim.x][N] staging rows for backward stepping stones
     int hshift;            // fixed-point headroom of the REDUX sum: S_new < 2^hshift * 2^floor(log2 S_prev) always
     int k1c, k2c;          // (277-hshift)<<23 and (hshift-23)<<23: exponent arithmetic of the fixed-point scale
+    int xlo[2], xhi[2];    // per direction: float bits of band_lower/chk resp. band_upper/chk (a hair inside), pre-scaled so
+                           // that as_float(x - exponent bits of the previous sum) is the band edge in fixed-point units
     PaintConsts<float> cf;
     PaintConsts<double> cd;
 };
@@ -662,10 +664,13 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 kk = __shfl_sync(0xffffffffu, kk, 0);
                 if (nseg > 1 && kk >= P.nt && kk < njobs) {
                     const volatile int *slot = P.segready + (size_t)DIR * (njobs - P.nt) + (kk - P.nt);
-                    int v;
-                    while ((v = *slot) == 0) __nanosleep(RP_SPIN_NS);
+                    int v; // the loop condition is a warp vote: all lanes leave together
+                    do {
+                        v = *slot;
+                        if (v == 0) __nanosleep(RP_SPIN_NS);
+                    } while (!__all_sync(0xffffffffu, v != 0));
                     __threadfence(); // the parked state was written before the push
-                    kk = v - 1;
+                    kk = __shfl_sync(0xffffffffu, v - 1, 0); // provably warp-uniform
                 }
             }
             if (MULTI) {
@@ -724,12 +729,19 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         T tl = (T)0;
         double lsr = 0.0; // log-scale added by rescaling
         // fixed-point scale of the REDUX sum (fp32 single-warp teams), from the exponent of the previous sum
-        float k1 = 0.f, k2 = 0.f;
-        auto set_scale = [&](float sprev) {
-            const int ebs = __float_as_int(sprev) & 0x7f800000;
+        // tlo / thi: the rare path is taken when the integer (high) part of the fixed-point sum falls outside
+        // [tlo, thi].  That is a superset of {B outside the rescaling band} u {fewer than 64 units left}: the sum is
+        // hi + d with |d| <= 16, so B < lower implies hi < X + 17 <= 1.5 X + 64 (X = lower/chk in fixed-point units) and
+        // B > upper implies hi > Y - 17.  The handler repeats the exact test, so results do not change; what changes is
+        // that the branch needs only REDUX -> I2F -> two compares instead of the whole float reconstruction of B.
+        float k1 = 0.f, k2 = 0.f, tlo = 0.f, thi = 0.f;
+        auto set_scale_e = [&](int ebs) {
             k1 = __int_as_float(P.k1c - ebs);   // 2^(23 - hshift - E)
             k2 = __int_as_float(ebs + P.k2c);   // 2^(E + hshift - 23)
+            tlo = fmaf(__int_as_float(P.xlo[DIR] - ebs), 1.5f, 64.0f);
+            thi = __int_as_float(P.xhi[DIR] - ebs) - 17.0f;
         };
+        auto set_scale = [&](float sprev) { set_scale_e(__float_as_int(sprev) & 0x7f800000); };
         if (!MULTI && sizeof(T) == 4) set_scale(DIR ? (float)P.N : 1.0f);
 
         // x <- (x + R) * (mis ? tau : 1);  returns the team-wide sum.  mis = target derived && reference
@@ -773,7 +785,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             return S;
         };
         // team-wide sum: warp butterfly, then (multi-warp teams) one bar.sync and a shared-memory exchange
-        auto reduce = [&](T S, int parity, bool &lowprec) -> T {
+        auto reduce = [&](T S, int parity, float tlo_e, int &sa_out, bool &rare) -> T {
             if (!MULTI && sizeof(T) == 4) {
                 // Single-warp fp32 teams: the 32 lane sums are added as 46-bit fixed point with two integer REDUX
                 // (exact, order-free) instead of a 5-level shuffle butterfly (150 -> ~70 cycles of dependent latency).
@@ -791,8 +803,10 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 const float b = fmaf(rem, 8388608.0f, 12582912.0f);
                 const int sa = __reduce_add_sync(0xffffffffu, __float_as_int(a)) - (int)(32u * 0x4B000000u);
                 const int sb = __reduce_add_sync(0xffffffffu, __float_as_int(b)) - (int)(32u * 0x4B400000u);
-                lowprec = sa < 64; // handled on the rare path (the step is redone with the butterfly)
-                return (T)(fmaf((float)sb, 1.0f / 8388608.0f, (float)sa) * k2);
+                const float fsa = (float)sa;
+                sa_out = sa;       // sa < 64: handled on the rare path (the step is redone with the butterfly)
+                rare = (fsa < tlo_e) || (fsa > thi);
+                return (T)(fmaf((float)sb, 1.0f / 8388608.0f, fsa) * k2);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
@@ -1015,6 +1029,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                     const int tp = atomicAdd(queue + 2, 1);
                     atomicExch(P.segready + (size_t)DIR * (P.nt * (nseg - 1)) + tp, (seg + 1) * P.nt + kk + 1);
                 }
+                if (!MULTI) __syncwarp(); // reconverge here, provably: without it ptxas guards every REDUX / vote of the hot loop with a BRA.DIV
             } else {
 #pragma unroll
                 for (int j = 0; j < WPT; j++)
@@ -1028,8 +1043,8 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 q1 = __ldcg(&pi[2]);
                 post = __ldcg(&pi[3]) != 0;
                 pev = __ldcg(&pi[4]);
-                k1 = __int_as_float(__ldcg(&pi[5]));
-                k2 = __int_as_float(__ldcg(&pi[6]));
+                set_scale_e(P.k1c - __ldcg(&pi[5])); // k1, k2 and the branch thresholds follow from the parked k1
+                (void)pi[6];
             }
         };
         if (!CLUSTER && seg > 0) park_io(false);
@@ -1046,17 +1061,25 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             pnx += ES;
             sX = e2.site;
             T Sl = step_local(wX, twX, tdm, R);
-            bool lowprec = false;
-            const T S = reduce(Sl, p & 1, lowprec);
+            int sa = 64;
+            bool rare = false;
+            // a pending event (stepping-stone store, last step, ...) is folded into the lower threshold ahead of time, so
+            // that nothing but the two compares sits between the REDUX and the branch
+            const bool ev = (p + 1 == pev);
+            const float tlo_e = ev ? __int_as_float(0x7f800000) : tlo;
+            const T S = reduce(Sl, p & 1, tlo_e, sa, rare);
             const T ccur = cX;
             R = S * ccur;
             cX = (T)e2.c;
-            if (!MULTI && sizeof(T) == 4) set_scale((float)S);
-            const T B = DIR ? chk * S : S;
-            const bool oob = (B < band_lo) || (B > band_hi);
+            if (!MULTI && sizeof(T) == 4) {
+                set_scale((float)S);
+            } else {
+                const T B = DIR ? chk * S : S;
+                rare = (B < band_lo) || (B > band_hi) || ev;
+            }
             // the rare path is taken by all threads or none (S is the team-wide sum): tell the compiler with a vote, so
             // the branch needs no reconvergence bookkeeping
-            if (__builtin_expect(__any_sync(0xffffffffu, oob || lowprec || (p + 1 == pev)), 0)) handler(p, S, ccur, Sl, lowprec);
+            if (__builtin_expect(__any_sync(0xffffffffu, rare), 0)) handler(p, S, ccur, Sl, sa < 64);
         };
 
         // steps 0..m, two per iteration (even steps compute from set A, odd ones from set B)
