@@ -134,7 +134,7 @@ struct LaunchPlan {
 
 int plan_launch(const rp_chunk *c, LaunchPlan &lp)
 {
-    const int nfw = c->nfw;
+    const int nfw = (c->N + 31) / 32; // genotype words per row, a partial last word included (the painter pads it with phantoms)
     const bool fp64 = (c->flags & RP_FP64) != 0;
     int wpt = c->tune.words_per_thread;
     if (wpt != 0 && wpt != 1 && wpt != 2) return fail(RP_EINVAL, "words_per_thread must be 0, 1 or 2");
@@ -524,7 +524,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     P.N = N;
     P.L = c->L;
     P.W = W;
-    P.nfw = c->nfw;
+    P.nfw = (N + 31) / 32; // the partial last word counts as a word of the team
     P.tailn = c->tailn;
     P.k0 = k0;
     P.nt = nt;

@@ -521,7 +521,7 @@ struct PaintParams {
     const uint32_t *G;     // SNP-major bits
     int wps;               // words per SNP row
     int N, L, W;
-    int nfw;               // full 32-haplotype words: N / 32
+    int nfw;               // 32-haplotype words per row, a partial last word included: ceil(N / 32)
     int tailn;             // N % 32
     int k0, nt;            // targets [k0, k0+nt); each is one forward and one backward job
     const void *ent;       // EntF[] or EntD[], padded by 4 valid entries at both ends
@@ -629,13 +629,17 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
     // word or padding, so threads beyond the row's end read word 0 and ignore it.
     const char *gthr = reinterpret_cast<const char *>(P.G + ((gt * WPT + WPT - 1) < P.wps ? gt * WPT : 0));
     asm volatile("" : "+l"(gthr));
-    const bool has_tail = P.tailn > 0;                 // kernel-uniform
-    const bool tail_warp = has_tail && (gt < 32);
-    const bool tail_lane = tail_warp && (lane < P.tailn);
-    const char *gtail = reinterpret_cast<const char *>(P.G + (has_tail ? P.nfw : 0));
-    uint32_t lanebit = 1u << lane;
-    asm volatile("" : "+l"(gtail));
-    asm volatile("" : "+r"(lanebit));
+    // The last word of a row may be partial (P.tailn = N % 32 haplotypes).  Its owner treats it as a full word: the
+    // missing slots are phantom haplotypes with genotype bit 0 (the packer pads with zeros), i.e. haplotypes that
+    // mismatch wherever the target is derived.  All phantoms carry the same value, which every thread tracks in one
+    // scalar (xph, the same two roundings per step as the registers, so it is bit-identical to them) and the owner
+    // subtracts nph * xph from its sum.  A phantom is never larger than any real element (same R, never a larger
+    // multiplier), so xph <= S/N and the subtraction costs no precision.  No extra load, predicate or branch per step.
+    T nph = (T)0;
+#pragma unroll
+    for (int j = 0; j < WPT; j++)
+        if (P.tailn > 0 && gt * WPT + j == P.nfw - 1) nph = (T)(32 - P.tailn);
+    opaque(nph);
 
     const T chk = DIR ? K.ntheta : (T)1;        // the band is tested on chk*S  (B = ntheta*G backward)
     const T resc_R = DIR ? K.inv_ntheta : (T)1; // R after a rescale, before *c_i
@@ -704,13 +708,10 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         const int rot = k & 31, wk = k >> 5;
         bool own[WPT];
 #pragma unroll
-        for (int j = 0; j < WPT; j++) own[j] = (wk < P.nfw) && (gt * WPT + j == wk);
-        const bool tail_live = tail_lane && !((wk == P.nfw) && (lane == rot)); // valid tail slot that is not the target
+        for (int j = 0; j < WPT; j++) own[j] = (gt * WPT + j == wk);
         T ownmul[WPT]; // 0 on the thread/word holding the target (slot 0 after rotation), else 1
 #pragma unroll
         for (int j = 0; j < WPT; j++) { ownmul[j] = own[j] ? (T)0 : (T)1; opaque(ownmul[j]); }
-        T tailmul = tail_live ? (T)1 : (T)0;
-        opaque(tailmul);
 
         // boundary bookkeeping, in the order the job meets the windows: forward w = q, backward w = W-1-q
         const int *bidx = (DIR ? P.ib : P.ia) + (size_t)kk * P.W;
@@ -726,7 +727,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         for (int j = 0; j < WPT; j++)
 #pragma unroll
             for (int e = 0; e < 16; e++) a[j][e] = RT::mk((T)0, (T)0);
-        T tl = (T)0;
+        T xph = (T)0, mph = (T)1; // phantom value and its multiplier (tau where the target is derived)
         double lsr = 0.0; // log-scale added by rescaling
         // fixed-point scale of the REDUX sum (fp32 single-warp teams), from the exponent of the previous sum
         // tlo / thi: the rare path is taken when the integer (high) part of the fixed-point sum falls outside
@@ -746,7 +747,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 
         // x <- (x + R) * (mis ? tau : 1);  returns the team-wide sum.  mis = target derived && reference
         // ancestral; tdm is all-ones when the target is derived at the site (always, except SNP 0 / L-1).
-        auto step_local = [&](const uint32_t (&w)[WPT], uint32_t tw, uint32_t tdm, T R) -> T {
+        auto step_local = [&](const uint32_t (&w)[WPT], uint32_t tdm, T R) -> T {
             // partial sums: four independent chains when a thread owns one word, two when it owns two
             // (register budget of the 96-register multi-warp variant)
             constexpr int NACC = (WPT == 1) ? 4 : 2;
@@ -776,12 +777,8 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             S0 = RT::add2(S0, S1);
             if (NACC == 4) S0 = RT::add2(S0, RT::add2(S2, S3));
             T S = S0.x + S0.y;
-            if (MULTI ? tail_warp : has_tail) {
-                T v = tl + R;
-                if (~tw & tdm & lanebit) v *= tau;
-                tl = v * tailmul;
-                S += tl;
-            }
+            xph = (xph + R) * mph;
+            S -= nph * xph;
             return S;
         };
         // team-wide sum: warp butterfly, then (multi-warp teams) one bar.sync and a shared-memory exchange
@@ -854,15 +851,11 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                         T vx = a[j][e].x + addR, vy = a[j][e].y + addR;
                         if (ones) { vx = (T)1; vy = (T)1; }
                         else if (e == 0 && own[j]) vx = (T)0;
-                        o[n0 + ((2 * e + rot) & 31)] = (O)vx;
-                        o[n0 + ((2 * e + 1 + rot) & 31)] = (O)vy;
+                        const int ix = n0 + ((2 * e + rot) & 31), iy = n0 + ((2 * e + 1 + rot) & 31);
+                        if (ix < P.N) o[ix] = (O)vx; // (a partial last word: the phantom slots are not stored)
+                        if (iy < P.N) o[iy] = (O)vy;
                     }
                 }
-            }
-            if (tail_lane) {
-                T v = tl + addR;
-                if (ones) v = (T)1; else if (!tail_live) v = (T)0;
-                o[P.nfw * 32 + lane] = (O)v;
             }
         };
 
@@ -876,12 +869,11 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         // while step p computes from set X, the genotype words of step p+1 are loaded into set Y (their site
         // index was loaded during step p-1) together with entry p+2 (site index and c, one vector load).
         // Entries up to 2 past either end of the target's list are read and never used (the table is padded).
-        uint32_t wA[WPT], wB[WPT], twA = 0, twB = 0;
+        uint32_t wA[WPT], wB[WPT];
         int sA, sB;   // site index whose words go INTO set A / B next
         T cA, cB;     // c of the step that computes from set A / B
         const int site_pbeg = pe[pbeg * ES].site; // == site_first unless this job continues a parked chain
         load_words(wA, gthr + (size_t)(unsigned)site_pbeg * rowbytes);
-        if (MULTI ? tail_warp : has_tail) twA = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)site_pbeg * rowbytes);
         cA = (T)pe[pbeg * ES].c;
         sB = pe[(pbeg + 1) * ES].site;  // step pbeg+1's words go into set B during step pbeg
         sA = 0;
@@ -890,6 +882,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 
         T R = DIR ? (T)1 : K.prior_n; // step 0 is x = (0 + R0) * m
         uint32_t tdm = td_first;
+        mph = td_first ? tau : (T)1;
         int q1 = q;
         bool post = false;
 
@@ -923,7 +916,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             }
             const T B = chk * S;
             bool rescaled = false;
-            if (p == 0) tdm = 0xffffffffu; // steps 1..m-1 visit sites where the target is derived
+            if (p == 0) { tdm = 0xffffffffu; mph = tau; } // steps 1..m-1 visit sites where the target is derived
             if (p != 0 && (B < K.lower || B > K.upper)) { // :334-347, :538-551; no test at the first site
                 rescaled = true;
                 if (sizeof(T) == 4) { // fp32 state: one reciprocal, then multiplies (<= 1 ulp from the division)
@@ -932,13 +925,13 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                     for (int j = 0; j < WPT; j++)
 #pragma unroll
                         for (int e = 0; e < 16; e++) { a[j][e].x *= inv; a[j][e].y *= inv; }
-                    tl *= inv;
+                    xph *= inv;
                 } else { // fp64 verification mode divides, as the reference does
 #pragma unroll
                     for (int j = 0; j < WPT; j++)
 #pragma unroll
                         for (int e = 0; e < 16; e++) { a[j][e].x /= B; a[j][e].y /= B; }
-                    tl /= B;
+                    xph /= B;
                 }
                 lsr += DIR ? (double)fast_log_dev((float)B) : log((double)B);
                 R = resc_R * cthis;
@@ -954,17 +947,12 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                         for (int j = 0; j < WPT; j++) {
                             if (valid[j]) {
                                 const int n0 = (gt * WPT + j) * 32;
-                                for (int e = 0; e < 32; e++) {
+                                for (int e = 0; e < 32 && n0 + e < P.N; e++) {
                                     T v = src[n0 + e];
                                     if (rescaled) v /= B;
                                     o[n0 + e] = (float)v;
                                 }
                             }
-                        }
-                        if (tail_lane) {
-                            T v = src[P.nfw * 32 + lane];
-                            if (rescaled) v /= B;
-                            o[P.nfw * 32 + lane] = (float)v;
                         }
                     }
                     if (gt == 0) outl[w] = (float)(lsb[w] + lsr);
@@ -976,7 +964,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             if (pn > m) { pev = 0x7fffffff; return; }
             pev = next_event();
             if (pev == pn) {
-                if (pn == m) tdm = td_last;
+                if (pn == m) { tdm = td_last; mph = td_last ? tau : (T)1; }
                 const int bp_now = q < P.W ? bpos(q) : -1;
                 if (bp_now == (DIR ? pn : pn - 1)) {
                     q1 = q;
@@ -1003,18 +991,18 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         auto park_io = [&](bool save) {
             char *park = P.segstate + ((size_t)DIR * P.nt + kk) * P.segstride;
             V2 *pv = reinterpret_cast<V2 *>(park);
-            T *pt = reinterpret_cast<T *>(park + (size_t)TT * WPT * 16 * sizeof(V2));
-            double *pd = reinterpret_cast<double *>(park + (size_t)TT * WPT * 16 * sizeof(V2) + 32 * sizeof(T));
-            int *pi = reinterpret_cast<int *>(pd + 2);
+            double *pd = reinterpret_cast<double *>(park + (size_t)TT * WPT * 16 * sizeof(V2));
+            int *pi = reinterpret_cast<int *>(pd + 4);
             if (save) {
 #pragma unroll
                 for (int j = 0; j < WPT; j++)
 #pragma unroll
                     for (int e = 0; e < 16; e++) __stcg(&pv[(size_t)(j * 16 + e) * TT + t], a[j][e]);
-                if (tail_warp) __stcg(&pt[lane], tl);
                 if (t == 0) {
                     __stcg(&pd[0], lsr);
                     __stcg(&pd[1], (double)R);
+                    __stcg(&pd[2], (double)xph);
+                    __stcg(&pd[3], (double)mph);
                     __stcg(&pi[0], (int)tdm);
                     __stcg(&pi[1], q);
                     __stcg(&pi[2], q1);
@@ -1035,9 +1023,10 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 for (int j = 0; j < WPT; j++)
 #pragma unroll
                     for (int e = 0; e < 16; e++) a[j][e] = __ldcg(&pv[(size_t)(j * 16 + e) * TT + t]);
-                if (tail_warp) tl = __ldcg(&pt[lane]);
                 lsr = __ldcg(&pd[0]);
                 R = (T)__ldcg(&pd[1]);
+                xph = (T)__ldcg(&pd[2]);
+                mph = (T)__ldcg(&pd[3]);
                 tdm = (uint32_t)__ldcg(&pi[0]);
                 q = __ldcg(&pi[1]);
                 q1 = __ldcg(&pi[2]);
@@ -1050,17 +1039,15 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         if (!CLUSTER && seg > 0) park_io(false);
 
         // one step computing from set X while filling set Y
-        auto do_step = [&](int p, uint32_t (&wX)[WPT], uint32_t &twX, T &cX, int &sX,
-                           uint32_t (&wY)[WPT], uint32_t &twY, T &cY, int &sY) {
+        auto do_step = [&](int p, uint32_t (&wX)[WPT], T &cX, int &sX, uint32_t (&wY)[WPT], T &cY, int &sY) {
             // loads for later steps first: words of step p+1 into Y, entry p+2 (site -> X's next fill, c -> X's next step)
             load_words(wY, gthr + (size_t)(unsigned)sY * rowbytes);
-            if (MULTI ? tail_warp : has_tail) twY = *reinterpret_cast<const uint32_t *>(gtail + (size_t)(unsigned)sY * rowbytes);
             // one (vector) load of entry p+2: its site is needed next step (to fetch the words of step p+2), its c at
             // the end of step p+2, which runs on this same register set
             const Ent e2 = *pnx;
             pnx += ES;
             sX = e2.site;
-            T Sl = step_local(wX, twX, tdm, R);
+            T Sl = step_local(wX, tdm, R);
             int sa = 64;
             bool rare = false;
             // a pending event (stepping-stone store, last step, ...) is folded into the lower threshold ahead of time, so
@@ -1084,9 +1071,9 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 
         // steps 0..m, two per iteration (even steps compute from set A, odd ones from set B)
         for (int p = pbeg; p < pend; p += 2) {
-            do_step(p, wA, twA, cA, sA, wB, twB, cB, sB);
+            do_step(p, wA, cA, sA, wB, cB, sB);
             if (p + 1 >= pend) break;
-            do_step(p + 1, wB, twB, cB, sB, wA, twA, cA, sA);
+            do_step(p + 1, wB, cB, sB, wA, cA, sA);
         }
         if (!CLUSTER && seg != nseg - 1) { // park the chain; whichever team takes job (seg+1, chain) continues it
             park_io(true);
