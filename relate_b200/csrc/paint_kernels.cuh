@@ -579,6 +579,10 @@ template <int WPT> __device__ __forceinline__ void load_words(uint32_t (&w)[WPT]
     }
 }
 
+#ifndef RP_PF
+#define RP_PF 1 // L1 prefetch hints for the genotype rows / site tables of later steps
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void opaque(float &x) { asm volatile("" : "+f"(x)); }
 __device__ __forceinline__ void opaque(double &x) { asm volatile("" : "+d"(x)); }
 
@@ -871,6 +875,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         // Entries up to 2 past either end of the target's list are read and never used (the table is padded).
         uint32_t wA[WPT], wB[WPT];
         int sA, sB;   // site index whose words go INTO set A / B next
+        int fA = 0, fB = 0; // site index whose row is prefetched into L1 at the top of the next step computing from set A / B
         T cA, cB;     // c of the step that computes from set A / B
         const int site_pbeg = pe[pbeg * ES].site; // == site_first unless this job continues a parked chain
         load_words(wA, gthr + (size_t)(unsigned)site_pbeg * rowbytes);
@@ -1039,9 +1044,17 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         if (!CLUSTER && seg > 0) park_io(false);
 
         // one step computing from set X while filling set Y
-        auto do_step = [&](int p, uint32_t (&wX)[WPT], T &cX, int &sX, uint32_t (&wY)[WPT], T &cY, int &sY) {
+        auto do_step = [&](int p, uint32_t (&wX)[WPT], T &cX, int &sX, int &fX, uint32_t (&wY)[WPT], T &cY, int &sY, int &fY) {
             // loads for later steps first: words of step p+1 into Y, entry p+2 (site -> X's next fill, c -> X's next step)
             load_words(wY, gthr + (size_t)(unsigned)sY * rowbytes);
+            // The row of step p+2 is loaded at the top of step p+1 and consumed a step later: one step of lead over an
+            // L2 latency that, under load, is about a step long (ncu: 8 % of the warps' time on that scoreboard).  So
+            // the site of entry p+3 is fetched here (same table line as entry p+2: an L1 hit) and its row is requested
+            // from L1 at the top of step p+1 (fX was filled a step ago with the site of entry p+2): two steps of lead.
+            if (RP_PF && !MULTI && WPT == 1) { // (measured: +1.4 % at config 2, nothing or a loss for the wider teams)
+                prefetch_l1(gthr + (size_t)(unsigned)fX * rowbytes);
+                fY = pnx[ES].site;
+            }
             // one (vector) load of entry p+2: its site is needed next step (to fetch the words of step p+2), its c at
             // the end of step p+2, which runs on this same register set
             const Ent e2 = *pnx;
@@ -1071,9 +1084,10 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 
         // steps 0..m, two per iteration (even steps compute from set A, odd ones from set B)
         for (int p = pbeg; p < pend; p += 2) {
-            do_step(p, wA, cA, sA, wB, cB, sB);
+            if (RP_PF && !MULTI && WPT == 1) prefetch_l1(pnx + 32 * ES); // site-table line (16 entries) two lines ahead
+            do_step(p, wA, cA, sA, fA, wB, cB, sB, fB);
             if (p + 1 >= pend) break;
-            do_step(p + 1, wB, cB, sB, wA, cA, sA);
+            do_step(p + 1, wB, cB, sB, fB, wA, cA, sA, fA);
         }
         if (!CLUSTER && seg != nseg - 1) { // park the chain; whichever team takes job (seg+1, chain) continues it
             park_io(true);
