@@ -607,7 +607,9 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
     const PaintConsts<T> &K = paint_consts<T>(P);
     // loop constants live in registers (opaque to the compiler, which would otherwise re-read the constant bank
     // every step)
-    T tau = K.tau, band_lo = K.lower, band_hi = K.upper;
+    // multi-warp / fp64 teams: the rare path is entered on S outside [band_lo, band_hi], the rescaling band divided by
+    // chk and widened by a hair; the handler repeats the reference's exact test on B = chk*S
+    T tau = K.tau, band_lo = K.lower / (DIR ? K.ntheta : (T)1) * (T)1.000002, band_hi = K.upper / (DIR ? K.ntheta : (T)1) * (T)0.999998;
     opaque(tau);
     opaque(band_lo);
     opaque(band_hi);
@@ -1074,8 +1076,8 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             if (!MULTI && sizeof(T) == 4) {
                 set_scale((float)S);
             } else {
-                const T B = DIR ? chk * S : S;
-                rare = (B < band_lo) || (B > band_hi) || ev;
+                const T lo_e = ev ? (T)INFINITY : band_lo; // a pending event folded into the threshold, ahead of the sum
+                rare = (S < lo_e) || (S > band_hi);
             }
             // the rare path is taken by all threads or none (S is the team-wide sum): tell the compiler with a vote, so
             // the branch needs no reconvergence bookkeeping

@@ -1,10 +1,4 @@
-for rep in 1 2; do
 python scripts/prof_case.py 1000 50000 5 0 0 1000 0 0 2>&1 | tail -1 | cut -c1-150
-RELATE_PAINT_LIB=$PWD/variants/lib_nopf.so python scripts/prof_case.py 1000 50000 5 0 0 1000 0 0 2>&1 | tail -1 | sed "s/^/nopf /" | cut -c1-150
-done
-for v in "" nopf; do 
-L=relate_b200/librelate_paint.so; [ -n "$v" ] && L=variants/lib_$v.so
-RELATE_PAINT_LIB=$PWD/$L python scripts/prof_case.py 2000 20000 3 0 0 2000 0 0 2>&1 | tail -1| sed "s/^/$v /" | cut -c1-150
-RELATE_PAINT_LIB=$PWD/$L python scripts/prof_case.py 5000 20000 2 0 0 5000 0 0 2>&1 | tail -1| sed "s/^/$v /" | cut -c1-150
-RELATE_PAINT_LIB=$PWD/$L python scripts/prof_case.py 10000 20000 2 0 0 2236 0 0 2>&1 | tail -1| sed "s/^/$v /" | cut -c1-150
-done
+python scripts/prof_case.py 2000 20000 3 0 0 2000 0 0 2>&1 | tail -1| cut -c1-150
+python scripts/prof_case.py 5000 20000 2 0 0 5000 0 0 2>&1 | tail -1|  cut -c1-150
+python scripts/prof_case.py 10000 20000 2 0 0 2236 0 0 2>&1 | tail -1| cut -c1-150
