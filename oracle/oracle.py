@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle_paint.so")
 REF_RELATE = os.path.join(HERE, "_ref", "Relate")
 REF_DLENS = os.path.join(HERE, "_ref", "dlens")
+REF_RELATE_GPU = os.path.join(HERE, "_ref", "Relate_gpu")  # the reference with GetMatrix bound to the GPU (bt_gpu_shim.cpp)
 _lib = None
 
 
