@@ -374,7 +374,8 @@ def main():
                                      "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src}},
                 "e2e": {"value": world * cells_per_step / e2e_max, "unit": UNIT,
                         "h2d_bytes_per_step": es["h2d_bytes"], "d2h_bytes_per_step": es["d2h_bytes"],
-                        "seconds_per_step": e2e_max, "call": "rp_paint_chunk (== relate --mode Paint): chunk files -> paint files",
+                        "seconds_per_step": e2e_max, "runs_ms": [round(1e3 * t, 3) for t, _ in e2e_runs],
+                        "call": "rp_paint_chunk (== relate --mode Paint): chunk files -> paint files",
                         "breakdown_ms": {k: es[k] for k in ("ms_load", "ms_h2d", "ms_prep", "ms_paint", "ms_rle", "ms_d2h", "ms_write", "ms_total")}},
                 "gpu_launches": launches,
                 "clocks": clocks,

@@ -7,6 +7,8 @@
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include "../../include/relate_paint.h"
 
+#include <emmintrin.h>
+
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -288,8 +290,13 @@ void dd_prefix(const double *r, int L, std::vector<double> &hi, std::vector<doub
 // The slices pass through a ring of `nslots` pinned slots (slice i sits in slot i % nslots): pinning the whole chunk
 // cost ~0.3 s per 0.5 GB at every cold start.  When the ring is shorter than the chunk, a slot is refilled only after
 // every device has copied the slice it held (consumed[i] == ndev).
+// The reader threads bit-pack what they read (SNP-major rows of `wps` words, the layout of rp_chunk::G): slice i is
+// `rows` whole SNP rows, `slice` = rows * wps * 4 bytes in the ring.  The devices then copy 1 bit per genotype instead
+// of 1 byte (8 devices painting one chunk pull 1/8 of the bytes through the host's memory and PCIe), the chars never
+// reach HBM and the pack kernel is not launched.
 struct HapFeed {
-    size_t slice = 0;
+    size_t slice = 0; // bytes of one ring slot
+    int rows = 0;     // SNP rows per slice
     int nsl = 0, nslots = 0, ndev = 1;
     const char *ring = nullptr;
     std::unique_ptr<std::atomic<int>[]> ready, consumed;
@@ -297,6 +304,25 @@ struct HapFeed {
     const char *src(int i) const { return ring + (size_t)(i % nslots) * slice; }
     bool wraps() const { return nsl > nslots; }
 };
+
+// chars '0'/'1' of one SNP row -> bits (bit n&31 of word n>>5 = hap[n] == '1'), words beyond the row zeroed;
+// what pack_snp_major_kernel does on the device
+inline void pack_row_host(const char *p, int N, uint32_t *out, int wps)
+{
+    const __m128i one = _mm_set1_epi8('1');
+    int n = 0, w = 0;
+    for (; n + 32 <= N; n += 32, w++) {
+        const unsigned lo = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(p + n)), one));
+        const unsigned hi = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(p + n + 16)), one));
+        out[w] = lo | (hi << 16);
+    }
+    if (n < N) {
+        uint32_t bits = 0;
+        for (int j = 0; n + j < N; j++) bits |= (uint32_t)(p[n + j] == '1') << j;
+        out[w++] = bits;
+    }
+    for (; w < wps; w++) out[w] = 0;
+}
 
 int chunk_from_host(int device, int N, int L, const char *hap, const double *r, const int *wb, int n_wb,
                     double theta, unsigned flags, rp_chunk **out, rp_stats *st, HapFeed *feed = nullptr)
@@ -366,7 +392,7 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
     const double t0 = now_ms();
     DevBuf &chars = c->chars;
     const size_t nchar = (size_t)L * N;
-    RP_TRYB(chars.ensure(nchar));
+    if (!feed) RP_TRYB(chars.ensure(nchar)); // (a feed delivers packed rows straight into G)
     RP_TRYB(c->G.ensure((size_t)L * c->wps * 4));
     RP_TRYB(c->GT.ensure((size_t)N * c->lw * 4));
     RP_TRYB(c->r.ensure((size_t)L * 8));
@@ -383,8 +409,9 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
             int state;
             while ((state = feed->ready[i].load(std::memory_order_acquire)) == 0) std::this_thread::yield();
             if (state < 0) return bail(fail(RP_EIO, "short read in the chunk's .hap file"));
-            const size_t at = (size_t)i * feed->slice, n = std::min(feed->slice, nchar - at);
-            RP_CUDAB(cudaMemcpyAsync(chars.as<char>() + at, feed->src(i), n, cudaMemcpyHostToDevice, c->stream));
+            const size_t rowb = (size_t)c->wps * 4;
+            const size_t at = (size_t)i * feed->rows * rowb, n = (size_t)std::min(feed->rows, L - i * feed->rows) * rowb;
+            RP_CUDAB(cudaMemcpyAsync(c->G.as<char>() + at, feed->src(i), n, cudaMemcpyHostToDevice, c->stream));
             if (feed->wraps()) { // the slot is reused: tell the readers once this device has its copy
                 RP_CUDAB(cudaStreamSynchronize(c->stream));
                 feed->consumed[i].fetch_add(1, std::memory_order_release);
@@ -399,9 +426,11 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
     {
         const long long total = (long long)L * c->wps;
         const int th = 256;
-        rp::pack_snp_major_kernel<<<(unsigned)((total + th - 1) / th), th, 0, c->stream>>>(
-            chars.as<unsigned char>(), N, L, c->G.as<uint32_t>(), c->wps);
-        RP_CUDAB(cudaGetLastError());
+        if (!feed) {
+            rp::pack_snp_major_kernel<<<(unsigned)((total + th - 1) / th), th, 0, c->stream>>>(
+                chars.as<unsigned char>(), N, L, c->G.as<uint32_t>(), c->wps);
+            RP_CUDAB(cudaGetLastError());
+        }
         dim3 grid((N + 31) / 32, (c->lw + 31) / 32), block(32, 32);
         rp::transpose_bits_kernel<<<grid, block, 0, c->stream>>>(c->G.as<uint32_t>(), c->wps, N, L,
                                                                  c->GT.as<uint32_t>(), c->lw);
@@ -416,8 +445,8 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
         cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
         st->ms_h2d += a;
         st->ms_prep += b;
-        st->h2d_bytes += (long long)nchar + (long long)L * 8 + (long long)(L + 1) * 16 + (long long)n_wb * 4;
-        st->launches += 2;
+        st->h2d_bytes += (feed ? (long long)L * c->wps * 4 : (long long)nchar) + (long long)L * 8 + (long long)(L + 1) * 16 + (long long)n_wb * 4;
+        st->launches += feed ? 1 : 2;
         st->ms_total += now_ms() - t0;
     }
     *out = c;
@@ -1395,8 +1424,12 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     HapFeed feed;
     const size_t ring_cap = (size_t)(getenv("RP_RING_KB") ? atoi(getenv("RP_RING_KB")) : 65536) << 10; // tests shrink it
-    feed.slice = (size_t)(getenv("RP_SLICE_KB") ? atoi(getenv("RP_SLICE_KB")) : (nchar <= ring_cap ? 1024 : 4096)) << 10;
-    feed.nsl = (int)((nchar + feed.slice - 1) / feed.slice);
+    // a slice = whole SNP rows worth about RP_SLICE_KB of genotype chars on disk; in the ring it is 1/8 of that
+    const size_t slice_chars = (size_t)(getenv("RP_SLICE_KB") ? atoi(getenv("RP_SLICE_KB")) : (nchar <= 8 * ring_cap ? 1024 : 4096)) << 10;
+    const int wps = (((hc.N + 31) / 32) + 3) / 4 * 4; // as rp_chunk::wps
+    feed.rows = (int)std::max<size_t>(1, slice_chars / (size_t)hc.N);
+    feed.slice = (size_t)feed.rows * wps * 4;
+    feed.nsl = (hc.L + feed.rows - 1) / feed.rows;
     feed.nslots = (int)std::min<size_t>((size_t)feed.nsl, std::max<size_t>(2, ring_cap / feed.slice));
     feed.ndev = (int)devs.size();
     PinnedBuf &hap_in = g_ws.at(devs[0]).hap_in;
@@ -1421,6 +1454,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     readers_left = nread;
     for (int t = 0; t < nread; t++)
         readers.emplace_back([&]() {
+            std::vector<char> raw; // the slice as it is on disk (pageable: it never meets the GPU)
             for (;;) {
                 const int i = next_slice.fetch_add(1);
                 if (i >= feed.nsl) break;
@@ -1430,8 +1464,13 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
                         if (feed.abort.load()) { ok = false; break; }
                         std::this_thread::yield();
                     }
-                const size_t at = (size_t)i * feed.slice, n = std::min(feed.slice, nchar - at);
-                ok = ok && rp::read_hap_range(hap_fd, at, n, const_cast<char *>(feed.src(i)));
+                const int row0 = i * feed.rows, nrows = std::min(feed.rows, hc.L - row0);
+                raw.resize((size_t)feed.rows * hc.N);
+                ok = ok && rp::read_hap_range(hap_fd, (size_t)row0 * hc.N, (size_t)nrows * hc.N, raw.data());
+                if (ok) {
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(const_cast<char *>(feed.src(i)));
+                    for (int rr = 0; rr < nrows; rr++) pack_row_host(raw.data() + (size_t)rr * hc.N, hc.N, dst + (size_t)rr * wps, wps);
+                }
                 feed.ready[i].store(ok ? 1 : -1, std::memory_order_release);
             }
             if (readers_left.fetch_sub(1) == 1) t_loaded = now_ms();

@@ -677,8 +677,8 @@ def test_small_batches_and_the_copy_pipeline_give_the_same_files(tmp_path, monke
         synth.make_chunk_dir(str(tmp_path / tag), 300, 2500, seed=43, n_windows=5)
     capi.paint_chunk(str(tmp_path / "one"), 0, "0.001,1", devices=[0])
     monkeypatch.setenv("RP_BATCH_TARGETS", "37")
-    monkeypatch.setenv("RP_SLICE_KB", "64")   # 750 KB of genotype bytes through a 4-slot input ring: the ring wraps
-    monkeypatch.setenv("RP_RING_KB", "256")
+    monkeypatch.setenv("RP_SLICE_KB", "64")   # 12 slices of 218 SNP rows (10 KB bit-packed each) through a 3-slot
+    monkeypatch.setenv("RP_RING_KB", "32")    # input ring: the ring wraps
     st = capi.paint_chunk(str(tmp_path / "many"), 0, "0.001,1", devices=list(range(capi.lib().rp_device_count())))
     assert st["n_targets"] == 300
     for w in range(5):
