@@ -74,7 +74,9 @@ typedef struct rp_stats {
 typedef struct rp_tune { /* all zero = automatic */
     int words_per_thread; /* 1 or 2: 32-bit genotype words (32 haplotypes each) per thread  */
     int ctas_per_sm;      /* persistent CTAs per SM                                          */
-    int reserved[6];
+    int reserved[6];      /* [1]: chain segments of the paint kernel (0 = automatic, 1 = whole chains as jobs, n = every
+                           * chain cut into n segments parked in HBM in between: load balance, results bit-identical);
+                           * [3]: force teams of that many CTAs (thread-block cluster); others 0                    */
 } rp_tune;
 
 const char *rp_last_error(void);
