@@ -27,6 +27,7 @@ struct GpuState {
     Data *data = nullptr;
     rp_chunk *chunk = nullptr;
     rp_window *win = nullptr;
+    bool painted = false; // RELATE_GPU_RESIDENT: the stepping stones of all targets are in HBM
     std::string out_dir;
     int chunk_index = 0;
     std::vector<int> wb;
@@ -82,11 +83,23 @@ void DistanceMeasure::GetMatrix(const int snp)
     if (g.data != data) { // a new DistanceMeasure on another Data object: (re)load the chunk
         if (g.win) rp_window_close(g.win), g.win = nullptr;
         if (g.chunk) rp_chunk_free(g.chunk), g.chunk = nullptr;
+        g.painted = false;
         open_chunk(*data);
     }
     if (snp > section_endpos || g.win == nullptr) {
         if (g.win) rp_window_close(g.win), g.win = nullptr;
-        if (rp_window_open_files(g.chunk, g.out_dir.c_str(), g.chunk_index, section, &g.win, nullptr) != RP_OK)
+        if (getenv("RELATE_GPU_RESIDENT")) {
+            // No paint files at all: paint every target once, keep the stepping stones in HBM (8*N*N*W bytes) and open
+            // each window from there (the codec's lossy collapse is applied on the device, so the matrices are
+            // bit-identical to the file round trip).  `--mode Paint` becomes unnecessary for this consumer.
+            if (!g.painted) {
+                if (rp_paint_targets_device(g.chunk, 0, data->N, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) != RP_OK)
+                    die("rp_paint_targets_device");
+                g.painted = true;
+            }
+            if (rp_window_open_resident(g.chunk, section, data->rpos.data(), &g.win, nullptr) != RP_OK)
+                die("rp_window_open_resident");
+        } else if (rp_window_open_files(g.chunk, g.out_dir.c_str(), g.chunk_index, section, &g.win, nullptr) != RP_OK)
             die("rp_window_open_files");
         // what the reference reads from the head of every record (fast_painting.cpp:589-590)
         section_startpos = g.wb[section];

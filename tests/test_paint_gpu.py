@@ -386,6 +386,19 @@ def test_reference_buildtopology_with_gpu_distance_matrices(tmp_path, have_ref):
     oracle.run_reference(bt, cwd=str(tmp_path / "cpu"))
     p = subprocess.run([oracle.REF_RELATE_GPU] + bt, cwd=str(tmp_path / "gpu"), capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
+    # the same consumer without any paint files: Paint inside the BuildTopology process, stepping stones resident in HBM,
+    # windows opened from there (rp_window_open_resident) -- byte-identical trees to the file round trip
+    synth.make_chunk_dir(str(tmp_path / "res" / "o"), N, L, seed=31, n_windows=W)
+    os.makedirs(str(tmp_path / "res" / "o" / "chunk_0"))  # (the directory Paint would have created)
+    p = subprocess.run([oracle.REF_RELATE_GPU] + bt, cwd=str(tmp_path / "res"), capture_output=True, text=True,
+                       env=dict(os.environ, RELATE_GPU_RESIDENT="1"))
+    assert p.returncode == 0, p.stderr
+    assert not os.path.exists(str(tmp_path / "res" / "o" / "chunk_0" / "paint"))
+    for w in range(W):
+        for ext in ("anc", "mut"):
+            assert filecmp.cmp(str(tmp_path / "gpu" / "o" / "chunk_0" / f"o_{w}.{ext}"),
+                               str(tmp_path / "res" / "o" / "chunk_0" / f"o_{w}.{ext}"), shallow=False), (w, ext)
+
     # MinMatch is greedy and tie-sensitive, so at N=200 the files are not byte-identical: compare the
     # trees themselves -- same tree positions, and per tree the set of clades (leaf sets below the internal nodes)
     ntrees = nsame = nclades = nshared = 0
