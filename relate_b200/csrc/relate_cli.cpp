@@ -13,9 +13,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <iomanip>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <set>
 #include <sstream>
 #include <string>
@@ -192,7 +194,7 @@ std::vector<std::string> with_mode(const Args &a, const std::string &mode, const
 }
 
 // pipeline/Paint.cpp:17-108 behind the C ABI
-int paint(const Args &a, int chunk_index, int last_chunk = -1)
+int paint(const Args &a, int chunk_index, int last_chunk = -1, std::ostream &log = std::cerr)
 {
     std::vector<int> devs;
     if (a.count("gpus")) {
@@ -205,11 +207,11 @@ int paint(const Args &a, int chunk_index, int last_chunk = -1)
         for (int i = 0; i < n; i++) devs.push_back(i);
     }
     if (devs.empty()) {
-        std::cerr << "relate: no CUDA device visible; --mode Paint has no CPU path in this build." << std::endl;
+        log << "relate: no CUDA device visible; --mode Paint has no CPU path in this build." << std::endl;
         return 1;
     }
-    std::cerr << "---------------------------------------------------------" << std::endl;
-    std::cerr << "Painting sequences..." << std::endl;
+    log << "---------------------------------------------------------" << std::endl;
+    log << "Painting sequences..." << std::endl;
     rp_stats st;
     memset(&st, 0, sizeof st);
     const char *painting = a.count("painting") ? a.get("painting").c_str() : nullptr;
@@ -218,17 +220,17 @@ int paint(const Args &a, int chunk_index, int last_chunk = -1)
                             : rp_paint_chunks(a.get("output").c_str(), chunk_index, last_chunk, painting, devs.data(),
                                               (int)devs.size(), a.count("fp64") ? RP_FP64 : 0u, &st);
     if (rc != RP_OK) {
-        std::cerr << "relate: Paint failed: " << rp_last_error() << std::endl;
+        log << "relate: Paint failed: " << rp_last_error() << std::endl;
         return 1;
     }
     rusage usage;
     getrusage(RUSAGE_SELF, &usage);
-    std::cerr << "GPU Paint: " << devs.size() << " device(s), " << st.n_targets << " targets, kernel " << std::fixed
+    log << "GPU Paint: " << devs.size() << " device(s), " << st.n_targets << " targets, kernel " << std::fixed
               << std::setprecision(3) << st.ms_paint << " ms, prep " << st.ms_prep << " ms, record encoder " << st.ms_rle << " ms, file writes " << st.ms_write
               << " ms, total " << st.ms_total << " ms." << std::endl;
-    std::cerr << "CPU Time spent: " << usage.ru_utime.tv_sec << "." << std::setfill('0') << std::setw(6) << usage.ru_utime.tv_usec
+    log << "CPU Time spent: " << usage.ru_utime.tv_sec << "." << std::setfill('0') << std::setw(6) << usage.ru_utime.tv_usec
               << "s; Max Memory usage: " << std::setprecision(6) << usage.ru_maxrss / 1000.0 << "Mb." << std::endl;
-    std::cerr << "---------------------------------------------------------" << std::endl << std::endl;
+    log << "---------------------------------------------------------" << std::endl << std::endl;
     return 0;
 }
 
@@ -338,6 +340,18 @@ int main(int argc, char **argv)
             }
             end_chunk = hdr[2] - 1;
         }
+        // Paint runs one chunk ahead of the reference's CPU stages: while BuildTopology ...
+        // CombineSections work on chunk c, chunk c+1 is painted in the background; its banner is printed when its turn
+        // comes.  InferBranchLengths deletes a chunk's paint files (InferBranchLengths.cpp:60-75), so at most two
+        // chunks' paint files are on disk at any time, as with the cluster scripts' bounded number of paintings.
+        struct Ahead { std::future<int> rc; std::ostringstream log; };
+        std::unique_ptr<Ahead> ahead;
+        auto start_paint = [&](int c) {
+            std::unique_ptr<Ahead> p(new Ahead());
+            Ahead *raw = p.get();
+            p->rc = std::async(std::launch::async, [&a, c, raw]() { return paint(a, c, -1, raw->log); });
+            return p;
+        };
         for (int c = start_chunk; c <= end_chunk; c++) {
             std::cerr << "---------------------------------------------------------" << std::endl;
             std::cerr << "Starting chunk " << c << " of " << end_chunk << "." << std::endl;
@@ -349,8 +363,13 @@ int main(int argc, char **argv)
             }
             const int num_sections = hdr[2] - 1;
             const std::string cs = std::to_string(c), ls = std::to_string(num_sections - 1);
-            int rc = paint(a, c);
+            if (!ahead) ahead = start_paint(c);
+            int rc = ahead->rc.get();
+            std::cerr << ahead->log.str();
+            ahead.reset();
             if (rc) return rc;
+            if (c < end_chunk) ahead = start_paint(c + 1);
+            // (an error return below waits for the background painter: a std::async future joins in its destructor)
             if ((rc = run_reference(ref, with_mode(a, "BuildTopology", {"--chunk_index", cs, "--first_section", "0", "--last_section", ls})))) return rc;
             if ((rc = run_reference(ref, with_mode(a, "FindEquivalentBranches", {"--chunk_index", cs})))) return rc;
             if (a.count("postprocess")) {

@@ -683,6 +683,31 @@ def test_config5_shape_multichunk_makechunks_then_paint_chunks(tmp_path):
         assert sum(same) >= W - 1, (c, same)
 
 
+def test_cli_mode_all_with_paint_ahead_equals_reference_all(tmp_path, have_ref):
+    """`relate --mode All` (MakeChunks and Paint native, Paint running one chunk ahead of the reference's CPU stages,
+    everything else delegated to the reference binary) on a 3-chunk data set: the final .anc/.mut are byte-identical
+    to the reference's own `--mode All` with the same seed, and no paint files are left behind."""
+    if not have_ref:
+        pytest.skip("oracle/_ref/Relate did not travel to this box")
+    from test_makechunks_cpu import write_haps, write_map
+    d = str(tmp_path)
+    hap, bp = synth.block_kingman(16, 50000, 78)
+    hp, sp = write_haps(d, hap, bp)
+    mp = write_map(d, bp, rows=200)
+    common = ["--mode", "All", "-m", "1.25e-8", "-N", "30000", "--haps", hp, "--sample", sp, "--map", mp, "--seed", "1",
+              "--memory", "0.0015"]
+    p = subprocess.run([oracle.REF_RELATE] + common + ["-o", "ref"], cwd=d, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    p = subprocess.run([EXE] + common + ["-o", "gpu"], cwd=d, capture_output=True, text=True,
+                       env=dict(os.environ, RELATE_REFERENCE_BIN=oracle.REF_RELATE))
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert p.stderr.count("Painting sequences...") == 3 and p.stderr.count("Starting chunk") == 3
+    assert p.stderr.index("Starting chunk 1") < p.stderr.rindex("Painting sequences...")  # banners in chunk order
+    for ext in ("anc", "mut"):
+        assert filecmp.cmp(os.path.join(d, f"ref.{ext}"), os.path.join(d, f"gpu.{ext}"), shallow=False), ext
+    assert not os.path.exists(os.path.join(d, "gpu"))  # Finalize removed the working directory, paint files included
+
+
 def test_small_batches_and_the_copy_pipeline_give_the_same_files(tmp_path, monkeypatch):
     """The stage driver with forced 37-target batches (several batches per device, alternating image buffers, pieces
     of many batches in flight) writes byte-identical files to the single-batch run."""
