@@ -71,6 +71,44 @@ def test_fp32_matches_oracle(N, L, W, seed, wpt, nk):
     assert g.stats["launches"] == 6 and g.stats["ms_paint"] > 0
 
 
+def test_random_small_shapes_match_oracle():
+    """Seeded sweep over awkward shapes: tiny N and L (down to 2), ragged random window boundaries (one-SNP windows,
+    windows without any derived site of a target), recombination rates from exact zeros to beyond the rho cap, random
+    genotypes of any density, a theta other than the default.  Boundary SNPs exact, vectors within 1e-4, both state types."""
+    rng = np.random.default_rng(20261017)
+    for case in range(40):
+        N = int(rng.integers(2, 71))
+        L = int(rng.integers(2, 301))
+        W = int(rng.integers(1, min(L, 9) + 1))
+        cuts = np.sort(rng.choice(np.arange(1, L), size=W - 1, replace=False)) if W > 1 else np.array([], dtype=np.int64)
+        wb = np.concatenate([[0], cuts, [L]]).astype(np.int32)
+        dens = float(rng.choice([0.02, 0.2, 0.5, 0.9]))
+        hap = np.where(rng.random((L, N)) < dens, ord("1"), ord("0")).astype(np.uint8)
+        r = rng.choice([0.0, 1e-7, 1e-4, 3e-3, 0.5, 7.0], size=L, p=[0.15, 0.2, 0.3, 0.2, 0.1, 0.05]).astype(np.float64)
+        theta = float(np.float32(rng.choice([0.001, 0.025, 0.2])))
+        o = oracle.paint_targets(hap, r, wb, theta, 0, N)
+        for fp64 in (False, True):
+            with capi.DeviceChunk.from_arrays(hap, r, wb, theta, fp64=fp64) as c:
+                g = c.paint_targets(0, N)
+            assert np.array_equal(g.site_begin, o["site_begin"]) and np.array_equal(g.site_end, o["site_end"]), case
+            tol = 1e-4 if not fp64 else 2e-7
+            assert rel_err(g.alpha, o["alpha"]) <= tol and rel_err(g.beta, o["beta"]) <= tol, (case, N, L, W, fp64)
+            assert np.abs(g.ls_alpha.astype(np.float64) - o["ls_alpha"]).max() <= 2e-3, case
+            assert np.abs(g.ls_beta.astype(np.float64) - o["ls_beta"]).max() <= 2e-3, case
+
+
+def test_long_chunk_many_windows():
+    """L beyond 2^18 SNPs with 60 windows (row offsets and site tables well past 32-bit byte counts at larger N; here
+    the point is the index arithmetic): a few targets against the oracle, and the chains cut into parked segments."""
+    N, L, W = 64, 400000, 60
+    hap, r, wb = make_case(N, L, W, 91)
+    with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+        c.set_tune(segments=8)
+        g = c.paint_targets(5, 13)
+    o = oracle.paint_targets(hap, r, wb, THETA, 5, 13)
+    compare(g, o, ls_atol=2e-2)  # log-scales reach ~1e5 here: one float ulp is 8e-3
+
+
 @pytest.mark.parametrize("N,L,W,seed,nk", [(8, 2500, 4, 1, None), (100, 1500, 6, 4, None), (1000, 1500, 4, 5, 64),
                                            (2100, 900, 3, 8, 32), (5000, 500, 2, 9, 16)])
 def test_fp64_mode_reproduces_oracle_to_one_ulp(N, L, W, seed, nk):
