@@ -1046,7 +1046,10 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         if (!CLUSTER && seg > 0) park_io(false);
 
         // one step computing from set X while filling set Y
-        auto do_step = [&](int p, uint32_t (&wX)[WPT], T &cX, int &sX, int &fX, uint32_t (&wY)[WPT], T &cY, int &sY, int &fY) {
+        // EV: the handler is known to be due after this step (a pending event); such steps are peeled out of the plain
+        // loop below, so that plain steps carry no event test at all
+        auto do_step = [&](auto evc, int p, uint32_t (&wX)[WPT], T &cX, int &sX, int &fX, uint32_t (&wY)[WPT], T &cY, int &sY, int &fY) {
+            constexpr int EV = decltype(evc)::value; // 0 plain step, 1 event step, 2 test inside the step (multi-warp teams)
             // loads for later steps first: words of step p+1 into Y, entry p+2 (site -> X's next fill, c -> X's next step)
             load_words(wY, gthr + (size_t)(unsigned)sY * rowbytes);
             // The row of step p+2 is loaded at the top of step p+1 and consumed a step later: one step of lead over an
@@ -1065,31 +1068,51 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             T Sl = step_local(wX, tdm, R);
             int sa = 64;
             bool rare = false;
-            // a pending event (stepping-stone store, last step, ...) is folded into the lower threshold ahead of time, so
-            // that nothing but the two compares sits between the REDUX and the branch
-            const bool ev = (p + 1 == pev);
-            const float tlo_e = ev ? __int_as_float(0x7f800000) : tlo;
-            const T S = reduce(Sl, p & 1, tlo_e, sa, rare);
+            const bool ev = (EV == 2) && (p + 1 == pev);
+            const T S = reduce(Sl, p & 1, tlo, sa, rare);
             const T ccur = cX;
             R = S * ccur;
             cX = (T)e2.c;
             if (!MULTI && sizeof(T) == 4) {
                 set_scale((float)S);
             } else {
-                const T lo_e = ev ? (T)INFINITY : band_lo; // a pending event folded into the threshold, ahead of the sum
+                const T lo_e = ev ? (T)INFINITY : band_lo; // (EV == 2) a pending event folded into the threshold
                 rare = (S < lo_e) || (S > band_hi);
             }
             // the rare path is taken by all threads or none (S is the team-wide sum): tell the compiler with a vote, so
             // the branch needs no reconvergence bookkeeping
-            if (__builtin_expect(__any_sync(0xffffffffu, rare), 0)) handler(p, S, ccur, Sl, sa < 64);
+            if (EV == 1) handler(p, S, ccur, Sl, sa < 64);
+            else if (__builtin_expect(__any_sync(0xffffffffu, rare), 0)) handler(p, S, ccur, Sl, sa < 64);
         };
+        auto step_even = [&](auto evc, int p) { do_step(evc, p, wA, cA, sA, fA, wB, cB, sB, fB); }; // computes from set A
+        auto step_odd = [&](auto evc, int p) { do_step(evc, p, wB, cB, sB, fB, wA, cA, sA, fA); };  // computes from set B
+        using PlainStep = std::integral_constant<int, 0>;
+        using EventStep = std::integral_constant<int, 1>;
+        using TestStep = std::integral_constant<int, 2>;
 
-        // steps 0..m, two per iteration (even steps compute from set A, odd ones from set B)
-        for (int p = pbeg; p < pend; p += 2) {
-            if (RP_PF && !MULTI && WPT == 1) prefetch_l1(pnx + 32 * ES); // site-table line (16 entries) two lines ahead
-            do_step(p, wA, cA, sA, fA, wB, cB, sB, fB);
-            if (p + 1 >= pend) break;
-            do_step(p + 1, wB, cB, sB, fB, wA, cA, sA, fA);
+        // steps pbeg..pend-1: even steps compute from set A, odd ones from set B.  The handler announces the step after
+        // which it must run next (pev = that step + 1: a stepping-stone store, the last step, ...); the steps up to it
+        // run in a plain two-step loop, the event step itself is peeled.
+        if (MULTI || sizeof(T) == 8) { // (peeling costs these variants registers: they keep the test inside the step)
+            for (int p = pbeg; p < pend; p += 2) {
+                step_even(TestStep{}, p);
+                if (p + 1 >= pend) break;
+                step_odd(TestStep{}, p + 1);
+            }
+        } else for (int p = pbeg; p < pend;) {
+            const bool has_ev = pev <= pend;              // the event step is pev-1
+            const int plain_end = has_ev ? pev - 1 : pend; // steps [p, plain_end) are plain
+            if ((p & 1) && p < plain_end) { step_odd(PlainStep{}, p); p++; }
+            for (; p + 1 < plain_end; p += 2) {
+                if (RP_PF && !MULTI && WPT == 1) prefetch_l1(pnx + 32 * ES); // site-table line (16 entries) two lines ahead
+                step_even(PlainStep{}, p);
+                step_odd(PlainStep{}, p + 1);
+            }
+            if (p < plain_end) { step_even(PlainStep{}, p); p++; }
+            if (has_ev && p < pend) { // p == pev - 1
+                if (p & 1) step_odd(EventStep{}, p); else step_even(EventStep{}, p);
+                p++;
+            }
         }
         if (!CLUSTER && seg != nseg - 1) { // park the chain; whichever team takes job (seg+1, chain) continues it
             park_io(true);
