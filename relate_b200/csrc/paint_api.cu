@@ -586,8 +586,8 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
         const double growth = 2.0 * (1.0 + 2.0 * 99.0 / ntheta);
         P.hshift = (int)ceil(log2(growth)) + 1;
         if (P.hshift > 20) return fail(RP_EUNSUPPORTED, "theta too close to 1 for the fp32 painter (use RP_FP64)");
-        P.k1c = (277 - P.hshift) << 23;
-        P.k2c = (P.hshift - 23) * (1 << 23);
+        P.k1c = 283 << 23;          // k1 = as_float(k1c - exponent bits of the bound) = 2^(29 - E)
+        P.k2c = -29 * (1 << 23);    // k2 = as_float(exponent bits + k2c)            = 2^(E - 29)
         // band edges in fixed-point units of the REDUX sum, as float bit patterns to which the kernel adds the exponent of
         // the previous sum: forward B = S, backward B = ntheta*S
         for (int dir = 0; dir < 2; dir++) {

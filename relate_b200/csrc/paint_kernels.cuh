@@ -538,8 +538,8 @@ struct PaintParams {
     char *segstate;        // [2][nt] parked states of segstride bytes: team vector, tail elements, scalars
     size_t segstride;
     double *scratch;       // fp64 mode only: [gridDim.x][N] staging rows for backward stepping stones
-    int hshift;            // fixed-point headroom of the REDUX sum: S_new < 2^hshift * 2^floor(log2 S_prev) always
-    int k1c, k2c;          // (277-hshift)<<23 and (hshift-23)<<23: exponent arithmetic of the fixed-point scale
+    int hshift;            // (unused by the single-REDUX sum; kept for the ABI of PaintParams users)
+    int k1c, k2c;          // 283<<23 and -29<<23: exponent arithmetic of the fixed-point unit 2^(E-29)
     int xlo[2], xhi[2];    // per direction: float bits of band_lower/chk resp. band_upper/chk (a hair inside), pre-scaled so
                            // that as_float(x - exponent bits of the previous sum) is the band edge in fixed-point units
     PaintConsts<float> cf;
@@ -579,6 +579,11 @@ template <int WPT> __device__ __forceinline__ void load_words(uint32_t (&w)[WPT]
     }
 }
 
+#ifndef RP_SUM_FLOOR_LOG2
+#define RP_SUM_FLOOR_LOG2 23 // least fixed-point units the single-REDUX team sum must carry (else: butterfly on the rare path).
+                            // Measured at config 2 (scripts/acc_check.py, sweep of 20/23/25/27): kernel 2.20 / 2.21 / 2.25 / 2.31 ms,
+                            // max relative error of the stepping stones 4.1e-6 / 8.6e-7 / 8.4e-7 / 7.6e-7
+#endif
 #ifndef RP_PF
 #define RP_PF 1 // L1 prefetch hints for the genotype rows / site tables of later steps
 #endif
@@ -611,6 +616,8 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
     // chk and widened by a hair; the handler repeats the reference's exact test on B = chk*S
     T tau = K.tau, band_lo = K.lower / (DIR ? K.ntheta : (T)1) * (T)1.000002, band_hi = K.upper / (DIR ? K.ntheta : (T)1) * (T)0.999998;
     opaque(tau);
+    float Nf = (float)P.N; // every element gains R per step: S_new <= S + N*R bounds the coming sum
+    opaque(Nf);
     opaque(band_lo);
     opaque(band_hi);
     const Ent *ents = reinterpret_cast<const Ent *>(P.ent);
@@ -742,14 +749,24 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         // B > upper implies hi > Y - 17.  The handler repeats the exact test, so results do not change; what changes is
         // that the branch needs only REDUX -> I2F -> two compares instead of the whole float reconstruction of B.
         float k1 = 0.f, k2 = 0.f, tlo = 0.f, thi = 0.f;
+        // The fixed-point unit is 2^(E-29), E the exponent of an upper bound of the coming sum: S_new <= S + N*R (every
+        // element gains R and is then multiplied by tau or 1), so the 32 lane sums, rounded to that unit, add up to less
+        // than 2^30 in ONE integer REDUX; at least kSumFloor units (2^23: the lanes' roundings are <= 16 units, ~2 typical)
+        // are required of the result, else the step goes through the rare path, which redoes the sum with the shuffle
+        // butterfly (the sum then lost more than 2^6 of its bound in one step).
+        constexpr float kSumFloor = (float)(1u << RP_SUM_FLOOR_LOG2);
         auto set_scale_e = [&](int ebs) {
-            k1 = __int_as_float(P.k1c - ebs);   // 2^(23 - hshift - E)
-            k2 = __int_as_float(ebs + P.k2c);   // 2^(E + hshift - 23)
-            tlo = fmaf(__int_as_float(P.xlo[DIR] - ebs), 1.5f, 64.0f);
+            k1 = __int_as_float(P.k1c - ebs);   // 2^(29 - E)
+            k2 = __int_as_float(ebs + P.k2c);   // 2^(E - 29)
+            tlo = __int_as_float(P.xlo[DIR] - ebs) + (kSumFloor + 17.0f);
             thi = __int_as_float(P.xhi[DIR] - ebs) - 17.0f;
         };
-        auto set_scale = [&](float sprev) { set_scale_e(__float_as_int(sprev) & 0x7f800000); };
-        if (!MULTI && sizeof(T) == 4) set_scale(DIR ? (float)P.N : 1.0f);
+        // bound = S + N*R for the step whose additive term is R
+        auto set_scale = [&](float Scur, float Rnext) {
+            const float bound = fmaxf(fmaf(Rnext, Nf, Scur), 1e-30f);
+            set_scale_e(__float_as_int(bound) & 0x7f800000);
+        };
+        if (!MULTI && sizeof(T) == 4) set_scale(0.0f, DIR ? 1.0f : (float)K.prior_n);
 
         // x <- (x + R) * (mis ? tau : 1);  returns the team-wide sum.  mis = target derived && reference
         // ancestral; tdm is all-ones when the target is derived at the site (always, except SNP 0 / L-1).
@@ -790,26 +807,15 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         // team-wide sum: warp butterfly, then (multi-warp teams) one bar.sync and a shared-memory exchange
         auto reduce = [&](T S, int parity, float tlo_e, int &sa_out, bool &rare) -> T {
             if (!MULTI && sizeof(T) == 4) {
-                // Single-warp fp32 teams: the 32 lane sums are added as 46-bit fixed point with two integer REDUX
-                // (exact, order-free) instead of a 5-level shuffle butterfly (150 -> ~70 cycles of dependent latency).
-                // The scale comes from the previous step's sum: 0 <= S < 2^hshift * 2^floor(log2 S_prev), because
-                // S_new <= S_prev * (1 + N*c) and N*c <= 2*0.99/0.01 (rho cap) / (1-theta).  hi/lo are 23-bit halves
-                // taken with the 2^23 / 1.5*2^23 magic-number roundings; every operation up to the I2F is exact, the
-                // lanes' roundings to the 2^-46 grid add up to <= 16 units.  When the sum fell so far below the scale
-                // that fewer than 2^29 units are left (the vector lost > 2^(17-hshift) of its mass in one step),
-                // `lowprec` sends the step through the rare-path handler, which redoes the sum with the butterfly, so
-                // the result always carries fp32 precision.
-                const float sl = (float)S;
-                const float a = fmaf(sl, k1, 8388608.0f);
-                const float ah = a - 8388608.0f;
-                const float rem = fmaf(sl, k1, -ah);
-                const float b = fmaf(rem, 8388608.0f, 12582912.0f);
-                const int sa = __reduce_add_sync(0xffffffffu, __float_as_int(a)) - (int)(32u * 0x4B000000u);
-                const int sb = __reduce_add_sync(0xffffffffu, __float_as_int(b)) - (int)(32u * 0x4B400000u);
+                // Single-warp fp32 teams: the 32 lane sums are rounded to the fixed-point unit chosen by set_scale and added
+                // by one integer REDUX (order-free; ~30 cycles of dependent latency instead of the ~150 of a 5-level
+                // shuffle butterfly).  v4/v5 carried 46 bits in two REDUX with a fixed 2^hshift of headroom over the
+                // previous sum; the exact bound S + N*R makes one 32-bit word enough.
+                const int sa = __reduce_add_sync(0xffffffffu, __float2int_rn((float)S * k1));
                 const float fsa = (float)sa;
-                sa_out = sa;       // sa < 64: handled on the rare path (the step is redone with the butterfly)
+                sa_out = sa;       // sa < kSumFloor: handled on the rare path (the step is redone with the butterfly)
                 rare = (fsa < tlo_e) || (fsa > thi);
-                return (T)(fmaf((float)sb, 1.0f / 8388608.0f, fsa) * k2);
+                return (T)(fsa * k2);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
@@ -919,7 +925,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 for (int o = 16; o > 0; o >>= 1) Sl += __shfl_xor_sync(0xffffffffu, Sl, o);
                 S = Sl;
                 R = S * cthis;
-                set_scale((float)S);
+                set_scale((float)S, (float)R);
             }
             const T B = chk * S;
             bool rescaled = false;
@@ -942,7 +948,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
                 }
                 lsr += DIR ? (double)fast_log_dev((float)B) : log((double)B);
                 R = resc_R * cthis;
-                if (!MULTI && sizeof(T) == 4) set_scale((float)resc_R); // the state now sums to 1 (forward) or 1/ntheta
+                if (!MULTI && sizeof(T) == 4) set_scale((float)resc_R, (float)R); // the state now sums to 1 (forward) or 1/ntheta
             }
             if (DIR && post) { // finalise the backward stepping stone(s) of step p: divide by B if it rescaled
                 for (int qq = q; qq < q1; qq++) {
@@ -1074,15 +1080,15 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             R = S * ccur;
             cX = (T)e2.c;
             if (!MULTI && sizeof(T) == 4) {
-                set_scale((float)S);
+                set_scale((float)S, (float)R);
             } else {
                 const T lo_e = ev ? (T)INFINITY : band_lo; // (EV == 2) a pending event folded into the threshold
                 rare = (S < lo_e) || (S > band_hi);
             }
             // the rare path is taken by all threads or none (S is the team-wide sum): tell the compiler with a vote, so
             // the branch needs no reconvergence bookkeeping
-            if (EV == 1) handler(p, S, ccur, Sl, sa < 64);
-            else if (__builtin_expect(__any_sync(0xffffffffu, rare), 0)) handler(p, S, ccur, Sl, sa < 64);
+            if (EV == 1) handler(p, S, ccur, Sl, (float)sa < kSumFloor);
+            else if (__builtin_expect(__any_sync(0xffffffffu, rare), 0)) handler(p, S, ccur, Sl, (float)sa < kSumFloor);
         };
         auto step_even = [&](auto evc, int p) { do_step(evc, p, wA, cA, sA, fA, wB, cB, sB, fB); }; // computes from set A
         auto step_odd = [&](auto evc, int p) { do_step(evc, p, wB, cB, sB, fB, wA, cA, sA, fA); };  // computes from set B
