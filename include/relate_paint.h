@@ -193,6 +193,10 @@ int rp_peak_fp32(int device, double *lane_ops_per_s_mix, double *lane_ops_per_s_
 int rp_debug_pack(int device, int N, int L, const char *hap, uint32_t *snp_major, int *words_per_snp,
                   uint32_t *hap_major, int *words_per_hap);
 
+/* The stage driver's host-side packer (what its reader threads apply to the rows of chunk_<c>.hap they read): L rows of
+ * N chars -> L rows of words_per_snp words, bit n&31 of word n>>5 = (hap[n] == '1'), padding zero.  Host-only. */
+int rp_debug_pack_host(int N, int L, const char *hap, uint32_t *snp_major, int words_per_snp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,7 @@ SYMBOLS = {
                                  C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
     "rp_rle_encode": (C.c_int, [_P, C.c_int, _P, _P]),
     "rp_fast_log_device": (C.c_int, [C.c_int, _P, _P, C.c_int]),
+    "rp_debug_pack_host": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int]),
     "rp_debug_pack": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int), _P, C.POINTER(C.c_int)]),
 }
 

@@ -961,6 +961,13 @@ int rp_peak_fp32(int device, double *lane_ops_per_s_mix, double *lane_ops_per_s_
     return RP_OK;
 }
 
+int rp_debug_pack_host(int N, int L, const char *hap, uint32_t *snp_major, int words_per_snp)
+{
+    if (!hap || !snp_major || N < 1 || L < 1 || words_per_snp < (N + 31) / 32) return fail(RP_EINVAL, "bad argument");
+    for (int s = 0; s < L; s++) pack_row_host(hap + (size_t)s * N, N, snp_major + (size_t)s * words_per_snp, words_per_snp);
+    return RP_OK;
+}
+
 int rp_debug_pack(int device, int N, int L, const char *hap, uint32_t *snp_major, int *words_per_snp,
                   uint32_t *hap_major, int *words_per_hap)
 {

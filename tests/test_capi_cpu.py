@@ -88,6 +88,21 @@ def test_host_rle_encoder_matches_oracle():
             assert a[1].sum() == n
 
 
+@pytest.mark.parametrize("N,L", [(1, 3), (8, 70), (31, 9), (32, 5), (33, 5), (100, 40), (1000, 7), (1056, 3)])
+def test_host_bit_packer(N, L):
+    """The stage driver's reader threads pack the genotype rows they read (SSE2 compare + movemask, a scalar tail, zero
+    padding): against numpy's packbits, for full words, partial last words and padded rows."""
+    rng = np.random.default_rng(N * 131 + L)
+    hap = np.where(rng.random((L, N)) < 0.4, ord("1"), ord("0")).astype(np.uint8)
+    wps = (((N + 31) // 32 + 3) // 4) * 4
+    G = np.full((L, wps), 0xDEADBEEF, np.uint32)
+    capi.check(capi.lib().rp_debug_pack_host(N, L, hap.ctypes.data, G.ctypes.data, wps))
+    exp = np.zeros((L, wps * 32), bool)
+    exp[:, :N] = hap == ord("1")
+    expG = np.packbits(exp.reshape(L, -1, 32), axis=-1, bitorder="little").view(np.uint32).reshape(L, -1)
+    assert np.array_equal(G, expG)
+
+
 def test_cli_flag_surface(tmp_path):
     exe = os.path.join(ROOT, "relate_b200", "bin", "relate")
     p = subprocess.run([exe, "--mode", "Paint"], capture_output=True, text=True)
