@@ -588,16 +588,16 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
         if (P.hshift > 20) return fail(RP_EUNSUPPORTED, "theta too close to 1 for the fp32 painter (use RP_FP64)");
         P.k1c = 283 << 23;          // k1 = as_float(k1c - exponent bits of the bound) = 2^(29 - E)
         P.k2c = -29 * (1 << 23);    // k2 = as_float(exponent bits + k2c)            = 2^(E - 29)
-        // band edges in fixed-point units of the REDUX sum, as float bit patterns to which the kernel adds the exponent of
-        // the previous sum: forward B = S, backward B = ntheta*S
+        // band edges for the kernel's rare-path pre-filter (it multiplies them into fixed-point units): forward B = S,
+        // backward B = ntheta*S
         for (int dir = 0; dir < 2; dir++) {
             const float chk = dir ? P.cf.ntheta : 1.0f;
             const float lo = P.cf.lower / chk * 1.000002f, hi = P.cf.upper / chk * 0.999998f;
             int lob, hib;
             memcpy(&lob, &lo, 4);
             memcpy(&hib, &hi, 4);
-            P.xlo[dir] = lob + P.k1c - (127 << 23);
-            P.xhi[dir] = hib + P.k1c - (127 << 23);
+            P.xlo[dir] = lob;
+            P.xhi[dir] = hib;
         }
     }
     int ctas = 0;

@@ -540,8 +540,7 @@ struct PaintParams {
     double *scratch;       // fp64 mode only: [gridDim.x][N] staging rows for backward stepping stones
     int hshift;            // (unused by the single-REDUX sum; kept for the ABI of PaintParams users)
     int k1c, k2c;          // 283<<23 and -29<<23: exponent arithmetic of the fixed-point unit 2^(E-29)
-    int xlo[2], xhi[2];    // per direction: float bits of band_lower/chk resp. band_upper/chk (a hair inside), pre-scaled so
-                           // that as_float(x - exponent bits of the previous sum) is the band edge in fixed-point units
+    int xlo[2], xhi[2];    // per direction: float bits of band_lower/chk resp. band_upper/chk (a hair inside)
     PaintConsts<float> cf;
     PaintConsts<double> cd;
 };
@@ -755,11 +754,14 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         // are required of the result, else the step goes through the rare path, which redoes the sum with the shuffle
         // butterfly (the sum then lost more than 2^6 of its bound in one step).
         constexpr float kSumFloor = (float)(1u << RP_SUM_FLOOR_LOG2);
+        float blo_c = __int_as_float(P.xlo[DIR]), bhi_c = __int_as_float(P.xhi[DIR]); // band edges / chk, a hair inside
+        opaque(blo_c);
+        opaque(bhi_c);
         auto set_scale_e = [&](int ebs) {
             k1 = __int_as_float(P.k1c - ebs);   // 2^(29 - E)
             k2 = __int_as_float(ebs + P.k2c);   // 2^(E - 29)
-            tlo = __int_as_float(P.xlo[DIR] - ebs) + (kSumFloor + 17.0f);
-            thi = __int_as_float(P.xhi[DIR] - ebs) - 17.0f;
+            tlo = fmaf(k1, blo_c, kSumFloor + 17.0f); // band edges in fixed-point units: (lower / chk) * k1, (upper / chk) * k1
+            thi = fmaf(k1, bhi_c, -17.0f);
         };
         // bound = S + N*R for the step whose additive term is R
         auto set_scale = [&](float Scur, float Rnext) {
