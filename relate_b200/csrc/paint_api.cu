@@ -103,6 +103,7 @@ struct rp_chunk {
     int device = 0;
     int N = 0, L = 0, W = 0;
     int wps = 0, lw = 0, nfw = 0, tailn = 0;
+    int padbit = 0; // pad bits of a partial last word in G: 1 when theta > 1/2 (the painter's phantoms take the smaller multiplier)
     unsigned flags = 0;
     double theta = 0.001;
     int sm_count = 148;
@@ -298,6 +299,7 @@ struct HapFeed {
     size_t slice = 0; // bytes of one ring slot
     int rows = 0;     // SNP rows per slice
     int nsl = 0, nslots = 0, ndev = 1;
+    int padbit = 0;   // genotype bit of the slots past N in a partial last word (1 when theta > 1/2)
     const char *ring = nullptr;
     std::unique_ptr<std::atomic<int>[]> ready, consumed;
     std::atomic<int> abort{0};
@@ -307,7 +309,7 @@ struct HapFeed {
 
 // chars '0'/'1' of one SNP row -> bits (bit n&31 of word n>>5 = hap[n] == '1'), words beyond the row zeroed;
 // what pack_snp_major_kernel does on the device
-inline void pack_row_host(const char *p, int N, uint32_t *out, int wps)
+inline void pack_row_host(const char *p, int N, uint32_t *out, int wps, int padbit = 0)
 {
     const __m128i one = _mm_set1_epi8('1');
     int n = 0, w = 0;
@@ -319,6 +321,7 @@ inline void pack_row_host(const char *p, int N, uint32_t *out, int wps)
     if (n < N) {
         uint32_t bits = 0;
         for (int j = 0; n + j < N; j++) bits |= (uint32_t)(p[n + j] == '1') << j;
+        if (padbit) bits |= ~0u << (N - n); // phantom slots of the partial last word (tau > 1)
         out[w++] = bits;
     }
     for (; w < wps; w++) out[w] = 0;
@@ -371,6 +374,7 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
     c->wb.assign(wb, wb + n_wb);
     c->nfw = N / 32;
     c->tailn = N % 32;
+    c->padbit = theta > 0.5 ? 1 : 0;
     c->wps = (((N + 31) / 32) + 3) / 4 * 4; // rows padded to 16 bytes
     c->lw = (L + 31) / 32;
     if (!reused) {
@@ -428,7 +432,7 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
         const int th = 256;
         if (!feed) {
             rp::pack_snp_major_kernel<<<(unsigned)((total + th - 1) / th), th, 0, c->stream>>>(
-                chars.as<unsigned char>(), N, L, c->G.as<uint32_t>(), c->wps);
+                chars.as<unsigned char>(), N, L, c->G.as<uint32_t>(), c->wps, c->padbit);
             RP_CUDAB(cudaGetLastError());
         }
         dim3 grid((N + 31) / 32, (c->lw + 31) / 32), block(32, 32);
@@ -555,6 +559,7 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     P.W = W;
     P.nfw = (N + 31) / 32; // the partial last word counts as a word of the team
     P.tailn = c->tailn;
+    P.padbit = c->padbit;
     P.k0 = k0;
     P.nt = nt;
     P.ent = c->ent.as<char>() + pad * entsz;
@@ -582,12 +587,14 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     P.cf.inv_ntheta = (float)P.cd.inv_ntheta;
     P.cf.lower = (float)P.cd.lower;
     P.cf.upper = (float)P.cd.upper;
-    {   // headroom of the fixed-point REDUX sum: S_new <= S_prev*(1 + N*c'), N*c' <= 2*99/(1-theta); S_prev < 2^(E+1)
-        const double growth = 2.0 * (1.0 + 2.0 * 99.0 / ntheta);
-        P.hshift = (int)ceil(log2(growth)) + 1;
-        if (P.hshift > 20) return fail(RP_EUNSUPPORTED, "theta too close to 1 for the fp32 painter (use RP_FP64)");
-        P.k1c = 283 << 23;          // k1 = as_float(k1c - exponent bits of the bound) = 2^(29 - E)
-        P.k2c = -29 * (1 << 23);    // k2 = as_float(exponent bits + k2c)            = 2^(E - 29)
+    {   // Fixed-point unit of the single-REDUX team sum: 2^(E - 29 + h), E the exponent of the bound S + N*R the kernel
+        // forms per step.  That bound assumes multipliers <= 1; for theta > 1/2 the mismatch multiplier tau = theta/(1-theta)
+        // exceeds 1 and the sum can reach tau*(S + N*R): h = ceil(log2(tau)) bits of headroom cover it.
+        const double tau = c->theta / ntheta;
+        P.hshift = tau > 1.0 ? (int)ceil(log2(tau)) : 0;
+        if (P.hshift > 6) return fail(RP_EUNSUPPORTED, "theta too close to 1 for the fp32 painter (use RP_FP64)");
+        P.k1c = (283 - P.hshift) << 23;       // k1 = as_float(k1c - exponent bits of the bound) = 2^(29 - h - E)
+        P.k2c = (-29 + P.hshift) * (1 << 23); // k2 = as_float(exponent bits + k2c)            = 2^(E + h - 29)
         // band edges for the kernel's rare-path pre-filter (it multiplies them into fixed-point units): forward B = S,
         // backward B = ntheta*S
         for (int dir = 0; dir < 2; dir++) {
@@ -1439,6 +1446,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     feed.nsl = (hc.L + feed.rows - 1) / feed.rows;
     feed.nslots = (int)std::min<size_t>((size_t)feed.nsl, std::max<size_t>(2, ring_cap / feed.slice));
     feed.ndev = (int)devs.size();
+    feed.padbit = hc.theta > 0.5 ? 1 : 0; // as chunk_from_host sets rp_chunk::padbit
     PinnedBuf &hap_in = g_ws.at(devs[0]).hap_in;
     if (hap_in.ensure((size_t)feed.nslots * feed.slice) != RP_OK) {
         close(hap_fd);
@@ -1476,7 +1484,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
                 ok = ok && rp::read_hap_range(hap_fd, (size_t)row0 * hc.N, (size_t)nrows * hc.N, raw.data());
                 if (ok) {
                     uint32_t *dst = reinterpret_cast<uint32_t *>(const_cast<char *>(feed.src(i)));
-                    for (int rr = 0; rr < nrows; rr++) pack_row_host(raw.data() + (size_t)rr * hc.N, hc.N, dst + (size_t)rr * wps, wps);
+                    for (int rr = 0; rr < nrows; rr++) pack_row_host(raw.data() + (size_t)rr * hc.N, hc.N, dst + (size_t)rr * wps, wps, feed.padbit);
                 }
                 feed.ready[i].store(ok ? 1 : -1, std::memory_order_release);
             }

@@ -82,8 +82,9 @@ __global__ void __launch_bounds__(256) peak_fp32_kernel(float *out, int iters, f
 // ---------------------------------------------------------------------------------------
 // Bit packing.  hap: L*N chars; G: L rows of `wps` words, bit (n&31) of word n>>5 = hap[s][n]=='1'.
 // One thread per output word; a warp reads 1 KiB of consecutive chars.
+// padbit: value of the slots past N in a partial last word (the painter's phantom haplotypes, see paint_jobs)
 __global__ void pack_snp_major_kernel(const unsigned char *__restrict__ hap, int N, int L, uint32_t *__restrict__ G,
-                                      int wps)
+                                      int wps, int padbit)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)L * wps;
@@ -111,6 +112,7 @@ __global__ void pack_snp_major_kernel(const unsigned char *__restrict__ hap, int
         } else {
             for (int j = 0; j < cnt; j++) bits |= (uint32_t)(p[j] == '1') << j;
         }
+        if (padbit && cnt < 32) bits |= ~0u << cnt;
     }
     G[idx] = bits;
 }
@@ -523,6 +525,7 @@ struct PaintParams {
     int N, L, W;
     int nfw;               // 32-haplotype words per row, a partial last word included: ceil(N / 32)
     int tailn;             // N % 32
+    int padbit;            // genotype bit of the phantom slots of a partial last word: 0 if tau <= 1, 1 if tau > 1
     int k0, nt;            // targets [k0, k0+nt); each is one forward and one backward job
     const void *ent;       // EntF[] or EntD[], padded by 4 valid entries at both ends
     const long long *off;  // [nt+1]
@@ -538,8 +541,8 @@ struct PaintParams {
     char *segstate;        // [2][nt] parked states of segstride bytes: team vector, tail elements, scalars
     size_t segstride;
     double *scratch;       // fp64 mode only: [gridDim.x][N] staging rows for backward stepping stones
-    int hshift;            // (unused by the single-REDUX sum; kept for the ABI of PaintParams users)
-    int k1c, k2c;          // 283<<23 and -29<<23: exponent arithmetic of the fixed-point unit 2^(E-29)
+    int hshift;            // h: headroom bits of the single-REDUX sum for multipliers > 1 (theta > 1/2), else 0
+    int k1c, k2c;          // (283-h)<<23 and (h-29)<<23: exponent arithmetic of the fixed-point unit 2^(E-29+h)
     int xlo[2], xhi[2];    // per direction: float bits of band_lower/chk resp. band_upper/chk (a hair inside)
     PaintConsts<float> cf;
     PaintConsts<double> cd;
@@ -642,10 +645,11 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
     const char *gthr = reinterpret_cast<const char *>(P.G + ((gt * WPT + WPT - 1) < P.wps ? gt * WPT : 0));
     asm volatile("" : "+l"(gthr));
     // The last word of a row may be partial (P.tailn = N % 32 haplotypes).  Its owner treats it as a full word: the
-    // missing slots are phantom haplotypes with genotype bit 0 (the packer pads with zeros), i.e. haplotypes that
-    // mismatch wherever the target is derived.  All phantoms carry the same value, which every thread tracks in one
-    // scalar (xph, the same two roundings per step as the registers, so it is bit-identical to them) and the owner
-    // subtracts nph * xph from its sum.  A phantom is never larger than any real element (same R, never a larger
+    // missing slots are phantom haplotypes whose genotype bit the packer chose so that they always take the SMALLER of
+    // the two multipliers: bit 0 (mismatching wherever the target is derived) when tau <= 1, bit 1 (never mismatching)
+    // when tau > 1, i.e. theta > 1/2.  All phantoms carry the same value, which every thread tracks in one scalar (xph,
+    // the same two roundings per step as the registers, so it is bit-identical to them) and the owner subtracts
+    // nph * xph from its sum.  A phantom is then never larger than any real element (same R, never a larger
     // multiplier), so xph <= S/N and the subtraction costs no precision.  No extra load, predicate or branch per step.
     T nph = (T)0;
 #pragma unroll
@@ -897,7 +901,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 
         T R = DIR ? (T)1 : K.prior_n; // step 0 is x = (0 + R0) * m
         uint32_t tdm = td_first;
-        mph = td_first ? tau : (T)1;
+        mph = (td_first && !P.padbit) ? tau : (T)1;
         int q1 = q;
         bool post = false;
 
@@ -931,7 +935,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             }
             const T B = chk * S;
             bool rescaled = false;
-            if (p == 0) { tdm = 0xffffffffu; mph = tau; } // steps 1..m-1 visit sites where the target is derived
+            if (p == 0) { tdm = 0xffffffffu; mph = P.padbit ? (T)1 : tau; } // steps 1..m-1 visit sites where the target is derived
             if (p != 0 && (B < K.lower || B > K.upper)) { // :334-347, :538-551; no test at the first site
                 rescaled = true;
                 if (sizeof(T) == 4) { // fp32 state: one reciprocal, then multiplies (<= 1 ulp from the division)
@@ -979,7 +983,7 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
             if (pn > m) { pev = 0x7fffffff; return; }
             pev = next_event();
             if (pev == pn) {
-                if (pn == m) { tdm = td_last; mph = td_last ? tau : (T)1; }
+                if (pn == m) { tdm = td_last; mph = (td_last && !P.padbit) ? tau : (T)1; }
                 const int bp_now = q < P.W ? bpos(q) : -1;
                 if (bp_now == (DIR ? pn : pn - 1)) {
                     q1 = q;

@@ -74,7 +74,7 @@ def test_fp32_matches_oracle(N, L, W, seed, wpt, nk):
 def test_random_small_shapes_match_oracle():
     """Seeded sweep over awkward shapes: tiny N and L (down to 2), ragged random window boundaries (one-SNP windows,
     windows without any derived site of a target), recombination rates from exact zeros to beyond the rho cap, random
-    genotypes of any density, a theta other than the default.  Boundary SNPs exact, vectors within 1e-4, both state types."""
+    genotypes of any density, thetas other than the default (one beyond 1/2).  Boundary SNPs exact, vectors within 1e-4, both state types."""
     rng = np.random.default_rng(20261017)
     for case in range(40):
         N = int(rng.integers(2, 71))
@@ -85,7 +85,7 @@ def test_random_small_shapes_match_oracle():
         dens = float(rng.choice([0.02, 0.2, 0.5, 0.9]))
         hap = np.where(rng.random((L, N)) < dens, ord("1"), ord("0")).astype(np.uint8)
         r = rng.choice([0.0, 1e-7, 1e-4, 3e-3, 0.5, 7.0], size=L, p=[0.15, 0.2, 0.3, 0.2, 0.1, 0.05]).astype(np.float64)
-        theta = float(np.float32(rng.choice([0.001, 0.025, 0.2])))
+        theta = float(np.float32(rng.choice([0.001, 0.025, 0.2, 0.7])))  # (0.7: mismatch multiplier tau > 1)
         o = oracle.paint_targets(hap, r, wb, theta, 0, N)
         for fp64 in (False, True):
             with capi.DeviceChunk.from_arrays(hap, r, wb, theta, fp64=fp64) as c:
@@ -224,6 +224,24 @@ def test_painting_rho_and_default_theta(tmp_path):
             a, b = painting.split(",")
             theta, rho = float(np.float32(a)), float(np.float32(b))
         compare(g, oracle.paint_targets(ch.hap, ch.r * rho, ch.wb, theta, 0, 16))
+
+
+def test_theta_beyond_one_half_through_the_stage(tmp_path):
+    """theta > 1/2 makes the mismatch multiplier tau > 1: the phantom slots of a partial last genotype word must then be
+    packed as derived (they have to take the smaller multiplier), on the device (rp_chunk_load) and by the stage
+    driver's host packer alike, and the fixed-point team sum needs headroom.  N=100 (a 4-haplotype partial word)."""
+    d = str(tmp_path / "o")
+    synth.make_chunk_dir(d, 100, 1500, seed=61, n_windows=4)
+    ch = chunkio.read_chunk(d, 0)
+    theta = float(np.float32(0.7))
+    with capi.DeviceChunk.load(d, 0, "0.7,1") as c:
+        compare(c.paint_targets(0, 100), oracle.paint_targets(ch.hap, ch.r, ch.wb, theta, 0, 100))
+    capi.paint_chunk(d, 0, "0.7,1")
+    shutil.copytree(d, str(tmp_path / "ora"), ignore=shutil.ignore_patterns("paint"))
+    oracle.paint_chunk(str(tmp_path / "ora"), 0, "0.7,1")
+    for w in range(4):
+        decoded_close(os.path.join(d, "chunk_0", "paint", f"relate_{w}.bin"),
+                      str(tmp_path / "ora" / "chunk_0" / "paint" / f"relate_{w}.bin"), 100, 1.1e-3)
 
 
 def test_target_range_invariance_and_determinism():
