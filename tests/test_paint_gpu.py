@@ -242,6 +242,13 @@ def test_theta_beyond_one_half_through_the_stage(tmp_path):
     for w in range(4):
         decoded_close(os.path.join(d, "chunk_0", "paint", f"relate_{w}.bin"),
                       str(tmp_path / "ora" / "chunk_0" / "paint" / f"relate_{w}.bin"), 100, 1.1e-3)
+    # multi-warp teams and a cluster of two CTAs with a partial last word (N = 2100 = 65 words + 20 haplotypes)
+    hap, r, wb = make_case(2100, 600, 3, 62)
+    o = oracle.paint_targets(hap, r, wb, theta, 30, 60)
+    for cluster in (0, 2):
+        with capi.DeviceChunk.from_arrays(hap, r, wb, theta) as c:
+            c.set_tune(cluster=cluster)
+            compare(c.paint_targets(30, 60), o)
 
 
 def test_target_range_invariance_and_determinism():
