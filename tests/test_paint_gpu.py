@@ -673,7 +673,8 @@ def test_window_distances_match_reference_golden(tmp_path):
                     assert float(np.abs(got - ref).max()) <= tol, (sec, snp)
 
 
-@pytest.mark.parametrize("N,L,W", [(200, 3000, 3), (1000, 1500, 2), (2100, 700, 2)])
+@pytest.mark.parametrize("N,L,W", [(200, 3000, 3), (1000, 1500, 2), (2100, 700, 2), (5, 60, 2), (37, 90, 3), (64, 200, 1),
+                                   (33, 300, 4)])
 def test_window_distances_vs_oracle_on_gpu_painted_files(tmp_path, N, L, W):
     """Paint on the GPU, then the GPU window path vs the oracle's RePaintSection+GetMatrix on the same files
     (single-warp, tail and multi-warp teams)."""
