@@ -242,6 +242,14 @@ def test_theta_beyond_one_half_through_the_stage(tmp_path):
     for w in range(4):
         decoded_close(os.path.join(d, "chunk_0", "paint", f"relate_{w}.bin"),
                       str(tmp_path / "ora" / "chunk_0" / "paint" / f"relate_{w}.bin"), 100, 1.1e-3)
+    # the consumer side on those files: window repaint + distance matrices vs the oracle at the same theta
+    with capi.DeviceChunk.load(d, 0, "0.7,1") as c:
+        for sec in (0, 3):
+            out = str(tmp_path / f"ora_d{sec}.bin")
+            oracle.window_distances(d, 0, sec, 97, "0.7,1", out)
+            with capi.Window.open_files(c, d, 0, sec) as win:
+                worst = max(float(np.abs(win.distance(snp) - ref).max()) for snp, ref in oracle.read_distances(out).items())
+            assert worst <= 1e-4 * max(1.0, abs(np.log(theta / (1 - theta)))), (sec, worst)
     # multi-warp teams and a cluster of two CTAs with a partial last word (N = 2100 = 65 words + 20 haplotypes)
     hap, r, wb = make_case(2100, 600, 3, 62)
     o = oracle.paint_targets(hap, r, wb, theta, 30, 60)
