@@ -200,10 +200,9 @@ int launch_paint_t(rp_chunk *c, rp::PaintParams &P, int threads, int &ctas)
         P.segready = c->segdone.as<int>();
         P.segstate = c->segstate.as<char>();
     }
-#ifndef RP_FULLGRID
-#define RP_FULLGRID 1
-#endif
-    ctas = 2 * (int)std::min<long long>((long long)P.nt * (RP_FULLGRID ? nseg : 1), slots); // even CTAs paint forwards, odd ones backwards
+    // with segments the grid is the full occupancy even when there are fewer chains than slots: the idle teams are what
+    // lets chains migrate towards lightly loaded sub-partitions
+    ctas = 2 * (int)std::min<long long>((long long)P.nt * nseg, slots); // even CTAs paint forwards, odd ones backwards
     kern<<<ctas, threads, 0, c->stream>>>(P);
     RP_CUDA(cudaGetLastError());
     return RP_OK;
