@@ -144,7 +144,8 @@ int rp_paint_from_host(int device, int N, int L, const char *hap, const double *
                        float *beta, float *ls_alpha, float *ls_beta, int *site_begin, int *site_end,
                        rp_stats *stats);
 
-/* The whole stage: load chunk files, paint every target on the given devices (targets sharded over
+/* The whole stage: load chunk files (the genotype rows are bit-packed by the reader threads, so the devices
+ * receive 1 bit per genotype), paint every target on the given devices (targets sharded over
  * devices by visited-site count, no collective), RLE-encode and write
  * <out_dir>/chunk_<c>/paint/relate_<w>.bin in target order.  devices==NULL: device 0 only. */
 int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
