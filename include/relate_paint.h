@@ -145,9 +145,15 @@ int rp_paint_from_host(int device, int N, int L, const char *hap, const double *
                        rp_stats *stats);
 
 /* The whole stage: load chunk files (the genotype rows are bit-packed by the reader threads, so the devices
- * receive 1 bit per genotype), paint every target on the given devices (targets sharded over
- * devices by visited-site count, no collective), RLE-encode and write
- * <out_dir>/chunk_<c>/paint/relate_<w>.bin in target order.  devices==NULL: device 0 only. */
+ * receive 1 bit per genotype), paint every target on the given devices, encode the records on the device and write
+ * <out_dir>/chunk_<c>/paint/relate_<w>.bin in target order.  devices==NULL: device 0 only; a device index may
+ * appear only once (RP_EINVAL otherwise).  Every device holds a replica of the chunk; targets are cut into
+ * equal-count batches which the devices pull from one shared counter (dynamic balance, no collective); a batch's
+ * records are written at absolute file offsets as soon as the sizes of all earlier batches are known.
+ * Parity: with flags == 0 the state is fp32; stepping stones agree with the reference's to ~1e-6 relative (gate 1e-4),
+ * so the paint files are NOT byte-identical to the reference's (the lossy codec may also start a run one element
+ * earlier or later), but the reference's BuildTopology gives identical trees on the tested data.  With RP_FP64 the
+ * files are byte-identical to the reference's on every fixture the tests hold. */
 int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
                    int n_devices, unsigned flags, rp_stats *stats);
 
@@ -174,6 +180,8 @@ int rp_window_open(rp_chunk *c, int w, const float *alpha, const float *beta, co
 int rp_window_open_resident(rp_chunk *c, int w, const double *rpos, rp_window **out, rp_stats *stats);
 /* Same, reading <out_dir>/chunk_<c>/paint/relate_<w>.bin and chunk_<c>.rpos. */
 int rp_window_open_files(rp_chunk *c, const char *out_dir, int chunk_index, int w, rp_window **out, rp_stats *stats);
+/* Lifetime: a window refers to its chunk (bit matrices, stream); close it before freeing the chunk.  A window whose
+ * chunk has been freed only accepts rp_window_close; rp_window_distance on it fails with RP_EINVAL. */
 int rp_window_distance(rp_window *win, int snp, float *d);
 long long rp_window_rows(const rp_window *win);
 void rp_window_close(rp_window *win);
@@ -182,7 +190,8 @@ void rp_window_close(rp_window *win);
 void rp_release_cache(void);
 
 /* ---- small pieces exposed for the parity tests -------------------------------------- */
-/* Host encoder used by rp_paint_chunk; returns the number of runs K (vals/lens sized n). */
+/* Host restatement of the record codec's run rule (rp_paint_chunk / rp_paint_records use the device encoder,
+ * rle_kernel; the tests hold the two byte-identical); returns the number of runs K (vals/lens sized n). */
 int rp_rle_encode(const float *v, int n, float *vals, int *lens);
 /* Evaluates the kernel's device fast_log on n floats (host in/out). */
 int rp_fast_log_device(int device, const float *in, float *out, int n);

@@ -9,6 +9,7 @@
 
 #include <emmintrin.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -124,6 +125,7 @@ struct rp_chunk {
     cudaStream_t own_stream = nullptr;   // created by the library; `stream` may be replaced by a caller's
     cudaStream_t copy_stream = nullptr;  // device->host copies of encoded records (stage driver), overlapping the next batch
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<rp_chunk **> window_refs; // the `c` fields of the windows open on this chunk (cleared by rp_chunk_free)
 };
 
 namespace {
@@ -798,6 +800,7 @@ int rp_chunk_set_stream(rp_chunk *c, void *cuda_stream)
 void rp_chunk_free(rp_chunk *c)
 {
     if (!c) return;
+    for (rp_chunk **ref : c->window_refs) *ref = nullptr; // windows left open fail with RP_EINVAL instead of dangling
     cudaSetDevice(c->device);
     for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
                       &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch, &c->nor, &c->segstate, &c->segdone,
@@ -994,6 +997,7 @@ int rp_debug_pack(int device, int N, int L, const char *hap, uint32_t *snp_major
 // ---- window repaint + distance matrices ("next" row f1) -------------------------------------------
 struct rp_window {
     rp_chunk *c = nullptr;
+    int device = 0;
     int w = 0, start = 0, end = 0;
     long long rows = 0;
     int pitch = 0, tt = 0, wpt = 0; // row layout of `top` (RepaintParams::pitch)
@@ -1031,6 +1035,7 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     for (int k = 0; k < N; k++) rowoff[k + 1] = rowoff[k] + (ib[(size_t)k * W + w] - ia[(size_t)k * W + w] + 1);
     rp_window *win = new rp_window();
     win->c = c;
+    win->device = c->device;
     win->w = w;
     win->start = c->wb[w];
     win->end = (w < W - 1) ? c->wb[w + 1] - 1 : L - 1;
@@ -1130,6 +1135,7 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
         stats->cells = win->rows; // rows of the posterior held in HBM
         stats->ms_total += now_ms() - t0;
     }
+    c->window_refs.push_back(&win->c);
     *out = win;
     return RP_OK;
 #undef RP_CUDAW
@@ -1174,6 +1180,7 @@ int rp_window_distance(rp_window *win, int snp, float *d)
     if (!win || !d) return fail(RP_EINVAL, "null argument");
     if (snp < win->start || snp > win->end) return fail(RP_EINVAL, "snp outside the window");
     rp_chunk *c = win->c;
+    if (!c) return fail(RP_EINVAL, "the window's chunk has been freed");
     RP_CUDA(cudaSetDevice(c->device));
     rp::DistanceParams P{};
     P.GT = c->GT.as<uint32_t>();
@@ -1195,7 +1202,13 @@ long long rp_window_rows(const rp_window *win) { return win ? win->rows : 0; }
 void rp_window_close(rp_window *win)
 {
     if (!win) return;
-    if (win->c) cudaSetDevice(win->c->device);
+    if (win->c) {
+        cudaSetDevice(win->c->device);
+        auto &refs = win->c->window_refs;
+        refs.erase(std::remove(refs.begin(), refs.end(), &win->c), refs.end());
+    } else {
+        cudaSetDevice(win->device);
+    }
     for (DevBuf *b : {&win->top, &win->ls, &win->rowoff, &win->rpos, &win->d, &win->ab, &win->be, &win->lsa, &win->lsb}) b->release();
     delete win;
 }
@@ -1203,9 +1216,10 @@ void rp_window_close(rp_window *win)
 } // extern "C"
 
 // ---- the whole stage (pipeline/Paint.cpp:17-108) ----------------------------------------
-// chunk files -> pinned host -> every GPU's HBM (replica, own H2D, no collective) -> paint in batches of
-// targets pulled from one counter (dynamic balance over GPUs) -> pinned host -> RLE records encoded on host
-// threads per (window, block of targets) -> appended to the W files strictly in batch order.
+// chunk files -> reader threads bit-pack into a pinned ring -> every GPU's HBM (replica, own H2D, no collective) ->
+// paint in batches of targets pulled from one counter (dynamic balance over GPUs) -> records encoded on the device
+// (rle_kernel) -> pinned pieces -> pwrite at absolute file offsets (a batch's offsets are fixed as soon as the sizes
+// of all earlier batches are published, so pieces, batches and devices reach the files in any order).
 // Device buffers, pinned staging and streams are parked in a per-device cache between calls
 // (rp_release_cache() frees them), so a process painting many chunks pays for them once.
 namespace {
@@ -1411,8 +1425,12 @@ int check_devices(const int *devices, int n_devices, std::vector<int> &devs)
     devs.clear();
     if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
     else devs.push_back(0);
-    for (int d : devs)
-        if (d < 0 || d >= ndev) return fail(RP_EINVAL, "device index out of range");
+    for (size_t i = 0; i < devs.size(); i++) {
+        if (devs[i] < 0 || devs[i] >= ndev) return fail(RP_EINVAL, "device index out of range");
+        // two workers on one device would share its parked workspace (shell chunk, pinned output ring) and corrupt the files
+        for (size_t j = 0; j < i; j++)
+            if (devs[j] == devs[i]) return fail(RP_EINVAL, "device " + std::to_string(devs[i]) + " listed twice");
+    }
     return RP_OK;
 }
 
@@ -1581,7 +1599,11 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         for (auto &ev : tev)
             if (rc == RP_OK && cudaEventCreate(&ev) != cudaSuccess) rc = fail(RP_ECUDA, "cudaEventCreate failed");
         // Drains one encoded batch: device image -> pinned pieces -> write tasks.  Runs on its own thread and the copy
-        // stream while this worker already paints the next batch into the other image buffer.
+        // stream while this worker already paints the next batch into the other image buffer.  Its time and byte counts
+        // go to accumulators of its own (the worker updates `st` concurrently through paint_device / encode_device);
+        // they are folded into `st` once the last copier has been joined.
+        double drain_ms = 0.0;
+        long long drain_bytes = 0;
         auto drain = [&, di](int b, const char *img, std::vector<long long> off) {
             if (!publish_sizes(b, off)) return;
             const std::string oerr = files_open.get();
@@ -1637,8 +1659,8 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
             }
             float ms = 0;
             cudaEventElapsedTime(&ms, tev[0], tev[1]);
-            st.ms_d2h += ms;
-            st.d2h_bytes += bytes;
+            drain_ms += ms;
+            drain_bytes += bytes;
             trace("batch copied to host", devs[di]);
         };
         std::thread copier;
@@ -1661,6 +1683,8 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
             copier = std::thread(drain, b, img, c->h_img_off);
         }
         if (copier.joinable()) copier.join();
+        st.ms_d2h += drain_ms;
+        st.d2h_bytes += drain_bytes;
         if (rc != RP_OK) {
             std::unique_lock<std::mutex> lk(mu);
             set_error(rc, g_err);

@@ -202,6 +202,12 @@ int paint(const Args &a, int chunk_index, int last_chunk = -1, std::ostream &log
         std::string t;
         while (std::getline(ss, t, ','))
             if (!t.empty()) devs.push_back(atoi(t.c_str()));
+        for (size_t i = 0; i < devs.size(); i++)
+            for (size_t j = 0; j < i; j++)
+                if (devs[i] == devs[j]) {
+                    log << "relate: --gpus lists device " << devs[i] << " twice." << std::endl;
+                    return 1;
+                }
     } else {
         int n = rp_device_count();
         for (int i = 0; i < n; i++) devs.push_back(i);
