@@ -9,6 +9,9 @@ plan of `--memory 5`, `--painting 0.001,1`.  A step = one pass of the hot path o
 tables + the forward/backward kernel for all N targets.  With N GPUs every rank paints its own chunk of that
 shape (independent chunks, no data-path collective): weak scaling, value = total painted cells / max-over-ranks time.
 
+`value` is the device-resident rate (inputs already in HBM, stepping stones left in HBM); the quantity that is
+comparable with the reference arm — chunk files in, paint files out — is `e2e`.  Both arms print the same `config`.
+
 Keys beyond the base contract:
   roofline     dominant kernel (paint_kernel): algorithmic FP32 lane-ops 7*N*U per launch (SURVEY.md 8d;
                U = visited sites, counted exactly) / mean launch time (CUDA events on the launching stream),
@@ -17,6 +20,12 @@ Keys beyond the base contract:
                chunk files in, chunk_0/paint/relate_<w>.bin out; host->device and device->host copies, RLE encoding
                and file writes inside the timed region.
   cpu_baseline the unmodified reference binary on a bounded sample of the same workload, on this box's host.
+  sharded      strong scaling of ONE chunk (BASELINE.json configs[2]: N=5000 x L=100000, --memory 50) whose targets
+               are sharded over the N GPUs by rp_paint_chunk(devices=[0..N-1]), run from rank 0 while the other
+               ranks wait on a CPU (gloo) barrier: stage wall time, per-device kernel time and roofline fraction of the
+               multi-warp kernel, md5 of the paint files (must equal the 1-device files) and a d_ij check through
+               the oracle's one-row lens.  `sharded_config4` (N=10000 x L=100000, --memory 100) is added at 8 GPUs
+               (or RELATE_BENCH_CONFIG4=1) when the box has the disk and RAM for its 40 GB of paint files.
 """
 from __future__ import annotations
 
@@ -37,6 +46,13 @@ sys.path.insert(0, ROOT)
 N_HAP, N_SNP, MEMORY_GB, PAINTING = 1000, 50000, 5.0, "0.001,1"
 WORKLOAD = f"synthetic block-Kingman N={N_HAP} x L={N_SNP}, single chunk, --memory {MEMORY_GB:g}, --painting {PAINTING}"
 METRIC, UNIT = "painted cells/s (N^2*L/s), relate --mode Paint", "cells/s"
+# identical in both arms (the driver compares them)
+CONFIG = {"workload": WORKLOAD,
+          "l2": "GPU arm: flushed between timed iterations (256 MiB device write outside the event pair); reference arm: n/a",
+          "timing": "GPU arm: torch.cuda.Event pairs on the stream the library launches on, max over ranks; "
+                    "reference arm: host wall clock around the concurrent Paint processes"}
+SHARDED = {"config3": dict(N=5000, L=100000, seed=2, memory=50.0),
+           "config4": dict(N=10000, L=100000, seed=3, memory=100.0)}
 
 
 def make_chunk(out_dir, seed, L=N_SNP):
@@ -125,7 +141,7 @@ def run_reference_arm(args, rank, world):
     from oracle import oracle
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    L_s = int(os.environ.get("RELATE_BENCH_REF_SNPS", "1500"))
+    L_s = int(os.environ.get("RELATE_BENCH_REF_SNPS", "10000"))  # W > 1 windows, start-up cost amortised as in the workload
     use_ref = oracle.have_reference()
     tmp = tempfile.mkdtemp(prefix="relate_ref_")
     try:
@@ -163,7 +179,7 @@ def run_reference_arm(args, rank, world):
                   f"generator (same --painting); {'oracle/_ref/Relate' if use_ref else 'oracle port'}")
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+                "dtype": "f64", "data": "synthetic", "config": CONFIG, "sample": sample,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample,
                                  "host_cores": cores},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -240,6 +256,104 @@ def chunk_wb(chunk):
     return chunk._wb
 
 
+def _md5_files(paths):
+    """md5 over the concatenation order-independent digest list of the files (hashed in parallel threads)."""
+    import hashlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(p):
+        h = hashlib.md5()
+        with open(p, "rb") as f:
+            while True:
+                b = f.read(1 << 24)
+                if not b:
+                    break
+                h.update(b)
+        return h.hexdigest()
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as ex:
+        digs = list(ex.map(one, paths))
+    return hashlib.md5("".join(digs).encode()).hexdigest(), sum(os.path.getsize(p) for p in paths)
+
+
+def sharded_leg(name, devices, peaks, reps=3):
+    """Strong scaling of one chunk: rp_paint_chunk(devices) from this process; see the module docstring."""
+    import numpy as np
+    from relate_b200 import capi, chunkio, synth
+    from oracle import lens, oracle
+    cfg = SHARDED[name]
+    N, L = cfg["N"], cfg["L"]
+    cells = float(N) * N * L
+    nominal = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6
+    tmp = tempfile.mkdtemp(prefix=f"relate_{name}_")
+    os.environ["RP_IO_THREADS"] = str(os.cpu_count() or 8)   # this leg owns the host: the other ranks are parked
+    try:
+        out_dir = os.path.join(tmp, "o")
+        t0 = time.perf_counter()
+        hap, bp, rpos, wb = synth.make_chunk_dir(out_dir, N, L, cfg["seed"], memory_gb=cfg["memory"])
+        W = len(wb) - 1
+        t_gen = time.perf_counter() - t0
+        need = 2.2 * W * N * N * 4
+        free_disk = shutil.disk_usage(tmp).free
+        if free_disk < need + (8 << 30):
+            return {"config": name, "skipped": f"needs {need/1e9:.0f} GB of paint files, {free_disk/1e9:.0f} GB free in {tmp}"}
+        files = [os.path.join(out_dir, "chunk_0", "paint", f"relate_{w}.bin") for w in range(W)]
+
+        def run(devs):
+            shutil.rmtree(os.path.join(out_dir, "chunk_0"), ignore_errors=True)
+            t0 = time.perf_counter()
+            st = capi.paint_chunk(out_dir, 0, PAINTING, devices=devs)
+            return time.perf_counter() - t0, st
+        runs = [run(devices) for _ in range(1 + reps)]            # first call: allocations, pinning (reported apart)
+        warm = sorted(t for t, _ in runs[1:])
+        t_stage = warm[len(warm) // 2]
+        st = runs[-1][1]
+        per_dev = capi.stage_device_stats(len(devices))
+        md5_n, nbytes = _md5_files(files)
+        res = {"config": f"{name}: synthetic block-Kingman N={N} x L={L}, one chunk, --memory {cfg['memory']:g} (W={W} windows, "
+                         f"U={st['sites']} visited sites), --painting {PAINTING}; targets sharded over {len(devices)} GPU(s) by "
+                         f"rp_paint_chunk (equal-count batches pulled from one counter), chunk files -> paint files",
+               "n_devices": len(devices), "scaling": "strong",
+               "ms_stage": 1e3 * t_stage, "ms_stage_runs": [round(1e3 * t, 1) for t, _ in runs], "ms_stage_first_call": 1e3 * runs[0][0],
+               "cells_per_s": cells / t_stage, "ms_paint_max": st["ms_paint"], "kernel_cells_per_s": cells / (st["ms_paint"] * 1e-3),
+               "kernel": f"paint_kernel<float,{st['words_per_thread']},multi> teams of {st['team_threads']} threads",
+               "kernel_frac_nominal": [7.0 * N * d["sites"] / (d["ms_paint"] * 1e-3) / nominal if d["ms_paint"] > 0 else None for d in per_dev],
+               "per_device": [{k: d[k] for k in ("n_targets", "sites", "ms_prep", "ms_paint", "ms_rle", "ms_d2h", "launches")} for d in per_dev],
+               "breakdown_ms": {k: st[k] for k in ("ms_load", "ms_h2d", "ms_prep", "ms_paint", "ms_rle", "ms_d2h", "ms_write", "ms_total")},
+               "paint_file_bytes": nbytes, "files_md5": md5_n, "ms_generate_input": 1e3 * t_gen}
+        if len(devices) > 1:                                       # the N-device files must be the 1-device files
+            t1, st1 = run(devices[:1])
+            md5_1, _ = _md5_files(files)
+            res["files_md5_1gpu"] = md5_1
+            res["files_identical_to_1gpu"] = (md5_1 == md5_n)
+            res["ms_stage_1gpu_same_box"] = 1e3 * t1
+        # d_ij through the oracle's one-row lens (oracle/lens.py): GPU paint files vs the fp64 oracle's stepping stones
+        r = chunkio.r_from_rpos(rpos)
+        theta = float(np.float32(PAINTING.split(",")[0]))
+        worst, rows_checked, checked = 0.0, 0, []
+        for w in sorted({0, W // 2, W - 1}):
+            idx = lens.paint_file_index(files[w], N)
+            lo, hi = int(wb[w]), (int(wb[w + 1]) - 1 if w < W - 1 else L - 1)
+            snps = sorted({lo, lo + (hi - lo) // 3, lo + 2 * (hi - lo) // 3, hi})
+            for n in (3 + 37 * w) % N, (N // 2 + 11 * w) % N:
+                a, sa, la, b, sb, lb = lens.read_target_records(files[w], N, n, idx)
+                got = lens.dij_rows(hap, r, rpos, wb, theta, w, n, snps, a, b, sa, sb, la, lb)
+                o = oracle.paint_targets(hap, r, wb, theta, n, n + 1)
+                assert sa == o["site_begin"][0, w] and sb == o["site_end"][0, w], "boundary SNPs differ from the oracle's"
+                want = lens.dij_rows(hap, r, rpos, wb, theta, w, n, snps, lens.collapse(o["alpha"][0, w]), lens.collapse(o["beta"][0, w]),
+                                     sa, sb, o["ls_alpha"][0, w], o["ls_beta"][0, w])
+                worst = max(worst, float(np.abs(got.astype(np.float64) - want).max()))
+                rows_checked += len(snps)
+            checked.append(w)
+        tol = 1e-4 * abs(np.log(theta / (1 - theta)))
+        res["dij"] = {"windows": checked, "rows": rows_checked, "worst_abs_diff": worst, "tolerance": float(tol), "ok": bool(worst <= tol),
+                      "lens": "oracle/lens.py: ro_repaint_section + ro_matrix_row (pinned bit-identical to oracle/_ref/dlens) on the "
+                              "decoded GPU records vs the fp64 oracle's stepping stones after the codec's collapse"}
+        return res
+    finally:
+        os.environ.pop("RP_IO_THREADS", None)
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -248,6 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the strong-scaling leg (one config-3 chunk over all GPUs)")
     ap.add_argument("--words-per-thread", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     args = ap.parse_args()
@@ -274,9 +389,11 @@ def main():
     os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")   # ranks park here (no spinning GPU kernel) during rank 0's sharded leg
 
     tmp = tempfile.mkdtemp(prefix=f"relate_bench_r{rank}_")
     try:
@@ -348,6 +465,26 @@ def main():
         (t_max, e2e_max, kern_max) = sharding.allreduce_scalars([my_ms, my_e2e, kernel_ms], "max", device=dev)
         (u_sum,) = sharding.allreduce_scalars([float(U)], "sum", device=dev)
 
+        # ---- strong scaling of one chunk over all GPUs of the job (rank 0 drives every device) ----
+        sharded = {}
+        if not args.no_sharded:
+            chunk.set_stream(None)
+            torch.cuda.synchronize(dev)
+            if cpu_group is not None:
+                dist.barrier(group=cpu_group)            # every rank's own legs are done: the GPUs are idle
+            if rank == 0:
+                peaks0, _ = measured_peaks()
+                legs = ["config3"]
+                if world >= 8 or os.environ.get("RELATE_BENCH_CONFIG4") == "1":
+                    legs.append("config4")
+                for name in legs:
+                    try:
+                        sharded[name] = sharded_leg(name, list(range(world)), peaks0)
+                    except Exception as e:  # the headline line must survive a failure here
+                        sharded[name] = {"config": name, "error": f"{type(e).__name__}: {e}"}
+            if cpu_group is not None:
+                dist.barrier(group=cpu_group)
+
         if rank == 0:
             peaks, peak_src = measured_peaks()
             mix, scalar = capi.peak_fp32(local_rank)
@@ -359,10 +496,9 @@ def main():
                 "metric": METRIC, "value": world * cells_per_step / (t_max * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD + f" (W={W} windows, U={U} visited sites); one such chunk per GPU",
-                           "l2": "flushed between timed iterations (256 MiB device write outside the event pair)",
-                           "timing": "torch.cuda.Event pairs on the stream the library launches on; max over ranks",
-                           "team_threads": st["team_threads"], "words_per_thread": st["words_per_thread"], "ctas": st["ctas"]},
+                "config": CONFIG,
+                "run": {"windows": W, "visited_sites": U, "chunks": "one such chunk per GPU (weak scaling)",
+                        "team_threads": st["team_threads"], "words_per_thread": st["words_per_thread"], "ctas": st["ctas"]},
                 "roofline": {"bound": "fp32", "achieved": achieved / 1e12, "peak": mix / 1e12, "unit": "TFLOP/s",
                              "frac": achieved / mix, "traffic": (ncu_traffic() or (None, None))[0],
                              "traffic_source": (ncu_traffic() or (None, None))[1],
@@ -382,6 +518,10 @@ def main():
                 "clocks": clocks,
                 "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             }
+            if "config3" in sharded:
+                line["sharded"] = sharded["config3"]
+            if "config4" in sharded:
+                line["sharded_config4"] = sharded["config4"]
             if world == 1:
                 line["window_repaint"] = window_repaint_measure(chunk, rpos, W, peaks)
             if world == 1 and not args.no_cpu_baseline:

@@ -157,6 +157,12 @@ int rp_paint_from_host(int device, int N, int L, const char *hap, const double *
 int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
                    int n_devices, unsigned flags, rp_stats *stats);
 
+/* Statistics of device i (position in `devices`) of this process's last rp_paint_chunk call: its own kernel, prep,
+ * encoder and copy times and the targets / visited sites it painted (rp_stats of the call itself holds the maximum
+ * over devices of the times and the sums of the counts).  Host threads used for file I/O: RP_IO_THREADS in the
+ * environment, else the core count divided by LOCAL_WORLD_SIZE (one process per GPU launchers set it) when present, else all cores. */
+int rp_stage_device_stats(int i, rp_stats *out);
+
 /* Several chunks of one data set: chunks first_chunk..last_chunk are distributed over the
  * devices as whole chunks, largest first, one host thread per device, no collective.  What a maintainer would call
  * instead of the per-chunk loop of RelateParallel.sh:221-225 when several GPUs are present. */

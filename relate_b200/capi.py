@@ -71,6 +71,7 @@ SYMBOLS = {
                                      C.POINTER(RpTune), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(RpStats)]),
     "rp_paint_chunk": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, _P, C.c_int, C.c_uint, C.POINTER(RpStats)]),
     "rp_paint_chunks": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p, _P, C.c_int, C.c_uint, C.POINTER(RpStats)]),
+    "rp_stage_device_stats": (C.c_int, [C.c_int, C.POINTER(RpStats)]),
     "rp_release_cache": (None, []),
     "rp_window_open": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(RpStats)]),
     "rp_window_open_resident": (C.c_int, [_P, C.c_int, _P, C.POINTER(_P), C.POINTER(RpStats)]),
@@ -307,6 +308,16 @@ def paint_chunk(out_dir: str, chunk_index: int, painting: str | None = None, dev
     check(lib().rp_paint_chunk(out_dir.encode(), chunk_index, painting.encode() if painting is not None else None,
                                _ptr(dev), n, RP_FP64 if fp64 else 0, C.byref(st)))
     return st.as_dict()
+
+
+def stage_device_stats(n_devices: int) -> list:
+    """Per-device statistics of the last :func:`paint_chunk` call of this process."""
+    out = []
+    for i in range(n_devices):
+        st = RpStats()
+        check(lib().rp_stage_device_stats(i, C.byref(st)))
+        out.append(st.as_dict())
+    return out
 
 
 def paint_chunks(out_dir: str, first_chunk: int, last_chunk: int, painting: str | None = None, devices=None,

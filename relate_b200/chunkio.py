@@ -132,6 +132,7 @@ class Chunk:
     wb: np.ndarray      # int32 [W+1]
     hap: np.ndarray     # uint8 [L, N] chars
     r: np.ndarray       # float64 [L]
+    rpos: np.ndarray | None = None  # float64 [L+1]
 
     @property
     def W(self) -> int:
@@ -151,7 +152,11 @@ def read_chunk(out_dir: str, chunk: int = 0) -> Chunk:
         (n,) = struct.unpack("<I", f.read(4))
         assert n == L
         r = np.frombuffer(f.read(8 * L), dtype="<f8").copy()
-    return Chunk(N, L, wb, hap, r)
+    with open(base + ".rpos", "rb") as f:
+        (n,) = struct.unpack("<I", f.read(4))
+        assert n == L + 1
+        rpos = np.frombuffer(f.read(8 * (L + 1)), dtype="<f8").copy()
+    return Chunk(N, L, wb, hap, r, rpos)
 
 
 @dataclass

@@ -1384,6 +1384,18 @@ class WritePool {
 
 std::mutex g_stage_mu; // rp_paint_chunk calls are serialised (they share the cache)
 std::map<int, DeviceWorkspace> g_ws;
+std::vector<rp_stats> g_last_dstats; // per-device statistics of the last rp_paint_chunk call (rp_stage_device_stats)
+
+// Host threads this process may use for file I/O (chunk readers + paint-file writers).  Several processes painting at
+// once on one host (one rank per GPU) must share the cores: RP_IO_THREADS sets the budget; otherwise it is the core
+// count divided by LOCAL_WORLD_SIZE (set by torchrun) when that is present.
+unsigned io_thread_budget()
+{
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (const char *e = getenv("RP_IO_THREADS")) return (unsigned)std::max(1, atoi(e));
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) return std::max(2u, hw / (unsigned)std::max(1, atoi(e)));
+    return hw;
+}
 
 template <typename F> void parallel_for(int n, int nthreads, F f)
 {
@@ -1437,7 +1449,7 @@ int check_devices(const int *devices, int n_devices, std::vector<int> &devs)
 // One chunk on the given devices.  The caller holds g_stage_mu and has created the g_ws entries of `devs`; concurrent
 // calls must use disjoint device sets (rp_paint_chunks: one device each).
 int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting, const std::vector<int> &devs, unsigned flags,
-                      rp_stats *stats)
+                      rp_stats *stats, std::vector<rp_stats> *per_device = nullptr)
 {
     const double t0 = now_ms();
 
@@ -1452,7 +1464,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         if (!err.empty()) return fail(RP_EIO, err);
     }
     const size_t nchar = (size_t)hc.L * hc.N;
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned hw = io_thread_budget();
     HapFeed feed;
     const size_t ring_cap = (size_t)(getenv("RP_RING_KB") ? atoi(getenv("RP_RING_KB")) : 65536) << 10; // tests shrink it
     // a slice = whole SNP rows worth about RP_SLICE_KB of genotype chars on disk; in the ring it is 1/8 of that
@@ -1482,7 +1494,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     double t_loaded = t0;
     std::vector<std::thread> readers;
     const unsigned want_readers = getenv("RP_READERS") ? (unsigned)atoi(getenv("RP_READERS")) : 8u;
-    const int nread = (int)std::max(1u, std::min<unsigned>({want_readers, hw, (unsigned)feed.nslots}));
+    const int nread = (int)std::max(1u, std::min<unsigned>({want_readers, std::max(1u, hw / 2), (unsigned)feed.nslots}));
     readers_left = nread;
     for (int t = 0; t < nread; t++)
         readers.emplace_back([&]() {
@@ -1573,7 +1585,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         cv.wait(lk, [&] { return upto > b || first_rc != RP_OK; });
         return first_rc == RP_OK;
     };
-    WritePool pool((int)std::max(4u, std::min(16u, hw)));
+    WritePool pool((int)std::max(2u, std::min(16u, hw)));
     std::vector<std::unique_ptr<OutRing>> rings(devs.size());
 
     auto worker = [&](int di) {
@@ -1715,6 +1727,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         if (first_rc == RP_OK && !err.empty()) return fail(RP_EIO, err);
     }
     if (first_rc != RP_OK) return fail(first_rc, first_err);
+    if (per_device) *per_device = dstats;
     if (stats) {
         memset(stats, 0, sizeof *stats);
         for (const rp_stats &s : dstats) {
@@ -1750,7 +1763,16 @@ extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *
     RP_TRY(check_devices(devices, n_devices, devs));
     std::lock_guard<std::mutex> stage_lock(g_stage_mu);
     for (int d : devs) g_ws[d];
-    return paint_chunk_stage(out_dir, chunk_index, painting, devs, flags, stats);
+    return paint_chunk_stage(out_dir, chunk_index, painting, devs, flags, stats, &g_last_dstats);
+}
+
+extern "C" int rp_stage_device_stats(int i, rp_stats *out)
+{
+    if (!out) return fail(RP_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    if (i < 0 || i >= (int)g_last_dstats.size()) return fail(RP_EINVAL, "no such device in the last rp_paint_chunk call");
+    *out = g_last_dstats[i];
+    return RP_OK;
 }
 
 // Chunks first_chunk..last_chunk, whole chunks per device, largest first: one host thread per device

@@ -398,17 +398,16 @@ def test_paint_chunk_files_vs_reference_golden(tmp_path, name, painting, ref_dir
         ref = os.path.join(GOLDEN, name, ref_dir, f"relate_{w}.bin")
         # decoded values: the codec merges within 1e-3 of the run head, so allow 1e-3 + 1e-4
         flips += decoded_close(mine, ref, ch.N, 1.1e-3)
-    assert flips <= max(2, ch.N * ch.W // 50)
+    print(f"{name}/{ref_dir}: fp32 run-structure flips {flips} of {2 * ch.N * ch.W} vectors")
+    # observed on B200: 0 flips on all three fixtures (survey probe D7: 1 in 6000 at N=1000); allow that rate + 2
+    assert flips <= 2 + (2 * ch.N * ch.W) // 3000
     # fp64 verification mode: the reference's bytes
     shutil.rmtree(os.path.join(d, "chunk_0"))
     capi.paint_chunk(d, 0, painting, fp64=True)
     same = [filecmp.cmp(os.path.join(d, "chunk_0", "paint", f"relate_{w}.bin"), os.path.join(GOLDEN, name, ref_dir, f"relate_{w}.bin"),
                         shallow=False) for w in range(ch.W)]
-    if not all(same):  # at most isolated last-bit differences
-        for w in range(ch.W):
-            decoded_close(os.path.join(d, "chunk_0", "paint", f"relate_{w}.bin"), os.path.join(GOLDEN, name, ref_dir, f"relate_{w}.bin"),
-                          ch.N, 1.001e-3)
-    assert sum(same) >= ch.W - 1
+    print(f"{name}/{ref_dir}: fp64 mode byte-identical files {sum(same)} of {ch.W}")
+    assert all(same), [w for w in range(ch.W) if not same[w]]
 
 
 def test_cli_paint_then_reference_buildtopology_gives_identical_trees(tmp_path, have_ref):
@@ -756,7 +755,8 @@ def test_config5_shape_multichunk_makechunks_then_paint_chunks(tmp_path):
         for w in range(ch.W):
             flips += decoded_close(os.path.join(d, "o", f"chunk_{c}", "paint", f"relate_{w}.bin"),
                                    os.path.join(d, "ora", f"chunk_{c}", "paint", f"relate_{w}.bin"), N, 1.1e-3)
-        assert flips <= max(2, N * ch.W // 50)
+        print(f"config-5 shape, chunk {c}: fp32 run-structure flips {flips} of {2 * N * ch.W} vectors")
+        assert flips <= 2 + (2 * N * ch.W) // 3000
     # fp64 verification mode through the API, chunks spread over the devices again
     for c in range(n):
         shutil.rmtree(os.path.join(d, "o", f"chunk_{c}"))
@@ -766,7 +766,7 @@ def test_config5_shape_multichunk_makechunks_then_paint_chunks(tmp_path):
         W = chunkio.read_chunk(os.path.join(d, "o"), c).W
         same = [filecmp.cmp(os.path.join(d, "o", f"chunk_{c}", "paint", f"relate_{w}.bin"),
                             os.path.join(d, "ora", f"chunk_{c}", "paint", f"relate_{w}.bin"), shallow=False) for w in range(W)]
-        assert sum(same) >= W - 1, (c, same)
+        assert all(same), (c, same)
 
 
 def test_cli_mode_all_with_paint_ahead_equals_reference_all(tmp_path, have_ref):

@@ -1,0 +1,149 @@
+"""Parity at BASELINE.json's sizes (VERDICT r01 "parity-at-size gaps"), all through the reference's own consumer code:
+
+  * the BuildTopology gate of BASELINE.md section 4 at N = 1000: the unmodified reference's BuildTopology on GPU-painted
+    vs reference-painted stepping stones must build trees at the same SNPs with the same clade sets;
+  * d_ij through the unmodified reference's GetMatrix (oracle/_ref/dlens) on the FULL config 2 chunk, every window;
+  * alpha / beta of 64 targets at config 4's shape (N = 10 000 x L = 100 000) against the fp64 oracle.
+
+The reference runs are CPU minutes: they are started in the background when the module is first used and the tests
+collect them, so the whole file costs about three minutes of wall time on the GPU box.
+"""
+import os
+import shutil
+import subprocess
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import oracle
+from relate_b200 import capi, chunkio, synth
+from test_paint_gpu import clade_sets, read_anc_bin, read_dlens
+
+pytestmark = pytest.mark.gpu
+PAINTING = "0.001,1"
+THETA = float(np.float32(0.001))
+DTOL = 1e-4 * abs(np.log(THETA / (1 - THETA)))  # 6.9e-4 absolute (hard part 2)
+
+
+def _paint_ref_bg(cwd):
+    return subprocess.Popen([oracle.REF_RELATE, "--mode", "Paint", "--chunk_index", "0", "-o", "o", "--painting", PAINTING],
+                            cwd=cwd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+@pytest.fixture(scope="module")
+def ref_runs():
+    """Reference Paint of (i) N=1000 x L=9000 --memory 1.5 and (ii) the full config 2 chunk, started in the background."""
+    if not oracle.have_reference() or not os.access(oracle.REF_DLENS, os.X_OK):
+        pytest.skip("oracle/_ref did not travel to this box")
+    root = tempfile.mkdtemp(prefix="relate_atsize_")
+    jobs = {}
+    for tag, (N, L, seed, mem) in {"bt": (1000, 9000, 5, 1.5), "c2": (1000, 50000, 1, 5.0)}.items():
+        for side in ("ref", "gpu"):
+            d = os.path.join(root, tag, side)
+            os.makedirs(d)
+            hap, bp, rpos, wb = synth.make_chunk_dir(os.path.join(d, "o"), N, L, seed, memory_gb=mem)
+        jobs[tag] = dict(dir=os.path.join(root, tag), wb=wb, N=N, L=L, proc=_paint_ref_bg(os.path.join(root, tag, "ref")))
+    yield jobs
+    for j in jobs.values():
+        if j["proc"].poll() is None:
+            j["proc"].kill()
+    shutil.rmtree(root, ignore_errors=True)
+
+
+def test_buildtopology_gate_at_n1000(ref_runs):
+    """same tree positions and same clade sets per tree at N = 1000 (survey probe D7: 103/103 trees, a
+    few differing in internal-node numbering only).  One 3000-SNP window in the middle of the chunk (it needs both a
+    non-trivial alpha and a non-trivial beta stepping stone), reference BuildTopology --seed 1 on both paint directories."""
+    j = ref_runs["bt"]
+    W, N = len(j["wb"]) - 1, j["N"]
+    assert W >= 3
+    st = capi.paint_chunk(os.path.join(j["dir"], "gpu", "o"), 0, PAINTING)
+    assert st["n_targets"] == N
+    assert j["proc"].wait(timeout=600) == 0
+    bt = [oracle.REF_RELATE, "--mode", "BuildTopology", "--chunk_index", "0", "--first_section", "1", "--last_section", "1",
+          "-o", "o", "--painting", PAINTING, "--seed", "1"]
+    ps = [subprocess.Popen(bt, cwd=os.path.join(j["dir"], side), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+          for side in ("ref", "gpu")]
+    for p in ps:
+        _, err = p.communicate(timeout=900)
+        assert p.returncode == 0, err[-2000:]
+    ta = read_anc_bin(os.path.join(j["dir"], "ref", "o", "chunk_0", "o_1.anc"))
+    tb = read_anc_bin(os.path.join(j["dir"], "gpu", "o", "chunk_0", "o_1.anc"))
+    assert [pos for pos, _ in ta] == [pos for pos, _ in tb], "trees at different SNPs"
+    nsame = nclades = nshared = 0
+    for (_, pa), (_, pb) in zip(ta, tb):
+        ca, cb = clade_sets(pa, N), clade_sets(pb, N)
+        nsame += ca == cb
+        nclades += len(ca)
+        nshared += len(ca & cb)
+    same_bytes = open(os.path.join(j["dir"], "ref", "o", "chunk_0", "o_1.anc"), "rb").read() == \
+        open(os.path.join(j["dir"], "gpu", "o", "chunk_0", "o_1.anc"), "rb").read()
+    print(f"N=1000 BuildTopology gate: {len(ta)} trees at identical positions, {nsame} with identical clade sets, "
+          f"{nshared}/{nclades} clades shared, .anc byte-identical: {same_bytes}")
+    assert len(ta) >= 50
+    # MinMatch treats distances within 1.38 as ties (tree_builder.cpp:43), so a 1e-6 perturbation may resolve a tie
+    # differently in a few trees; the gate is the survey's: (almost) every tree with the same clade set
+    assert nsame >= 0.97 * len(ta) and nshared >= 0.999 * nclades
+
+
+def test_dij_through_reference_getmatrix_on_full_config2(ref_runs):
+    """Every window of the full config 2 chunk (N=1000 x L=50 000, --memory 5): oracle/_ref/dlens (the unmodified
+    reference's GetTopologyWithRepaint + GetMatrix) on reference-painted vs GPU-painted files, >= 5 SNPs per window."""
+    j = ref_runs["c2"]
+    W, N = len(j["wb"]) - 1, j["N"]
+    assert W >= 5
+    capi.paint_chunk(os.path.join(j["dir"], "gpu", "o"), 0, PAINTING)
+    assert j["proc"].wait(timeout=900) == 0
+
+    def lens(args):
+        side, sec = args
+        out = os.path.join(j["dir"], f"d_{side}_{sec}.bin")
+        span = int(j["wb"][sec + 1] - j["wb"][sec])
+        subprocess.run([oracle.REF_DLENS, "o", "0", str(sec), str(max(1, span // 5)), PAINTING, out],
+                       cwd=os.path.join(j["dir"], side), check=True)
+        return out
+    work = [(side, sec) for sec in range(W) for side in ("ref", "gpu")]
+    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 2)) as ex:  # ~5 GB of posterior per process
+        outs = dict(zip(work, ex.map(lens, work)))
+    worst, nmat, nbig = 0.0, 0, 0
+    for sec in range(W):
+        a, b = read_dlens(outs[("ref", sec)]), read_dlens(outs[("gpu", sec)])
+        assert a.keys() == b.keys() and len(a) >= 5
+        for snp in a:
+            d = np.abs(a[snp].astype(np.float64) - b[snp])
+            worst = max(worst, float(d.max()))
+            nbig += int((d > 1e-4 * np.maximum(a[snp], 1.0)).sum())
+            nmat += 1
+        os.remove(outs[("ref", sec)])
+        os.remove(outs[("gpu", sec)])
+    print(f"config 2 d_ij lens: {nmat} matrices over {W} windows, worst |dd| = {worst:.3e} (gate {DTOL:.2e}), "
+          f"{nbig} of {nmat * N * N} entries beyond 1e-4*max(d,1)")
+    assert worst <= DTOL
+
+
+def test_config4_shape_64_targets_vs_oracle():
+    """alpha / beta / log-scales / boundary SNPs of 64 targets spread over a config-4-shaped chunk (N = 10 000 x
+    L = 100 000, --memory 100 window plan) against the fp64 oracle (one second of CPU per target, run on all cores)."""
+    N, L = 10000, 100000
+    hap, bp = synth.block_kingman(N, L, 3)
+    r = chunkio.r_from_rpos(chunkio.uniform_map_rpos(bp))
+    wb = chunkio.window_boundaries(hap, 100.0)
+    ks = [int(k) for k in np.linspace(0, N - 1, 64).astype(int)]
+    oracle.lib()
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 2)) as ex:
+        futs = {k: ex.submit(oracle.paint_targets, hap, r, wb, THETA, k, k + 1) for k in ks}
+        worst_a = worst_b = worst_ls = 0.0
+        with capi.DeviceChunk.from_arrays(hap, r, wb, THETA) as c:
+            for k in ks:
+                g = c.paint_targets(k, k + 1)
+                o = futs[k].result()
+                assert np.array_equal(g.site_begin, o["site_begin"]) and np.array_equal(g.site_end, o["site_end"])
+                worst_a = max(worst_a, rel_err(g.alpha, o["alpha"]))
+                worst_b = max(worst_b, rel_err(g.beta, o["beta"]))
+                worst_ls = max(worst_ls, float(np.abs(g.ls_alpha.astype(np.float64) - o["ls_alpha"]).max()),
+                               float(np.abs(g.ls_beta.astype(np.float64) - o["ls_beta"]).max()))
+    print(f"config 4 shape, 64 targets: worst relative error alpha {worst_a:.2e}, beta {worst_b:.2e}; log-scales {worst_ls:.2e}")
+    assert worst_a <= 1e-4 and worst_b <= 1e-4 and worst_ls <= 5e-3

@@ -40,3 +40,24 @@ def test_oracle_distances_match_fresh_reference_run(tmp_path, have_ref):
         assert filecmp.cmp(a, b, shallow=False)
     dm = oracle.read_distances(b)
     assert len(dm) >= 3 and all(m.shape == (N, N) and np.all(np.diag(m) == 0) for m in dm.values())
+
+
+def test_row_lens_reproduces_reference_golden_rows(tmp_path):
+    """oracle/lens.py looks at one target row at a time (the at-size parity checks use it where the whole-window
+    reference run would need the --memory budget in RAM): rows must be bit-identical to the matrices that the
+    unmodified reference's GetMatrix wrote (dlens fixtures)."""
+    from oracle import lens
+    from relate_b200 import chunkio
+    d = unpack_golden("synth_n96", str(tmp_path))
+    ch = chunkio.read_chunk(d, 0)
+    theta = float(np.float32(0.001))
+    for sec in (1, 3):
+        want = oracle.read_distances(os.path.join(GOLDEN, "synth_n96", "dlens_ref", f"d_{sec}.bin.gz"))
+        pf = os.path.join(GOLDEN, "synth_n96", "paint_ref", f"relate_{sec}.bin")
+        idx = lens.paint_file_index(pf, ch.N)
+        snps = sorted(want)
+        for n in (0, 17, ch.N - 1):
+            a, sa, la, b, sb, lb = lens.read_target_records(pf, ch.N, n, idx)
+            rows = lens.dij_rows(ch.hap, ch.r, ch.rpos, ch.wb, theta, sec, n, snps, a, b, sa, sb, la, lb)
+            for i, snp in enumerate(snps):
+                assert np.array_equal(rows[i], want[snp][n]), (sec, n, snp)
