@@ -329,7 +329,7 @@ def sharded_leg(name, devices, peaks, reps=3):
         # d_ij through the oracle's one-row lens (oracle/lens.py): GPU paint files vs the fp64 oracle's stepping stones
         r = chunkio.r_from_rpos(rpos)
         theta = float(np.float32(PAINTING.split(",")[0]))
-        worst, rows_checked, checked = 0.0, 0, []
+        worst, rows_checked, checked, ndiff, nent, worst_vec = 0.0, 0, [], 0, 0, 0.0
         for w in sorted({0, W // 2, W - 1}):
             idx = lens.paint_file_index(files[w], N)
             lo, hi = int(wb[w]), (int(wb[w + 1]) - 1 if w < W - 1 else L - 1)
@@ -339,13 +339,19 @@ def sharded_leg(name, devices, peaks, reps=3):
                 got = lens.dij_rows(hap, r, rpos, wb, theta, w, n, snps, a, b, sa, sb, la, lb)
                 o = oracle.paint_targets(hap, r, wb, theta, n, n + 1)
                 assert sa == o["site_begin"][0, w] and sb == o["site_end"][0, w], "boundary SNPs differ from the oracle's"
-                want = lens.dij_rows(hap, r, rpos, wb, theta, w, n, snps, lens.collapse(o["alpha"][0, w]), lens.collapse(o["beta"][0, w]),
-                                     sa, sb, o["ls_alpha"][0, w], o["ls_beta"][0, w])
+                oa, ob = lens.collapse(o["alpha"][0, w]), lens.collapse(o["beta"][0, w])
+                want = lens.dij_rows(hap, r, rpos, wb, theta, w, n, snps, oa, ob, sa, sb, o["ls_alpha"][0, w], o["ls_beta"][0, w])
                 worst = max(worst, float(np.abs(got.astype(np.float64) - want).max()))
+                ndiff += int((got != want).sum())
+                nent += got.size
+                for x, y in ((a, oa), (b, ob)):   # the decoded stepping stones themselves (codec tolerance 1e-3)
+                    nz = y != 0
+                    worst_vec = max(worst_vec, float((np.abs(x[nz].astype(np.float64) - y[nz]) / y[nz]).max()))
                 rows_checked += len(snps)
             checked.append(w)
         tol = 1e-4 * abs(np.log(theta / (1 - theta)))
         res["dij"] = {"windows": checked, "rows": rows_checked, "worst_abs_diff": worst, "tolerance": float(tol), "ok": bool(worst <= tol),
+                      "entries": nent, "entries_not_bit_identical": ndiff, "worst_rel_diff_decoded_stepping_stones": worst_vec,
                       "lens": "oracle/lens.py: ro_repaint_section + ro_matrix_row (pinned bit-identical to oracle/_ref/dlens) on the "
                               "decoded GPU records vs the fp64 oracle's stepping stones after the codec's collapse"}
         return res
