@@ -76,7 +76,6 @@ typedef struct rp_tune { /* all zero = automatic */
     int ctas_per_sm;      /* persistent CTAs per SM                                          */
     int reserved[6];      /* [1]: chain segments of the paint kernel (0 = automatic, 1 = whole chains as jobs, n = every
                            * chain cut into n segments parked in HBM in between: load balance, results bit-identical);
-                           * [2]: 1 = single-warp teams run the plain painter instead of the look-ahead one (A/B measurements);
                            * [3]: force teams of that many CTAs (thread-block cluster); others 0                    */
 } rp_tune;
 

@@ -159,14 +159,11 @@ class DeviceChunk:
                                   RP_FP64 if fp64 else 0, C.byref(h)))
         return cls(h)
 
-    def set_tune(self, words_per_thread: int = 0, ctas_per_sm: int = 0, cluster: int = 0, segments: int = 0,
-                 plain_kernel: bool = False) -> None:
+    def set_tune(self, words_per_thread: int = 0, ctas_per_sm: int = 0, cluster: int = 0, segments: int = 0) -> None:
         """cluster > 1 forces teams of that many CTAs (thread-block cluster) where a single CTA would do (tests);
-        segments: 0 = automatic, 1 = whole chains as jobs, n = every chain cut into n parked segments;
-        plain_kernel: single-warp teams use the plain painter instead of the look-ahead one (A/B measurements)."""
+        segments: 0 = automatic, 1 = whole chains as jobs, n = every chain cut into n parked segments."""
         t = RpTune(words_per_thread, ctas_per_sm)
         t.reserved[1] = segments
-        t.reserved[2] = 1 if plain_kernel else 0
         t.reserved[3] = cluster
         check(lib().rp_chunk_set_tune(self._h, C.byref(t)))
 

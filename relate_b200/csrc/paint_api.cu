@@ -111,7 +111,7 @@ struct rp_chunk {
     std::vector<int> wb;
     rp_tune tune{};
     // resident
-    DevBuf G, GT, r, Phi, Plo, wbdev, chars, cnt; // cnt: derived alleles per SNP (the look-ahead painter's table entries)
+    DevBuf G, GT, r, Phi, Plo, wbdev, chars;
     // per-paint work buffers (grown on demand, reused)
     DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch, nor, segstate, segdone;
     // record encoder (device RLE): run counts, byte offsets, the W file images of the last batch
@@ -129,8 +129,6 @@ struct rp_chunk {
 };
 
 namespace {
-
-constexpr size_t kEntPad = 8; // table entries of padding in front of and behind the site tables
 
 struct LaunchPlan {
     int wpt = 1;
@@ -212,39 +210,6 @@ int launch_paint_t(rp_chunk *c, rp::PaintParams &P, int threads, int &ctas)
     return RP_OK;
 }
 
-// Look-ahead painter (paint_look_kernel): single-warp fp32 teams, multipliers <= 1.  Same grid, segments and ready queue.
-template <int WPT> int launch_look_t(rp_chunk *c, rp::PaintParams &P, int &ctas)
-{
-    auto kern = rp::paint_look_kernel<WPT>;
-    int occ = 0;
-    RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, 0));
-    if (occ < 1) return fail(RP_ECUDA, "paint kernel does not fit on an SM");
-    if (c->tune.ctas_per_sm > 0) occ = std::min(occ, c->tune.ctas_per_sm);
-    const int slots = std::max(1, occ * c->sm_count / 2);
-    int nseg = 1;
-    const int want = c->tune.reserved[1];
-    if (want > 0) nseg = want;
-    else if (2 * P.nt > slots)
-        nseg = (int)std::max<long long>(1, std::min<long long>(8, c->last_sites / std::max(1, P.nt) / 512));
-    P.nseg = nseg;
-    P.segready = nullptr;
-    P.segstate = nullptr;
-    P.segstride = 0;
-    if (nseg > 1) {
-        P.segstride = (((size_t)32 * WPT * 32 + 32) * sizeof(float) + 64 + 15) & ~(size_t)15;
-        RP_TRY(c->segstate.ensure(2 * (size_t)P.nt * P.segstride));
-        const size_t rq = 2 * (size_t)P.nt * (nseg - 1) * 4;
-        RP_TRY(c->segdone.ensure(rq));
-        RP_CUDA(cudaMemsetAsync(c->segdone.p, 0, rq, c->stream));
-        P.segready = c->segdone.as<int>();
-        P.segstate = c->segstate.as<char>();
-    }
-    ctas = 2 * (int)std::min<long long>((long long)P.nt * nseg, slots);
-    kern<<<ctas, 32, 0, c->stream>>>(P);
-    RP_CUDA(cudaGetLastError());
-    return RP_OK;
-}
-
 // grid size is needed before the launch to size the fp64 scratch; compute it the same way
 template <typename T, int WPT, bool MULTI> int grid_for(const rp_chunk *c, int nt, int threads, int &ctas)
 {
@@ -293,10 +258,6 @@ int launch_paint(rp_chunk *c, rp::PaintParams &P, const LaunchPlan &lp, DevBuf &
         RP_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
         return RP_OK;
     }
-    // single-warp teams with multipliers <= 1 (theta <= 0.47; the default is 0.001): the look-ahead painter.
-    // tune.reserved[2] == 1 selects the plain kernel (A/B measurements, tests).
-    if (!lp.multi && P.cf.tau <= 0.9f && c->tune.reserved[2] != 1)
-        return lp.wpt == 1 ? launch_look_t<1>(c, P, ctas) : launch_look_t<2>(c, P, ctas);
     if (lp.wpt == 1)
         return lp.multi ? launch_paint_t<float, 1, true>(c, P, lp.threads, ctas)
                         : launch_paint_t<float, 1, false>(c, P, lp.threads, ctas);
@@ -443,7 +404,6 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
     RP_TRYB(c->Phi.ensure((size_t)(L + 1) * 8));
     RP_TRYB(c->Plo.ensure((size_t)(L + 1) * 8));
     RP_TRYB(c->wbdev.ensure((size_t)n_wb * 4));
-    RP_TRYB(c->cnt.ensure((size_t)L * 4));
     RP_CUDAB(cudaEventRecord(c->ev[0], c->stream));
     std::vector<double> hi, lo;
     dd_prefix(r, L, hi, lo);
@@ -479,7 +439,6 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
         dim3 grid((N + 31) / 32, (c->lw + 31) / 32), block(32, 32);
         rp::transpose_bits_kernel<<<grid, block, 0, c->stream>>>(c->G.as<uint32_t>(), c->wps, N, L,
                                                                  c->GT.as<uint32_t>(), c->lw);
-        rp::count_derived_kernel<<<(unsigned)((L + 7) / 8), 256, 0, c->stream>>>(c->G.as<uint32_t>(), c->wps, N, L, c->cnt.as<int>());
         RP_CUDAB(cudaGetLastError());
     }
     RP_CUDAB(cudaEventRecord(c->ev[2], c->stream));
@@ -492,7 +451,7 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
         st->ms_h2d += a;
         st->ms_prep += b;
         st->h2d_bytes += (feed ? (long long)L * c->wps * 4 : (long long)nchar) + (long long)L * 8 + (long long)(L + 1) * 16 + (long long)n_wb * 4;
-        st->launches += feed ? 2 : 3;
+        st->launches += feed ? 1 : 2;
         st->ms_total += now_ms() - t0;
     }
     *out = c;
@@ -542,9 +501,9 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     RP_CUDA(cudaStreamSynchronize(s));
     const long long U = *c->h_total;
     c->last_sites = U;
-    // the paint kernels read up to 4 entries past either end of a target's list: pad both ends
+    // the paint kernel's prefetch reads up to 3 entries past either end of a target's list: pad both ends
     const size_t entsz = fp64 ? sizeof(rp::EntD) : sizeof(rp::EntF);
-    const size_t pad = kEntPad;
+    const size_t pad = 4;
     RP_TRY(c->ent.ensure(((size_t)U + 2 * pad) * entsz));
     RP_CUDA(cudaMemsetAsync(c->ent.p, 0, pad * entsz, s));
     RP_CUDA(cudaMemsetAsync(c->ent.as<char>() + (pad + (size_t)U) * entsz, 0, pad * entsz, s));
@@ -559,11 +518,6 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     tc.log_ntheta = log(ntheta);
     tc.log_small = log(0.01);
     tc.Nm1 = N - 1.0;
-    tc.tau = c->theta / ntheta;
-    tc.cnt = c->cnt.as<int>();
-    tc.GT = c->GT.as<uint32_t>();
-    tc.lw = c->lw;
-    tc.k0 = k0;
     const unsigned gb = (unsigned)((nw + th - 1) / th);
     if (fp64) {
         auto *e = c->ent.as<rp::EntD>() + pad;
@@ -848,7 +802,7 @@ void rp_chunk_free(rp_chunk *c)
     if (!c) return;
     for (rp_chunk **ref : c->window_refs) *ref = nullptr; // windows left open fail with RP_EINVAL instead of dangling
     cudaSetDevice(c->device);
-    for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->cnt, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
+    for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
                       &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch, &c->nor, &c->segstate, &c->segdone,
                       &c->rleK, &c->rec_off, &c->win_bytes, &c->img_off, &c->image, &c->image_alt})
         b->release();
@@ -1127,7 +1081,7 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     P.G = c->G.as<uint32_t>();
     P.wps = c->wps; P.N = N; P.L = L; P.W = W; P.nfw = c->nfw; P.tailn = c->tailn;
     P.w = w; P.nt = N;
-    P.ent = c->ent.as<char>() + kEntPad * sizeof(rp::EntF);
+    P.ent = c->ent.as<char>() + 4 * sizeof(rp::EntF);
     P.off = c->off.as<long long>();
     P.nor = c->nor.as<double>();
     P.r = c->r.as<double>();

@@ -304,35 +304,7 @@ __global__ void boundaries_kernel(const ENT *__restrict__ ent, const long long *
 //   lsB[w] = log(N-1) - D*log(ntheta) + sum_{j>ib[w]} nor_j   (backward, :399,471-472)
 struct TableConsts {
     double log_ntheta, log_small, Nm1;
-    double tau;            // theta / (1 - theta): the mismatch multiplier
-    const int *cnt;        // [L] derived alleles per SNP among the N haplotypes
-    const uint32_t *GT;    // haplotype-major bits (the target's own allele at SNP 0 / L-1)
-    int lw, k0;
 };
-
-// M of an entry (see EntF): `interior` entries are sites where the target is derived by construction
-__device__ __forceinline__ double entry_M(const TableConsts &tc, int kk, int site, bool interior)
-{
-    bool derived = interior;
-    if (!interior) derived = (tc.GT[(size_t)(tc.k0 + kk) * tc.lw + (site >> 5)] >> (site & 31)) & 1u;
-    const double cnt = (double)tc.cnt[site], N = tc.Nm1 + 1.0;
-    return derived ? (cnt - 1.0) + tc.tau * (N - cnt) : tc.Nm1;
-}
-
-// cnt[s] = number of derived alleles at SNP s (bits of row s of G below N).  One warp per row.
-__global__ void count_derived_kernel(const uint32_t *__restrict__ G, int wps, int N, int L, int *__restrict__ cnt)
-{
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (row >= L) return;
-    const uint32_t *g = G + (size_t)row * wps;
-    const int nfull = N >> 5, tail = N & 31;
-    int c = 0;
-    for (int w = lane; w < nfull; w += 32) c += __popc(g[w]);
-    if (tail && lane == 0) c += __popc(g[nfull] & ((1u << tail) - 1u));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) cnt[row] = c;
-}
 
 // SEQ_GAP: gaps of at most this many SNPs are summed in the reference's order (fp64 verification mode: 16);
 // the fp32 path takes every gap from the double-double prefix (SEQ_GAP = 0), which is exact to ~1e-30.
@@ -379,7 +351,6 @@ __global__ void tables_kernel(ENT *__restrict__ ent, const long long *__restrict
                     nor[u] = tc.log_small + tc.log_ntheta;
                 }
                 e[i].set_c(rho / ((1.0 - rho) * tc.Nm1));
-                e[i].set_M(entry_M(tc, warp, a, i > 0 && i < D - 1));
                 if (no) no[i] = nor[u];
             }
         }
@@ -462,7 +433,6 @@ __global__ void __launch_bounds__(32 * NW) tables_cta_kernel(ENT *__restrict__ e
                     nor[u] = tc.log_small + tc.log_ntheta;
                 }
                 e[i].set_c(rho / ((1.0 - rho) * tc.Nm1));
-                e[i].set_M(entry_M(tc, kk, a, i > 0 && i < D - 1));
                 if (no) no[i] = nor[u];
             }
         }
@@ -511,21 +481,16 @@ __global__ void __launch_bounds__(32 * NW) tables_cta_kernel(ENT *__restrict__ e
 
 // ---------------------------------------------------------------------------------------
 // Per-step table entries.
-struct __align__(16) EntF { // fp32 mode: (c, M) are read as one 8-byte pair by the look-ahead painter
-    float c;
-    float M;   // sum over the references n != k of the step's multipliers: (cnt-1) + tau*(N-cnt) where the target is derived
-               // (cnt = derived alleles at the site), N-1 where it is not (only possible at SNP 0 / L-1)
+struct __align__(8) EntF { // fp32 mode
     int site;
-    int pad;
+    float c;
     __device__ __forceinline__ void set_c(double v) { c = (float)v; }
-    __device__ __forceinline__ void set_M(double v) { M = (float)v; }
 };
 struct __align__(16) EntD { // fp64 verification mode
     int site;
     int pad;
     double c;
     __device__ __forceinline__ void set_c(double v) { c = v; }
-    __device__ __forceinline__ void set_M(double) {}
 };
 
 template <typename T> struct Real;
@@ -1189,429 +1154,6 @@ paint_kernel(const PaintParams P)
     // even CTAs walk the site lists forwards (alpha), odd CTAs backwards (beta): two instantiations of one loop
     if (blockIdx.x & 1) paint_jobs<T, WPT, MULTI, 1>(P, &s_job, s_part);
     else paint_jobs<T, WPT, MULTI, 0>(P, &s_job, s_part);
-}
-
-
-// =========================================================================================
-// Look-ahead painter (single-warp fp32 teams, multipliers <= 1).
-//
-// The plain recursion  x <- (x + R) * m_p;  S_p = sum x;  R <- c_p * S_p  makes every step wait for its own sum: element
-// updates, thread sum, REDUX, scale, next R form one dependent chain, and with 3-4 resident chains per SM sub-partition
-// (config 2: 2000 chains on 592 schedulers) nothing covers the ~250 cycles that chain sits on top of the ~110 issue
-// slots of a step.  The sum is linear in the previous state, though:
-//     S_p = sum_n m_p[n] * (x_{p-1}[n] + R_{p-1}) = tau * S_{p-1} + (1 - tau) * P_p + R_{p-1} * M_p
-// with  P_p = sum over the references that MATCH at step p of x_{p-1}[n]   (mass that is not multiplied by tau)
-// and   M_p = sum_n m_p[n]                                                 (a property of the site: table entry).
-// P_p does not depend on R_{p-1}: it is accumulated while x_{p-1} is being produced (phase p-1, with the genotype row
-// of step p, which is loaded two steps ahead anyway), reduced across the warp by one integer REDUX issued at the end
-// of phase p-1, and only consumed at the end of phase p.  The team sum thus has a whole phase of the warp's own
-// element updates to land behind, and what is left between two phases is  I2F -> FFMA -> FMUL.  The tracked S enters
-// its successor with weight tau (0.001 by default), so rounding errors do not accumulate; P is measured every step.
-// Price: one predicated FADD per element on top of the 3 FP32 ops (FMA pipe 96 -> 128 cycles per word-step is not
-// needed: the predicated adds replace the packed sum of the plain kernel, 32 scalar against 16 packed issue slots).
-//
-// No phantoms and no forced zero for the target's own slot: slots that are not a reference of this chain (the target,
-// the slots past N in a partial last word, words past the row) are simply never part of a match mask, so whatever
-// they hold is never summed; they always take the multiplier tau and stay bounded.
-//
-// Fixed point: P_{p+1} <= S_p (multipliers <= 1), so the unit is 2^(E-29) with E the exponent of S_p itself; the 32 lane
-// values add up to < 2^30 (+ rounding).  S_{p+1} must be worth at least 2^RP_SUM_FLOOR_LOG2 of those units, else the
-// handler recomputes it as the plain sum of x_{p+1} with a shuffle butterfly (rare: the sum lost > 2^6 in one step).
-template <int WPT, int DIR>
-__device__ __forceinline__ void paint_jobs_look(const PaintParams &P)
-{
-    using T = float;
-    using RT = Real<float>;
-    using V2 = float2;
-    using Ent = EntF;
-    constexpr int ES = DIR ? -1 : 1;
-    const int t = threadIdx.x, lane = t;
-    const PaintConsts<T> &K = P.cf;
-    T tau = K.tau;
-    opaque(tau);
-    T omt = 1.0f - K.tau; // (1 - tau), exact enough: tau is a rounded float already
-    opaque(omt);
-    const Ent *ents = reinterpret_cast<const Ent *>(P.ent);
-    int *queue = P.queue + DIR;
-    unsigned rowbytes = (unsigned)P.wps * 4u;
-    asm volatile("" : "+r"(rowbytes));
-    bool valid[WPT];
-#pragma unroll
-    for (int j = 0; j < WPT; j++) valid[j] = (t * WPT + j) < P.nfw;
-    const char *gthr = reinterpret_cast<const char *>(P.G + ((t * WPT + WPT - 1) < P.wps ? t * WPT : 0));
-    asm volatile("" : "+l"(gthr));
-    const T chk = DIR ? K.ntheta : (T)1;
-    const T resc_R = DIR ? K.inv_ntheta : (T)1;
-    float blo_c = __int_as_float(P.xlo[DIR]), bhi_c = __int_as_float(P.xhi[DIR]); // band edges / chk, a hair inside
-    opaque(blo_c);
-    opaque(bhi_c);
-    constexpr float kSumFloor = (float)(1u << RP_SUM_FLOOR_LOG2);
-    constexpr int K1C = 283 << 23, K2C = -29 * (1 << 23);
-
-    const int nseg = P.nseg;
-    for (;;) {
-        // ---- ready queue (see paint_jobs) ----
-        const int njobs = P.nt * nseg;
-        int kk = 0;
-        if (lane == 0) kk = atomicAdd(queue, 1);
-        kk = __shfl_sync(0xffffffffu, kk, 0);
-        if (nseg > 1 && kk >= P.nt && kk < njobs) {
-            const volatile int *slot = P.segready + (size_t)DIR * (njobs - P.nt) + (kk - P.nt);
-            int v;
-            do {
-                v = *slot;
-                if (v == 0) __nanosleep(RP_SPIN_NS);
-            } while (!__all_sync(0xffffffffu, v != 0));
-            __threadfence();
-            kk = __shfl_sync(0xffffffffu, v - 1, 0);
-        }
-        if (kk >= njobs) break;
-        int seg = 0;
-        if (nseg > 1) {
-            seg = kk / P.nt;
-            kk -= seg * P.nt;
-        }
-        const int k = P.k0 + kk;
-        const long long base = P.off[kk];
-        const int m = (int)(P.off[kk + 1] - base) - 1;
-        int pbeg = 0, pend = m + 1;
-        if (nseg > 1) {
-            if (seg > 0) pbeg = (int)(((long long)(m + 1) * seg / nseg) & ~1LL);
-            if (seg < nseg - 1) pend = (int)(((long long)(m + 1) * (seg + 1) / nseg) & ~1LL);
-        }
-        const Ent *pe = ents + base + (DIR ? m : 0); // entry of step p is pe[p*ES]
-        const int rot = k & 31, wk = k >> 5;
-        bool own[WPT];
-        uint32_t keep[WPT]; // the slots of this thread's words that are references of this chain (unrotated bit positions)
-#pragma unroll
-        for (int j = 0; j < WPT; j++) {
-            const int wi = t * WPT + j;
-            own[j] = (wi == wk);
-            uint32_t kp = 0u;
-            if (wi < P.nfw) kp = (wi == P.nfw - 1 && P.tailn > 0) ? ((1u << P.tailn) - 1u) : 0xffffffffu;
-            if (own[j]) kp &= ~(1u << rot);
-            keep[j] = kp;
-            asm volatile("" : "+r"(keep[j]));
-        }
-
-        const int *bidx = (DIR ? P.ib : P.ia) + (size_t)kk * P.W;
-        const double *lsb = (DIR ? P.lsB : P.lsA) + (size_t)kk * P.W;
-        float *outv = (DIR ? P.beta : P.alpha) + (size_t)kk * P.W * P.N;
-        float *outl = (DIR ? P.ls_beta : P.ls_alpha) + (size_t)kk * P.W;
-        auto bpos = [&](int qq) -> int { return DIR ? (m - bidx[P.W - 1 - qq]) : bidx[qq]; };
-        int q = 0;
-
-        V2 a[WPT][16];
-#pragma unroll
-        for (int j = 0; j < WPT; j++)
-#pragma unroll
-            for (int e = 0; e < 16; e++) a[j][e] = make_float2(0.f, 0.f);
-        double lsr = 0.0;
-
-        // the target's own allele at the first and the last step: where it is ancestral nothing mismatches
-        const int site_first = pe[0].site, site_last = pe[m * ES].site;
-        const uint32_t ntd_first = ((P.G[(size_t)site_first * P.wps + wk] >> rot) & 1u) ? 0u : 0xffffffffu;
-        uint32_t ntd_last = ((P.G[(size_t)site_last * P.wps + wk] >> rot) & 1u) ? 0u : 0xffffffffu;
-        asm volatile("" : "+r"(ntd_last));
-        // match mask of step qstep from its genotype words: bit s (rotated: slot s of the word) is set where the reference
-        // does NOT take the multiplier tau and is part of the chain
-        auto expand = [&](uint32_t (&mk)[WPT], const uint32_t (&w)[WPT], uint32_t ntd) {
-#pragma unroll
-            for (int j = 0; j < WPT; j++) {
-                const uint32_t mm = (w[j] | ntd) & keep[j];
-                mk[j] = __funnelshift_r(mm, mm, rot);
-            }
-        };
-
-        auto store_vec = [&](float *o, T addR, bool ones) {
-#pragma unroll
-            for (int j = 0; j < WPT; j++) {
-                if (valid[j]) {
-                    const int n0 = (t * WPT + j) * 32;
-#pragma unroll
-                    for (int e = 0; e < 16; e++) {
-                        T vx = a[j][e].x + addR, vy = a[j][e].y + addR;
-                        if (ones) { vx = (T)1; vy = (T)1; }
-                        else if (e == 0 && own[j]) vx = (T)0;
-                        const int ix = n0 + ((2 * e + rot) & 31), iy = n0 + ((2 * e + 1 + rot) & 31);
-                        if (ix < P.N) o[ix] = vx;
-                        if (iy < P.N) o[iy] = vy;
-                    }
-                }
-            }
-        };
-
-        // ---- pipeline state ----
-        // Set A serves even steps, set B odd ones.  While phase p runs: M?[p&1] is the match mask of step p, M?[(p+1)&1] that
-        // of step p+1 (built at the top of the phase from W?[(p+1)&1], which is then refilled with the words of step p+3);
-        // cm?[p&1] = (c, M) of step p, cm?[(p+1)&1] is loaded with those of step p+1; site3 = site of step p+3.
-        uint32_t MC[WPT], W1[WPT], W2[WPT]; // mask of the step being computed; words of the next step and the one after
-        float2 cm0;                         // (c, M) of the step being computed
-        int site3;
-        {
-            uint32_t w0[WPT];
-            load_words(w0, gthr + (size_t)(unsigned)pe[pbeg * ES].site * rowbytes);
-            expand(MC, w0, pbeg == 0 ? ntd_first : (pbeg == m ? ntd_last : 0u));
-            load_words(W1, gthr + (size_t)(unsigned)pe[(pbeg + 1) * ES].site * rowbytes);
-            load_words(W2, gthr + (size_t)(unsigned)pe[(pbeg + 2) * ES].site * rowbytes);
-            site3 = pe[(pbeg + 3) * ES].site;
-            cm0 = *reinterpret_cast<const float2 *>(&pe[pbeg * ES].c);
-        }
-        const Ent *pq = pe + pbeg * ES; // entry of the step being computed
-
-        T R = DIR ? (T)1 : K.prior_n;
-        T S = 0.f;                 // S_{p-1}, tracked
-        int sa = 0;                // REDUX of P_p in fixed point (in flight during the phase)
-        float coef = 0.f;          // (1 - tau) * unit of sa; the unit is 2^(E-29), E the exponent of the S that bounded P
-        float tloS = blo_c;        // lower rare-path threshold: max(band edge, precision floor of S_p = 2^FLOOR units of sa)
-        const float floor_per_coef = kSumFloor / omt; // precision floor = coef * this
-        int q1 = q;
-        bool post = false;
-        int pev = 1;
-
-        if (DIR && seg == 0) { // beta at SNP L-1 is all ones, the target included (:413-418, :433-448)
-            int qe = q;
-            while (qe < P.W && bpos(qe) == 0) qe++;
-            for (int qq = q; qq < qe; qq++) {
-                const int w = P.W - 1 - qq;
-                store_vec(outv + (size_t)w * P.N, (T)0, true);
-                if (t == 0) outl[w] = (float)lsb[w];
-            }
-            q = qe;
-        }
-        auto next_event = [&]() -> int {
-            const int nb = q < P.W ? bpos(q) + (DIR ? 0 : 1) : 0x7fffffff;
-            return nb < m ? nb : m;
-        };
-
-        T hS = 0.f, hP = 0.f; // the handler's view of S_p and of this thread's share of P_{p+1}; it may change both
-        // rare path, run between phase p and phase p+1 (events as in paint_jobs)
-        auto handler = [&](int p, T cthis, bool lowp) {
-            // (the vote makes the branch provably warp-uniform: it contains shuffles)
-            if (__any_sync(0xffffffffu, lowp)) { // the fixed-point P ran out of bits: S_p is the plain sum of the chain's elements
-                T Sl = 0.f;
-#pragma unroll
-                for (int j = 0; j < WPT; j++) {
-                    const uint32_t kr = __funnelshift_r(keep[j], keep[j], rot);
-#pragma unroll
-                    for (int e = 0; e < 16; e++) {
-                        if (kr & (1u << (2 * e))) Sl += a[j][e].x;
-                        if (kr & (2u << (2 * e))) Sl += a[j][e].y;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) Sl += __shfl_xor_sync(0xffffffffu, Sl, o);
-                hS = Sl;
-                R = hS * cthis;
-            }
-            const T B = chk * hS;
-            bool rescaled = false;
-            if (p != 0 && (B < K.lower || B > K.upper)) { // :334-347, :538-551; no test at the first site
-                rescaled = true;
-                const T inv = (T)1 / B;
-#pragma unroll
-                for (int j = 0; j < WPT; j++)
-#pragma unroll
-                    for (int e = 0; e < 16; e++) { a[j][e].x *= inv; a[j][e].y *= inv; }
-                hP *= inv;
-                lsr += DIR ? (double)fast_log_dev((float)B) : log((double)B);
-                R = resc_R * cthis;
-                hS = resc_R; // the state now sums to 1 (forward) or 1/ntheta
-            }
-            if (DIR && post) { // finalise the backward stepping stone(s) of step p: divide by B if it rescaled
-                for (int qq = q; qq < q1; qq++) {
-                    const int w = P.W - 1 - qq;
-                    float *o = outv + (size_t)w * P.N;
-                    if (rescaled) {
-#pragma unroll
-                        for (int j = 0; j < WPT; j++) {
-                            if (valid[j]) {
-                                const int n0 = (t * WPT + j) * 32;
-                                for (int e = 0; e < 32 && n0 + e < P.N; e++) o[n0 + e] = o[n0 + e] / B;
-                            }
-                        }
-                    }
-                    if (t == 0) outl[w] = (float)(lsb[w] + lsr);
-                }
-                q = q1;
-                post = false;
-            }
-            const int pn = p + 1;
-            if (pn > m) { pev = 0x7fffffff; return; }
-            pev = next_event();
-            if (pev == pn) {
-                const int bp_now = q < P.W ? bpos(q) : -1;
-                if (bp_now == (DIR ? pn : pn - 1)) {
-                    q1 = q;
-                    while (q1 < P.W && bpos(q1) == bp_now) q1++;
-                    if (!DIR) { // alpha after step p, post-rescale (:354-374)
-                        for (int qq = q; qq < q1; qq++) {
-                            store_vec(outv + (size_t)qq * P.N, (T)0, false);
-                            if (t == 0) outl[qq] = (float)(lsb[qq] + lsr);
-                        }
-                        q = q1;
-                    } else { // beta of step pn is b = g_old + R' before the emission multiply (:481-488)
-                        post = true;
-                        for (int qq = q; qq < q1; qq++) store_vec(outv + (size_t)(P.W - 1 - qq) * P.N, R, false);
-                    }
-                }
-                pev = post ? pn + 1 : (pn == m ? 0x7fffffff : next_event());
-                if (!post && pev == pn) pev = pn + 1;
-            }
-        };
-
-        auto park_io = [&](bool save) {
-            char *park = P.segstate + ((size_t)DIR * P.nt + kk) * P.segstride;
-            V2 *pv = reinterpret_cast<V2 *>(park);
-            double *pd = reinterpret_cast<double *>(park + (size_t)32 * WPT * 16 * sizeof(V2));
-            int *pi = reinterpret_cast<int *>(pd + 4);
-            if (save) {
-#pragma unroll
-                for (int j = 0; j < WPT; j++)
-#pragma unroll
-                    for (int e = 0; e < 16; e++) __stcg(&pv[(size_t)(j * 16 + e) * 32 + t], a[j][e]);
-                if (t == 0) {
-                    __stcg(&pd[0], lsr);
-                    __stcg(&pd[1], (double)R);
-                    __stcg(&pd[2], (double)S);
-                    __stcg(&pd[3], (double)coef);
-                    __stcg(&pi[0], sa);
-                    __stcg(&pi[1], q);
-                    __stcg(&pi[2], q1);
-                    __stcg(&pi[3], post ? 1 : 0);
-                    __stcg(&pi[4], pev);
-                }
-                __threadfence();
-                __syncwarp();
-                if (t == 0) {
-                    const int tp = atomicAdd(queue + 2, 1);
-                    atomicExch(P.segready + (size_t)DIR * (P.nt * (nseg - 1)) + tp, (seg + 1) * P.nt + kk + 1);
-                }
-                __syncwarp();
-            } else {
-#pragma unroll
-                for (int j = 0; j < WPT; j++)
-#pragma unroll
-                    for (int e = 0; e < 16; e++) a[j][e] = __ldcg(&pv[(size_t)(j * 16 + e) * 32 + t]);
-                lsr = __ldcg(&pd[0]);
-                R = (T)__ldcg(&pd[1]);
-                S = (T)__ldcg(&pd[2]);
-                coef = (T)__ldcg(&pd[3]);
-                sa = __ldcg(&pi[0]);
-                q = __ldcg(&pi[1]);
-                q1 = __ldcg(&pi[2]);
-                post = __ldcg(&pi[3]) != 0;
-                pev = __ldcg(&pi[4]);
-                tloS = fmaxf(blo_c, coef * floor_per_coef);
-            }
-        };
-        if (seg > 0) park_io(false);
-
-        // one phase: x_p from x_{p-1} (mask MX), P_{p+1} from x_p (mask MY, built here), S_p and R_p from the landed P_p
-        auto do_step = [&](auto evc, int p) {
-            constexpr int EV = decltype(evc)::value;
-            uint32_t (&MX)[WPT] = MC;
-            uint32_t MY[WPT];
-            expand(MY, W1, (p + 1 == m) ? ntd_last : 0u);
-#pragma unroll
-            for (int j = 0; j < WPT; j++) W1[j] = W2[j];
-            load_words(W2, gthr + (size_t)(unsigned)site3 * rowbytes); // words of step p+3
-            site3 = pq[4 * ES].site;
-            const float2 cmX = cm0;
-            cm0 = *reinterpret_cast<const float2 *>(&pq[ES].c); // (c, M) of step p+1
-            pq += ES;
-            const float base_s = fmaf(R, cmX.y, tau * S); // tau*S_{p-1} + R_{p-1}*M_p
-            float P0 = 0.f, P1 = 0.f, P2 = 0.f, P3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < WPT; j++) {
-                const V2 R2 = make_float2(R, R);
-                const uint32_t mx = MX[j], my = MY[j];
-                // byte by byte of the masks: 8 element updates under predicates drawn from mx, then the 8 matching-mass adds
-                // under predicates drawn from my (R2P delivers 7 predicates of one mask byte at a time; with the two uses
-                // interleaved element by element ptxas juggles the 7 predicate registers two bits at a time)
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-#pragma unroll
-                    for (int e = 4 * g; e < 4 * g + 4; e++) {
-                        V2 v = RT::add2(a[j][e], R2);
-                        if (!(mx & (1u << (2 * e)))) v.x *= tau;
-                        if (!(mx & (2u << (2 * e)))) v.y *= tau;
-                        a[j][e] = v;
-                    }
-#pragma unroll
-                    for (int e = 4 * g; e < 4 * g + 4; e++) {
-                        const V2 v = a[j][e];
-                        if (e & 1) {
-                            if (my & (1u << (2 * e))) P2 += v.x;
-                            if (my & (2u << (2 * e))) P3 += v.y;
-                        } else {
-                            if (my & (1u << (2 * e))) P0 += v.x;
-                            if (my & (2u << (2 * e))) P1 += v.y;
-                        }
-                    }
-                }
-            }
-            hP = (P0 + P1) + (P2 + P3);
-            // P_p has landed (its REDUX was issued a phase ago)
-            hS = fmaf((float)sa, coef, base_s);
-            const T ccur = cmX.x;
-            R = hS * ccur;
-            const bool rare = (hS < tloS) || (hS > bhi_c);
-            const bool lowp = hS < coef * floor_per_coef; // fewer than 2^FLOOR units of the landed P's scale
-            // Unit for P_{p+1} <= S_p, its REDUX, and what the next landing needs.  Issued BEFORE the rare-path branch (and
-            // redone behind it when the handler ran): placed after the branch, ptxas sinks the REDUX into the next phase
-            // right in front of its consumer, which exposes the very latency this kernel exists to hide.
-            auto tail = [&]() {
-                S = hS;
-                const int ebs = __float_as_int(fmaxf(S, 1e-30f)) & 0x7f800000;
-                const float k1 = __int_as_float(K1C - ebs), k2 = __int_as_float(ebs + K2C);
-                sa = __reduce_add_sync(0xffffffffu, __float2int_rn(hP * k1));
-                coef = k2 * omt;
-                tloS = fmaxf(blo_c, coef * floor_per_coef);
-            };
-            tail();
-            if (EV == 1) {
-                handler(p, ccur, lowp);
-                tail();
-            } else if (__builtin_expect(__any_sync(0xffffffffu, rare), 0)) {
-                handler(p, ccur, lowp);
-                tail();
-            }
-#pragma unroll
-            for (int j = 0; j < WPT; j++) MC[j] = MY[j];
-        };
-        using PlainStep = std::integral_constant<int, 0>;
-        using EventStep = std::integral_constant<int, 1>;
-
-        for (int p = pbeg; p < pend;) {
-            const bool has_ev = pev <= pend;
-            const int plain_end = has_ev ? pev - 1 : pend;
-#pragma unroll 1
-            for (; p < plain_end; p++) do_step(PlainStep{}, p);
-            if (has_ev && p < pend) {
-                do_step(EventStep{}, p);
-                p++;
-            }
-        }
-        if (seg != nseg - 1) {
-            park_io(true);
-            continue;
-        }
-        if (!DIR) { // alpha stepping stones at the last visited site
-            while (q < P.W) {
-                store_vec(outv + (size_t)q * P.N, (T)0, false);
-                if (t == 0) outl[q] = (float)(lsb[q] + lsr);
-                q++;
-            }
-        }
-    }
-}
-
-template <int WPT>
-__global__ void __launch_bounds__(32, WPT == 1 ? 16 : 8) paint_look_kernel(const PaintParams P)
-{
-    if (blockIdx.x & 1) paint_jobs_look<WPT, 1>(P);
-    else paint_jobs_look<WPT, 0>(P);
 }
 
 // Cluster teams: 512 threads x 2 words per CTA, 2..16 CTAs per team (cluster dims set at launch).

@@ -1,4 +1,4 @@
-"""Paint one synthetic chunk a few times (for ncu / quick timing).  usage: prof_case.py N L [reps] [wpt] [ctas_per_sm] [nk] [nodense] [segments] [cluster] [plain]"""
+"""Paint one synthetic chunk a few times (for ncu / quick timing).  usage: prof_case.py N L [reps] [wpt] [ctas_per_sm] [nk] [nodense] [segments] [cluster]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -11,14 +11,13 @@ nk = int(sys.argv[6]) if len(sys.argv) > 6 else N
 nodense = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 segments = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 cluster = int(sys.argv[9]) if len(sys.argv) > 9 else 0
-plain = int(sys.argv[10]) if len(sys.argv) > 10 else 0
 hap, bp = synth.block_kingman(N, L, 1)
 r = chunkio.r_from_rpos(chunkio.uniform_map_rpos(bp))
 mem = 5.0 if N <= 1000 else (50.0 if N <= 5000 else 100.0)
 wb = chunkio.window_boundaries(hap, mem)
 with capi.DeviceChunk.from_arrays(hap, r, wb, 0.001) as c:
     import ctypes as C
-    t = capi.RpTune(wpt, cps); t.reserved[0] = nodense; t.reserved[1] = segments; t.reserved[2] = plain; t.reserved[3] = cluster
+    t = capi.RpTune(wpt, cps); t.reserved[0] = nodense; t.reserved[1] = segments; t.reserved[3] = cluster
     capi.check(capi.lib().rp_chunk_set_tune(c._h, C.byref(t)))
     for it in range(reps):
         st = c.paint_targets_device(0, nk)
