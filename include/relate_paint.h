@@ -96,6 +96,16 @@ void rp_host_free(void *p);
  * for the lines the reference prints to stderr) may be NULL. */
 int rp_make_chunks(const char *haps, const char *sample, const char *map, const char *dist, const char *out_dir,
                    int transversion, float memory_gb, int *n_chunks, char *warnings, size_t warnings_cap);
+/* Same with options.  RP_MC_HAPBITS: also write <out_dir>/chunk_<c>.hapbits, the genotype rows of the chunk in the
+ * painter's bit layout (header: "RPHBITS1", int N, L, words_per_snp, 0; then L rows of words_per_snp 32-bit words, bit
+ * n&31 of word n>>5 = allele of haplotype n).  rp_paint_chunk reads it instead of the 8x larger chunk_<c>.hap when its
+ * header matches, and deletes it after painting the chunk, so that the directory holds exactly the reference's files
+ * again (its Finalize refuses to remove a directory with unknown files).  rp_make_chunks itself takes the option from
+ * the environment (RELATE_HAPBITS=1); `relate --mode All`, where Paint is certain to follow, sets it. */
+#define RP_MC_HAPBITS 1u
+int rp_make_chunks_ex(const char *haps, const char *sample, const char *map, const char *dist, const char *out_dir,
+                      int transversion, float memory_gb, unsigned mc_flags, int *n_chunks, char *warnings,
+                      size_t warnings_cap);
 
 /* ---- chunk lifetime ---------------------------------------------------------------- */
 /* hap: L*N chars '0'/'1', SNP-major (Data::sequence); r: L doubles, already multiplied by rho;

@@ -81,6 +81,8 @@ SYMBOLS = {
     "rp_window_close": (None, [_P]),
     "rp_make_chunks": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_float,
                                  C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
+    "rp_make_chunks_ex": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_float, C.c_uint,
+                                    C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
     "rp_rle_encode": (C.c_int, [_P, C.c_int, _P, _P]),
     "rp_fast_log_device": (C.c_int, [C.c_int, _P, _P, C.c_int]),
     "rp_debug_pack_host": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int]),
@@ -335,12 +337,13 @@ def paint_chunks(out_dir: str, first_chunk: int, last_chunk: int, painting: str 
 
 
 def make_chunks(haps: str, sample: str, gmap: str, out_dir: str, dist: str | None = None, transversion: bool = False,
-                memory_gb: float = 5.0):
-    """``Relate --mode MakeChunks`` (host-only): -> (number of chunks, the warnings the reference prints to stderr)."""
+                memory_gb: float = 5.0, hapbits: bool = False):
+    """``Relate --mode MakeChunks`` (host-only): -> (number of chunks, the warnings the reference prints to stderr).
+    hapbits: also write the bit-packed sidecar ``chunk_<c>.hapbits`` that :func:`paint_chunk` consumes."""
     n = C.c_int(0)
     buf = C.create_string_buffer(4096)
-    check(lib().rp_make_chunks(haps.encode(), sample.encode(), gmap.encode(), dist.encode() if dist else None,
-                               out_dir.encode(), int(transversion), memory_gb, C.byref(n), buf, len(buf)))
+    check(lib().rp_make_chunks_ex(haps.encode(), sample.encode(), gmap.encode(), dist.encode() if dist else None,
+                                  out_dir.encode(), int(transversion), memory_gb, 1 if hapbits else 0, C.byref(n), buf, len(buf)))
     return n.value, buf.value.decode()
 
 

@@ -1,17 +1,22 @@
-// make_chunks.hpp — the loader in front of the Paint path: SHAPEIT haps/sample + genetic map -> the chunk files
-// `Relate --mode Paint` and every later stage read.  Restates, file for file and byte for byte,
-//   Data::MakeChunks            /root/reference/include/src/data.cpp:117-518
-//   haps::haps / haps::ReadSNP  /root/reference/include/src/data.hpp:128-162, data.cpp:544-573
-//   map::map                    /root/reference/include/src/data.cpp:591-625
-//   gzip::open                  /root/reference/include/src/data.cpp:7-60  (gzip input through `gunzip -c`)
-// Outputs in <out>/: parameters.bin, props.bin, and per chunk c: parameters_c<c>.bin, chunk_<c>.{hap,state,bp,dist,rpos,r}.
-// Host-only (text parsing and file layout); the painter's bit-packing of the genotype bytes happens on the GPU
-// when a chunk is loaded (rp_chunk_load / rp_paint_chunk).
+// make_chunks.hpp — the loader in front of the Paint path: SHAPEIT haps/sample + genetic map -> the chunk files that
+// `Relate --mode Paint` and every later stage read.
 //
-// Differences from the reference are confined to failure behaviour: where it assert()s or exit()s, this returns an
-// error string (the C ABI never terminates the process), and the whole haps file is streamed once per pass with a
-// large buffer instead of fscanf/fgets (same tokenisation: whitespace-separated fields, then the '0'/'1' characters
-// of the rest of the line).
+// What it must reproduce, byte for byte, is what the reference's `Relate --mode MakeChunks` leaves in <out>/
+// (Data::MakeChunks, /root/reference/include/src/data.cpp:117-518; haps / map readers data.hpp:128-162,
+// data.cpp:544-625): parameters.bin, props.bin and per chunk parameters_c<c>.bin, chunk_<c>.{hap,state,bp,dist,rpos,r}.
+// How it gets there is this repo's own three passes:
+//
+//   1. scan   one streaming pass over the haps text: per SNP its position / ids / alleles and the genotype row,
+//             bit-packed straight into the painter's HBM layout (bit n&31 of word n>>5, rows padded to 16 bytes);
+//             the whole data set stays resident that way (N*L/8 bytes: 125 MB at N = 10 000 x L = 100 000);
+//   2. plan   a pure function of the per-SNP derived-allele counts: chunk extents (with the 20 000-SNP overlap) and
+//             window boundaries under the --memory budget (the rules of data.cpp:129-231, see plan_chunks);
+//   3. emit   per chunk, the files; rows are expanded back to the reference's one-char-per-allele format, and —
+//             optionally — also written as they are to `chunk_<c>.hapbits`, which rp_paint_chunk reads instead of the
+//             8x larger .hap (and deletes once it has painted the chunk: the reference's Finalize refuses to remove a
+//             directory that still holds a file it does not know).
+//
+// Host-only.  Failures come back as an error string (the C ABI never terminates the process).
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -32,471 +37,522 @@ struct MakeChunksInfo {
     std::string warnings; // the lines the reference prints to stderr
 };
 
+// header of chunk_<c>.hapbits (little-endian): rows follow, `wps` 32-bit words each
+struct HapBitsHeader {
+    char magic[8]; // "RPHBITS1"
+    int N, L, wps, reserved;
+};
+inline const char *hapbits_magic() { return "RPHBITS1"; }
+
 namespace mc {
 
-// gzip::open: a file is gzip if it starts 1f 8b 08, and is then read through `gunzip -c '<name>'`
-struct InFile {
-    FILE *fp = nullptr;
-    bool piped = false;
+// ---- input: plain or gzip (through `gunzip -c`, as the reference does it), read in large blocks, handed out by line ----
+class TextFile {
+  public:
+    ~TextFile() { close(); }
     std::string open(const std::string &name)
     {
-        FILE *chk = fopen(name.c_str(), "rb");
-        if (!chk) return "Failed to open file " + name;
-        unsigned char b[3] = {0, 0, 0};
-        const size_t got = fread(b, 1, 3, chk);
-        fclose(chk);
-        const bool gz = got == 3 && b[0] == 0x1f && b[1] == 0x8b && b[2] == 0x08;
-        if (gz) {
-            const std::string cmd = "gunzip -c '" + name + "'";
-            fp = popen(cmd.c_str(), "r");
-            piped = true;
-        } else {
-            fp = fopen(name.c_str(), "r");
-        }
-        if (!fp) return "Failed to open file " + name;
+        close();
+        FILE *probe = fopen(name.c_str(), "rb");
+        if (!probe) return "Failed to open file " + name;
+        unsigned char sig[3] = {0, 0, 0};
+        const size_t got = fread(sig, 1, 3, probe);
+        fclose(probe);
+        piped_ = got == 3 && sig[0] == 0x1f && sig[1] == 0x8b && sig[2] == 0x08;
+        fp_ = piped_ ? popen(("gunzip -c '" + name + "'").c_str(), "r") : fopen(name.c_str(), "rb");
+        if (!fp_) return "Failed to open file " + name;
+        block_.resize(8u << 20);
+        have_ = used_ = 0;
         return "";
     }
     void close()
     {
-        if (!fp) return;
-        if (piped) pclose(fp);
-        else fclose(fp);
-        fp = nullptr;
+        if (fp_) (piped_ ? pclose : fclose)(fp_);
+        fp_ = nullptr;
     }
-    ~InFile() { close(); }
-};
-
-inline bool is_space(int c) { return c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r'; }
-
-// buffered reader with the two primitives the reference's parsers are made of
-struct Reader {
-    FILE *fp;
-    std::vector<char> buf;
-    size_t pos = 0, len = 0;
-    explicit Reader(FILE *f) : fp(f), buf(1 << 22) {}
-    int peek()
+    // next line without its '\n' (a final line without one is delivered too); *terminated tells which it was
+    bool line(const char *&begin, const char *&end, bool *terminated = nullptr)
     {
-        if (pos == len) {
-            len = fread(buf.data(), 1, buf.size(), fp);
-            pos = 0;
-            if (len == 0) return EOF;
-        }
-        return (unsigned char)buf[pos];
-    }
-    int get()
-    {
-        const int c = peek();
-        if (c != EOF) pos++;
-        return c;
-    }
-    // fscanf("%s"): skip white space, then the run of non-space characters; false at end of input
-    bool token(std::string &out)
-    {
-        out.clear();
-        int c;
-        while ((c = peek()) != EOF && is_space(c)) pos++;
-        if (c == EOF) return false;
-        while ((c = peek()) != EOF && !is_space(c)) {
-            out.push_back((char)c);
-            pos++;
-        }
-        return true;
-    }
-    // fgets: the rest of the line including the '\n' (or up to end of input)
-    void rest_of_line(std::string &out)
-    {
-        out.clear();
         for (;;) {
-            if (pos == len && peek() == EOF) return;
-            const char *b = buf.data() + pos;
-            const char *nl = (const char *)memchr(b, '\n', len - pos);
+            const char *b = block_.data() + used_;
+            const char *nl = static_cast<const char *>(memchr(b, '\n', have_ - used_));
             if (nl) {
-                out.append(b, nl - b + 1);
-                pos += nl - b + 1;
-                return;
+                begin = b;
+                end = nl;
+                used_ = (size_t)(nl - block_.data()) + 1;
+                if (terminated) *terminated = true;
+                return true;
             }
-            out.append(b, len - pos);
-            pos = len;
+            if (eof_) {
+                if (used_ == have_) return false;
+                begin = b;
+                end = block_.data() + have_;
+                used_ = have_;
+                if (terminated) *terminated = false;
+                return true;
+            }
+            // keep the partial line, refill behind it
+            const size_t keep = have_ - used_;
+            memmove(block_.data(), block_.data() + used_, keep);
+            used_ = 0;
+            have_ = keep;
+            if (have_ == block_.size()) block_.resize(block_.size() * 2);
+            const size_t got = fread(block_.data() + have_, 1, block_.size() - have_, fp_);
+            have_ += got;
+            if (got == 0) eof_ = true;
         }
     }
+
+  private:
+    FILE *fp_ = nullptr;
+    bool piped_ = false, eof_ = false;
+    std::vector<char> block_;
+    size_t have_ = 0, used_ = 0;
 };
 
-inline bool parse_int(const std::string &s, int &v) // fscanf("%d")
+inline bool blank(char c) { return c == ' ' || c == '\t' || c == '\v' || c == '\f' || c == '\r' || c == '\n'; }
+
+// next whitespace-separated field of [p, end); false if there is none
+inline bool field(const char *&p, const char *end, const char *&fb, const char *&fe)
 {
-    char *end = nullptr;
-    const long x = strtol(s.c_str(), &end, 10);
-    if (end == s.c_str()) return false;
-    v = (int)x;
+    while (p < end && blank(*p)) p++;
+    if (p == end) return false;
+    fb = p;
+    while (p < end && !blank(*p)) p++;
+    fe = p;
     return true;
 }
 
-inline std::string count_newlines(const std::string &name, long long &lines)
+// all fields of a whole file, for the small inputs (sample, dist, map)
+inline std::string all_fields(const std::string &name, std::vector<std::string> &out, long long *newlines = nullptr)
 {
-    InFile f;
+    TextFile f;
     std::string e = f.open(name);
     if (!e.empty()) return e;
-    std::vector<char> buf(1 << 22);
-    lines = 0;
-    size_t n;
-    while ((n = fread(buf.data(), 1, buf.size(), f.fp)) > 0) {
-        const char *p = buf.data(), *end = p + n;
-        while ((p = (const char *)memchr(p, '\n', end - p)) != nullptr) {
-            lines++;
-            p++;
+    const char *b, *en, *fb, *fe;
+    bool term = false;
+    long long nl = 0;
+    while (f.line(b, en, &term)) {
+        nl += term;
+        while (field(b, en, fb, fe)) out.emplace_back(fb, fe);
+    }
+    if (newlines) *newlines = nl;
+    return "";
+}
+
+// ---- pass 1 result: per-SNP columns + the bit-packed genotype rows ----
+struct SnpTable {
+    int N = 0, L = 0, wps = 0;
+    std::vector<int> bp;                      // L+1 entries (the last one is bp[L-1]+1, data.cpp:351)
+    std::vector<int> derived;                 // derived alleles per SNP
+    std::vector<std::string> rsid, anc, alt;
+    std::vector<uint32_t> bits;               // L rows of wps words
+    const uint32_t *row(int s) const { return bits.data() + (size_t)s * wps; }
+};
+
+inline int count_samples(const std::vector<std::string> &f) // haps::haps: two header rows, then ID_1 ID_2 missing
+{
+    int n = 0;
+    for (size_t i = 6; i + 3 <= f.size(); i += 3) n += (f[i] == f[i + 1]) ? 2 : 1;
+    return n;
+}
+
+inline std::string scan_haps(const std::string &f_haps, int N, SnpTable &t)
+{
+    TextFile f;
+    std::string e = f.open(f_haps);
+    if (!e.empty()) return e;
+    t.N = N;
+    t.wps = ((N + 31) / 32 + 3) / 4 * 4;
+    const char *b, *en, *fb, *fe;
+    bool term = false;
+    long long newlines = 0;
+    std::vector<uint32_t> rowbits((size_t)t.wps);
+    while (f.line(b, en, &term)) {
+        newlines += term;
+        const char *p = b;
+        if (!field(p, en, fb, fe)) continue; // blank line
+        const int s = (int)t.bp.size();
+        std::string id, a0, a1;
+        int pos = 0;
+        bool ok = field(p, en, fb, fe);
+        if (ok) id.assign(fb, fe);
+        ok = ok && field(p, en, fb, fe);
+        if (ok) {
+            char *stop = nullptr;
+            const std::string num(fb, fe);
+            pos = (int)strtol(num.c_str(), &stop, 10);
+            ok = stop != num.c_str();
         }
+        ok = ok && field(p, en, fb, fe);
+        if (ok) a0.assign(fb, fe);
+        ok = ok && field(p, en, fb, fe);
+        if (ok) a1.assign(fb, fe);
+        if (!ok) return "haps file: malformed line " + std::to_string(s + 1);
+        // the alleles: every '0' / '1' character of the rest of the line, anything else is a separator
+        std::fill(rowbits.begin(), rowbits.end(), 0u);
+        int n = 0, ones = 0;
+        for (; p < en && n < N; p++) {
+            const unsigned d = (unsigned)(*p - '0');
+            if (d <= 1u) {
+                rowbits[n >> 5] |= d << (n & 31);
+                ones += (int)d;
+                n++;
+            }
+        }
+        if (n != N) return "haps file: " + std::string(b, std::min(en, b + 60)) + "...: fewer than N alleles";
+        t.bp.push_back(pos);
+        t.derived.push_back(ones);
+        t.rsid.push_back(std::move(id));
+        t.anc.push_back(std::move(a0));
+        t.alt.push_back(std::move(a1));
+        t.bits.insert(t.bits.end(), rowbits.begin(), rowbits.end());
+    }
+    // the reference takes L from the number of '\n' characters; a data line without one would be read but not counted
+    t.L = (int)std::min<long long>(newlines, (long long)t.bp.size());
+    if (t.L < 1) return "empty haps/sample input";
+    t.bp.resize((size_t)t.L);
+    t.bp.push_back(t.bp[(size_t)t.L - 1] + 1);
+    return "";
+}
+
+// ---- pass 2: the plan ----
+struct ChunkPlan {
+    int file_begin = 0; // first SNP stored in the chunk's files (= new_begin - overlap for every chunk but the first)
+    int new_begin = 0;  // first SNP that no earlier chunk holds
+    int end = 0;        // one past the last SNP
+    std::vector<int> bounds; // window boundaries, absolute SNP indices: file_begin, ..., end
+    int new_windows = 0;     // windows opened by this chunk's own SNPs
+};
+
+struct PlanTotals {
+    double peak_window_floats = 0; // largest  sum over a window of derived*(N+1)
+    int max_new_windows = 0;
+    std::string warnings;
+};
+
+// Rules (data.cpp:129-231), stated on the derived-allele counts alone:
+//  * budget = memory*1e9/4 - (2N^2+3N) floats.  A window closes AT the SNP whose derived*(N+1) brings the running sum to
+//    the budget, provided the window already holds more than 10 SNPs; that SNP opens the next window (its own
+//    contribution is not carried over).
+//  * a chunk takes new SNPs while it has fewer than 500 boundaries (the ones inherited through the overlap included),
+//    fewer than `cap` new SNPs (cap = min(L+1, budget/N); 2 500 000 when memory >= 100) and SNPs remain.
+//  * every chunk but the first starts 20 000 SNPs early; it inherits the previous chunk's boundaries that lie beyond
+//    that point.  The previous chunk must be able to supply the overlap.
+inline std::string plan_chunks(const std::vector<int> &derived, int N, float memory_gb, std::vector<ChunkPlan> &plan, PlanTotals &tot)
+{
+    constexpr int kBoundaryCap = 500, kOverlap = 20000;
+    const int L = (int)derived.size();
+    const double fixed = (double)(2LL * N * N + 3LL * N);
+    const double budget = (double)memory_gb * 1e9 / 4.0 - fixed;
+    if (budget <= 0) return "Error: Need larger memory allowance.";
+    int cap = std::min(L + 1, (int)(budget / N));
+    if (memory_gb >= 100) cap = 2500000;
+    std::ostringstream warn;
+    int s = 0;
+    std::vector<int> prev_opened; // boundaries the previous chunk opened itself (its end not included)
+    while (s < L) {
+        ChunkPlan c;
+        c.new_begin = c.file_begin = s;
+        int inherited = 0;
+        if (!plan.empty()) {
+            const ChunkPlan &p = plan.back();
+            if (s - p.file_begin < kOverlap) return "chunk shorter than the 20000-SNP overlap (increase --memory)";
+            if (s - p.new_begin < kOverlap) return "overlap exceeds the chunk size";
+            c.file_begin = s - kOverlap;
+            c.bounds.push_back(c.file_begin);
+            for (int b : prev_opened)
+                if (b > c.file_begin) c.bounds.push_back(b);
+            inherited = (int)c.bounds.size();
+            if (!(inherited < kBoundaryCap - 1)) return "too many windows in the overlap";
+        }
+        std::vector<int> opened{s};
+        double load = 0.0;
+        int in_window = 0, taken = 0;
+        while ((int)opened.size() + inherited < kBoundaryCap && taken < cap && s < L) {
+            load += (double)(derived[s] * (N + 1));
+            if (load >= budget && in_window > 10) {
+                tot.peak_window_floats = std::max(tot.peak_window_floats, load);
+                opened.push_back(s);
+                load = 0.0;
+                in_window = 0;
+            }
+            s++;
+            in_window++;
+            taken++;
+        }
+        tot.peak_window_floats = std::max(tot.peak_window_floats, load);
+        c.end = s;
+        c.new_windows = (int)opened.size();
+        c.bounds.insert(c.bounds.end(), opened.begin(), opened.end());
+        c.bounds.push_back(s);
+        tot.max_new_windows = std::max(tot.max_new_windows, c.new_windows);
+        const float mean = (float)(taken / c.new_windows); // (integer division, as the reference reports it)
+        if (mean < 100) {
+            warn << "Memory allowance should be set " << 100 / mean << " times larger than\n";
+            warn << "the current setting using --memory (Default 5GB).\n";
+        }
+        prev_opened = std::move(opened);
+        plan.push_back(std::move(c));
+    }
+    tot.warnings = warn.str();
+    return "";
+}
+
+// ---- pass 3: files ----
+class OutFile {
+  public:
+    OutFile(const std::string &path, const char *mode = "wb") : path_(path), fp_(fopen(path.c_str(), mode))
+    {
+        if (fp_) setvbuf(fp_, nullptr, _IOFBF, 1 << 20);
+    }
+    ~OutFile()
+    {
+        if (fp_) fclose(fp_);
+    }
+    template <typename T> OutFile &put(const T &v) { return raw(&v, sizeof(T)); }
+    template <typename T> OutFile &put(const T *p, size_t n) { return raw(p, n * sizeof(T)); }
+    OutFile &raw(const void *p, size_t bytes)
+    {
+        if (fp_ && bytes && fwrite(p, 1, bytes, fp_) != bytes) bad_ = true;
+        return *this;
+    }
+    std::string finish() // "" or what went wrong
+    {
+        if (!fp_) return "cannot create " + path_;
+        const bool bad = bad_ || fclose(fp_) != 0;
+        fp_ = nullptr;
+        return bad ? "short write to " + path_ : "";
+    }
+
+  private:
+    std::string path_;
+    FILE *fp_;
+    bool bad_ = false;
+};
+
+inline bool transition(const std::string &a, const std::string &b) // data.cpp:301-302, 333-334
+{
+    return (a == "C" && b == "T") || (a == "T" && b == "C") || (a == "G" && b == "A") || (a == "A" && b == "G");
+}
+
+// bits of one row -> N chars '0' / '1'
+inline void expand_row(const uint32_t *w, int N, char *out)
+{
+    for (int n = 0; n < N; n += 32) {
+        uint32_t x = w[n >> 5];
+        const int m = std::min(32, N - n);
+        for (int j = 0; j < m; j++, x >>= 1) out[n + j] = (char)('0' + (x & 1u));
+    }
+}
+
+inline std::string emit_chunk(const std::string &out, int index, const ChunkPlan &c, const SnpTable &t, bool all_states_one,
+                              bool write_hapbits)
+{
+    const std::string base = out + "/chunk_" + std::to_string(index);
+    const int N = t.N, Lc = c.end - c.file_begin;
+    {
+        OutFile par(out + "/parameters_c" + std::to_string(index) + ".bin");
+        std::vector<int> rel(c.bounds);
+        for (int &b : rel) b -= c.file_begin;
+        par.put(N).put(Lc).put((int)rel.size()).put(rel.data(), rel.size());
+        const std::string e = par.finish();
+        if (!e.empty()) return e;
+    }
+    {
+        OutFile st(base + ".state");
+        st.put(Lc);
+        for (int s = c.file_begin; s < c.end; s++) st.put<int>(all_states_one ? 1 : (transition(t.anc[s], t.alt[s]) ? 0 : 1));
+        const std::string e = st.finish();
+        if (!e.empty()) return e;
+    }
+    {
+        OutFile hap(base + ".hap");
+        hap.put((size_t)Lc).put((size_t)N);
+        std::vector<char> row((size_t)N);
+        for (int s = c.file_begin; s < c.end; s++) {
+            expand_row(t.row(s), N, row.data());
+            hap.raw(row.data(), row.size());
+        }
+        const std::string e = hap.finish();
+        if (!e.empty()) return e;
+    }
+    if (write_hapbits) {
+        OutFile hb(base + ".hapbits");
+        HapBitsHeader h{};
+        memcpy(h.magic, hapbits_magic(), 8);
+        h.N = N;
+        h.L = Lc;
+        h.wps = t.wps;
+        hb.put(h).put(t.row(c.file_begin), (size_t)Lc * t.wps);
+        const std::string e = hb.finish();
+        if (!e.empty()) return e;
     }
     return "";
 }
 
-template <typename T> inline bool put(FILE *fp, const T *p, size_t n) { return fwrite(p, sizeof(T), n, fp) == n; }
+// genetic map (data.cpp:591-625) with the cursor the interpolation of data.cpp:451-470 walks along it
+class GeneticMap {
+  public:
+    std::string load(const std::string &name)
+    {
+        std::vector<std::string> f;
+        long long newlines = 0;
+        std::string e = all_fields(name, f, &newlines);
+        if (!e.empty()) return e;
+        const long long rows = newlines - 1; // the header line is not data
+        if (rows < 2) return "genetic map " + name + " needs at least two rows";
+        if ((long long)f.size() < 3 + 3 * rows) return "genetic map " + name + ": short row " + std::to_string((f.size() - 3) / 3 + 1);
+        bp_.resize((size_t)rows);
+        cm_.resize((size_t)rows);
+        for (long long i = 0; i < rows; i++) { // position (read as a double, kept as an int), rate (unused), cM
+            bp_[(size_t)i] = (int)strtod(f[(size_t)(3 + 3 * i)].c_str(), nullptr);
+            cm_[(size_t)i] = strtod(f[(size_t)(5 + 3 * i)].c_str(), nullptr);
+        }
+        for (size_t i = 0; i + 1 < bp_.size(); i++)
+            if (bp_[i + 1] < bp_[i]) return "genetic map is not sorted by position";
+        return "";
+    }
+    // Morgans at base pair `pos`; calls must come with non-decreasing pos
+    double morgans(int pos)
+    {
+        while (bp_[at_ + 1] <= pos && at_ < bp_.size() - 2) at_++;
+        const int span = bp_[at_ + 1] - bp_[at_];
+        if (span == 0 || bp_[at_] > pos) return cm_[at_] * 1e-2;
+        return ((pos - bp_[at_]) / ((double)span) * (cm_[at_ + 1] - cm_[at_]) + cm_[at_]) * 1e-2;
+    }
 
-inline bool is_transition(const std::string &a, const std::string &b) // data.cpp:301-302, 333-334
-{
-    return (a == "C" && b == "T") || (a == "T" && b == "C") || (a == "G" && b == "A") || (a == "A" && b == "G");
-}
+  private:
+    std::vector<int> bp_;
+    std::vector<double> cm_;
+    size_t at_ = 0;
+};
 
 } // namespace mc
 
 // returns "" on success, else the error text
 inline std::string make_chunks(const std::string &f_haps, const std::string &f_sample, const std::string &f_map,
                                const std::string &f_dist /* "unspecified" if none */, const std::string &out,
-                               bool use_transitions, float min_memory, MakeChunksInfo *info)
+                               bool use_transitions, float min_memory, MakeChunksInfo *info, bool write_hapbits = false)
 {
     using namespace mc;
+    // ---- scan ----
+    int N = 0;
+    {
+        std::vector<std::string> f;
+        std::string e = all_fields(f_sample, f);
+        if (!e.empty()) return e;
+        if (f.size() < 6) return "sample file " + f_sample + ": missing header";
+        N = count_samples(f);
+    }
+    if (N < 1) return "empty haps/sample input";
+    SnpTable t;
+    {
+        std::string e = scan_haps(f_haps, N, t);
+        if (!e.empty()) return e;
+    }
+    const int L = t.L;
+
+    // ---- plan ----
+    std::vector<ChunkPlan> plan;
+    PlanTotals tot;
+    {
+        std::vector<int> derived(t.derived.begin(), t.derived.begin() + L);
+        std::string e = plan_chunks(derived, N, min_memory, plan, tot);
+        if (!e.empty()) return e;
+    }
+    const int num_chunks = (int)plan.size();
+
+    // ---- emit: genotype / state / window files per chunk ----
+    for (int c = 0; c < num_chunks; c++) {
+        std::string e = emit_chunk(out, c, plan[c], t, use_transitions, write_hapbits);
+        if (!e.empty()) return e;
+    }
     std::ostringstream warn;
-    // ---- haps::haps: N from the sample file, L from the number of lines of the haps file ----
-    int N = 0, L = 0;
+    warn << tot.warnings;
+    warn << std::setprecision(2) << "Warning: Will use min " << 2.0 * (4.0 * N * N * (tot.max_new_windows + 2.0)) / 1e9 << "GB of hard disc.\n";
+    const double peak_gb = (tot.peak_window_floats + (double)(2LL * N * N + 3LL * N)) * (4.0 / 1e9);
     {
-        InFile f;
-        std::string e = f.open(f_sample);
-        if (!e.empty()) return e;
-        Reader rd(f.fp);
-        std::string a, b, c;
-        for (int h = 0; h < 2; h++)
-            if (!(rd.token(a) && rd.token(b) && rd.token(c))) return "sample file " + f_sample + ": missing header";
-        while (rd.token(a) && rd.token(b) && rd.token(c)) N += (a == b) ? 2 : 1;
-    }
-    {
-        long long lines = 0;
-        std::string e = count_newlines(f_haps, lines);
-        if (!e.empty()) return e;
-        L = (int)lines;
-    }
-    if (N < 1 || L < 1) return "empty haps/sample input";
-    const std::vector<char>::size_type uN = (std::vector<char>::size_type)N;
-
-    std::vector<int> bp_pos((size_t)L + 1);
-    std::vector<std::string> ancestral(L), alternative(L), rsid(L);
-
-    double min_memory_size = (min_memory)*1e9 / 4.0 - (2 * N * N + 3 * N), actual_min_memory_size = 0.0;
-    if (min_memory_size <= 0) return "Error: Need larger memory allowance.";
-    const int windows_per_section = 500;
-    int max_windows_per_section = 0;
-    const int overlap = 20000;
-    int max_chunk_size = std::min(L + 1, (int)(min_memory_size / N));
-    if (min_memory >= 100) max_chunk_size = 2500000;
-
-    // the reference keeps max_chunk_size rows of N chars; rows are allocated here as they are filled
-    std::vector<std::vector<char>> p_seq, p_overlap;
-    std::vector<int> window_boundaries(windows_per_section + 1), window_boundaries_overlap(windows_per_section + 1);
-    std::vector<int> section_boundary_start, section_boundary_end;
-    section_boundary_start.push_back(0);
-    int state_val = 1;
-    int min_snps_in_window = max_chunk_size;
-    float mean_snps_in_window = 0.0;
-    int num_windows = 0, num_windows_overlap = 0;
-    int overlap_in_section = 0;
-    int chunk_size = 0;
-    int chunk_index = 0;
-    double window_memory_size = 0.0;
-
-    InFile hf;
-    {
-        std::string e = hf.open(f_haps);
+        OutFile par(out + "/parameters.bin", "w");
+        par.put(N).put(L).put(num_chunks).put(peak_gb);
+        for (const ChunkPlan &c : plan) par.put(c.file_begin);
+        for (const ChunkPlan &c : plan) par.put(c.end);
+        std::string e = par.finish();
         if (!e.empty()) return e;
     }
-    Reader hr(hf.fp);
-    std::string tok, line, chr;
 
-    auto state_of = [&](int s) -> int {
-        if (use_transitions) return state_val;
-        state_val = is_transition(ancestral[s], alternative[s]) ? 0 : 1;
-        return state_val;
-    };
-
-    int snp = 0;
-    while (snp < L) {
-        const std::string base = out + "/chunk_" + std::to_string(chunk_index);
-        FILE *fp_haps_chunk = fopen((base + ".hap").c_str(), "wb");
-        FILE *fp_state = fopen((base + ".state").c_str(), "wb");
-        if (!fp_haps_chunk || !fp_state) {
-            if (fp_haps_chunk) fclose(fp_haps_chunk);
-            if (fp_state) fclose(fp_state);
-            return "cannot create " + base + ".hap/.state";
-        }
-        auto bail = [&](const std::string &msg) {
-            fclose(fp_haps_chunk);
-            fclose(fp_state);
-            return msg;
-        };
-
-        if (snp > 0) { // data.cpp:166-194: the last `overlap` SNPs of the previous chunk open this one
-            if (snp - section_boundary_start.back() < overlap) return bail("chunk shorter than the 20000-SNP overlap (increase --memory)");
-            overlap_in_section = overlap;
-            if (overlap_in_section > chunk_size) return bail("overlap exceeds the chunk size");
-            const int snp_section_begin = snp - overlap_in_section;
-            section_boundary_start.push_back(snp_section_begin);
-            p_overlap.assign(p_seq.begin() + (chunk_size - overlap_in_section), p_seq.begin() + chunk_size);
-            int *wo = window_boundaries_overlap.data();
-            wo[0] = snp_section_begin;
-            num_windows_overlap = 1;
-            for (int i = 0; i < num_windows; i++)
-                if (window_boundaries[i] > snp_section_begin) wo[num_windows_overlap++] = window_boundaries[i];
-            if (!(num_windows_overlap < windows_per_section - 1)) return bail("too many windows in the overlap");
-        }
-
-        const int snp_begin = snp;
-        window_memory_size = 0.0;
-        chunk_size = 0;
-        window_boundaries[0] = snp_begin;
-        num_windows = 1;
-        int snps_in_window = 0;
-        while (num_windows + num_windows_overlap < windows_per_section && chunk_size < max_chunk_size && snp < L) {
-            // haps::ReadSNP: "%s %s %d %s %s", then the '0'/'1' characters of the rest of the line
-            std::string s_bp;
-            if (!(hr.token(chr) && hr.token(rsid[snp]) && hr.token(s_bp) && hr.token(ancestral[snp]) && hr.token(alternative[snp])) ||
-                !parse_int(s_bp, bp_pos[snp]))
-                return bail("haps file: malformed line " + std::to_string(snp + 1));
-            hr.rest_of_line(line);
-            if ((int)p_seq.size() <= chunk_size) p_seq.emplace_back(N);
-            std::vector<char> &row = p_seq[chunk_size];
-            row.resize(N);
-            int n = 0, num_derived = 0;
-            for (size_t i = 0; i < line.size() && n < N; i++) {
-                const char d = line[i];
-                if (d == '0') row[n++] = '0';
-                else if (d == '1') {
-                    row[n++] = '1';
-                    num_derived++;
-                }
-            }
-            if (n != N) return bail("haps file: " + chr + " " + rsid[snp] + " " + std::to_string(bp_pos[snp]) + ": fewer than N alleles");
-
-            window_memory_size += num_derived * (N + 1);
-            if (window_memory_size >= min_memory_size && snps_in_window > 10) {
-                if (actual_min_memory_size < window_memory_size) actual_min_memory_size = window_memory_size;
-                if (min_snps_in_window > snps_in_window) min_snps_in_window = snps_in_window;
-                snps_in_window = 0;
-                window_memory_size = 0.0;
-                window_boundaries[num_windows] = snp;
-                num_windows++;
-            }
-            snp++;
-            snps_in_window++;
-            chunk_size++;
-        }
-        if (actual_min_memory_size < window_memory_size) actual_min_memory_size = window_memory_size;
-        if (min_snps_in_window > snps_in_window) min_snps_in_window = snps_in_window;
-        mean_snps_in_window = chunk_size / num_windows;
-        window_boundaries[num_windows] = snp;
-        if (num_windows > max_windows_per_section) max_windows_per_section = num_windows;
-        if (mean_snps_in_window < 100) {
-            warn << "Memory allowance should be set " << 100 / mean_snps_in_window << " times larger than\n";
-            warn << "the current setting using --memory (Default 5GB).\n";
-        }
-        section_boundary_end.push_back(snp);
-
-        int snp_tmp = section_boundary_start.back();
-        bool ok = true;
-        {
-            const std::string pp = out + "/parameters_c" + std::to_string(chunk_index) + ".bin";
-            FILE *fp = fopen(pp.c_str(), "w");
-            if (!fp) return bail("cannot create " + pp);
-            if (snp_begin == 0) {
-                const std::vector<char>::size_type uL_chunk = (std::vector<char>::size_type)chunk_size;
-                ok = ok && put(fp_haps_chunk, &uL_chunk, 1) && put(fp_haps_chunk, &uN, 1);
-                const int num_windows_in_section = num_windows + 1;
-                ok = ok && put(fp, &N, 1) && put(fp, &chunk_size, 1) && put(fp, &num_windows_in_section, 1) &&
-                     put(fp, window_boundaries.data(), (size_t)num_windows_in_section);
-                ok = ok && put(fp_state, &chunk_size, 1);
-            } else {
-                const int L_chunk = chunk_size + overlap_in_section;
-                const std::vector<char>::size_type uL_chunk = (std::vector<char>::size_type)L_chunk;
-                ok = ok && put(fp_haps_chunk, &uL_chunk, 1) && put(fp_haps_chunk, &uN, 1);
-                const int window_start = window_boundaries_overlap[0];
-                std::vector<int> wo(window_boundaries_overlap.begin(), window_boundaries_overlap.begin() + num_windows_overlap);
-                std::vector<int> wn(window_boundaries.begin(), window_boundaries.begin() + num_windows + 1);
-                for (int &x : wo) x -= window_start;
-                for (int &x : wn) x -= window_start;
-                const int num_windows_in_section = num_windows + num_windows_overlap + 1;
-                ok = ok && put(fp, &N, 1) && put(fp, &L_chunk, 1) && put(fp, &num_windows_in_section, 1) &&
-                     put(fp, wo.data(), wo.size()) && put(fp, wn.data(), wn.size());
-                ok = ok && put(fp_state, &L_chunk, 1);
-                for (int i = 0; i < overlap_in_section && ok; i++) {
-                    const int sv = state_of(snp_tmp);
-                    snp_tmp++;
-                    ok = put(fp_state, &sv, 1) && put(fp_haps_chunk, p_overlap[i].data(), (size_t)N);
-                }
-            }
-            fclose(fp);
-        }
-        for (int i = 0; i < chunk_size && ok; i++) {
-            const int sv = state_of(snp_tmp);
-            snp_tmp++;
-            ok = put(fp_state, &sv, 1) && put(fp_haps_chunk, p_seq[i].data(), (size_t)N);
-        }
-        fclose(fp_haps_chunk);
-        fclose(fp_state);
-        if (!ok) return "short write to " + base + ".hap/.state";
-        chunk_index++;
-    }
-    bp_pos[L] = bp_pos[L - 1] + 1;
-    hf.close();
-    p_seq.clear();
-    p_overlap.clear();
-
-    const int num_chunks = (int)section_boundary_start.size();
-    {
-        std::ostringstream w;
-        w << std::setprecision(2) << "Warning: Will use min " << 2.0 * (4.0 * N * N * (max_windows_per_section + 2.0)) / 1e9
-          << "GB of hard disc.\n";
-        warn << w.str();
-    }
-    {
-        FILE *fp = fopen((out + "/parameters.bin").c_str(), "w");
-        if (!fp) return "cannot create " + out + "/parameters.bin";
-        actual_min_memory_size += (2 * N * N + 3 * N);
-        actual_min_memory_size *= 4.0 / 1e9;
-        const bool ok = put(fp, &N, 1) && put(fp, &L, 1) && put(fp, &num_chunks, 1) && put(fp, &actual_min_memory_size, 1) &&
-                        put(fp, section_boundary_start.data(), (size_t)num_chunks) &&
-                        put(fp, section_boundary_end.data(), (size_t)num_chunks);
-        fclose(fp);
-        if (!ok) return "short write to parameters.bin";
-    }
-
-    // ---- dist (data.cpp:385-425) ----
-    std::vector<int> dist(L);
+    // ---- distances between SNPs (data.cpp:385-425) ----
+    std::vector<int> dist((size_t)L);
     if (f_dist == "unspecified") {
         for (int s = 0; s + 1 < L; s++) {
-            dist[s] = bp_pos[s + 1] - bp_pos[s];
+            dist[s] = t.bp[s + 1] - t.bp[s];
             if (dist[s] <= 0)
-                return "Failed at BP " + std::to_string(bp_pos[s]) + "\nSNPs are not sorted by bp or more than one SNP at same position.";
+                return "Failed at BP " + std::to_string(t.bp[s]) + "\nSNPs are not sorted by bp or more than one SNP at same position.";
         }
         dist[L - 1] = 1;
     } else {
-        InFile f;
-        std::string e = f.open(f_dist);
+        std::vector<std::string> f;
+        std::string e = all_fields(f_dist, f);
         if (!e.empty()) return e;
-        Reader rd(f.fp);
-        std::string a, b;
-        rd.token(a);
-        rd.token(b);
         int s = 0;
-        while (rd.token(a) && rd.token(b)) {
-            int mbp = 0, mdist = 0;
-            if (!parse_int(a, mbp) || !parse_int(b, mdist)) break;
+        for (size_t i = 2; i + 1 < f.size(); i += 2, s++) { // after the two header fields: position, distance
+            char *stop = nullptr;
+            const int pos = (int)strtol(f[i].c_str(), &stop, 10);
+            if (stop == f[i].c_str()) break;
             if (s >= L) return "dist file has more lines than the haps file";
-            if (bp_pos[s] != mbp) return "dist file: position " + std::to_string(mbp) + " does not match the haps file";
-            dist[s++] = mdist;
+            if (t.bp[s] != pos) return "dist file: position " + std::to_string(pos) + " does not match the haps file";
+            dist[s] = (int)strtol(f[i + 1].c_str(), nullptr, 10);
         }
     }
 
-    // ---- props.bin (data.cpp:427-449) ----
+    // ---- props.bin (data.cpp:427-449): int snp, bp, dist; three 1024-byte strings ----
     {
-        FILE *fp = fopen((out + "/props.bin").c_str(), "wb");
-        if (!fp) return "cannot create " + out + "/props.bin";
+        OutFile props(out + "/props.bin");
         std::vector<char> rec(12 + 3 * 1024);
-        bool ok = true;
-        for (int s = 0; s < L && ok; s++) {
+        for (int s = 0; s < L; s++) {
             std::fill(rec.begin(), rec.end(), 0);
-            memcpy(rec.data(), &s, 4);
-            memcpy(rec.data() + 4, &bp_pos[s], 4);
-            memcpy(rec.data() + 8, &dist[s], 4);
-            memcpy(rec.data() + 12, rsid[s].c_str(), std::min<size_t>(rsid[s].size(), 1023));
-            memcpy(rec.data() + 12 + 1024, ancestral[s].c_str(), std::min<size_t>(ancestral[s].size(), 1023));
-            memcpy(rec.data() + 12 + 2048, alternative[s].c_str(), std::min<size_t>(alternative[s].size(), 1023));
-            ok = put(fp, rec.data(), rec.size());
+            const int head[3] = {s, t.bp[s], dist[s]};
+            memcpy(rec.data(), head, 12);
+            const std::string *str[3] = {&t.rsid[s], &t.anc[s], &t.alt[s]};
+            for (int k = 0; k < 3; k++) memcpy(rec.data() + 12 + 1024 * k, str[k]->data(), std::min<size_t>(str[k]->size(), 1023));
+            props.raw(rec.data(), rec.size());
         }
-        fclose(fp);
-        if (!ok) return "short write to props.bin";
+        std::string e = props.finish();
+        if (!e.empty()) return e;
     }
 
-    // ---- genetic map -> rpos, r (data.cpp:451-481, map::map 591-625) ----
-    std::vector<int> mbp;
-    std::vector<double> mgen;
+    // ---- genetic positions and recombination distances (data.cpp:451-481) ----
+    std::vector<double> rpos((size_t)L + 1), r((size_t)L);
     {
-        long long lines = 0;
-        std::string e = count_newlines(f_map, lines);
+        GeneticMap gm;
+        std::string e = gm.load(f_map);
         if (!e.empty()) return e;
-        lines--; // header
-        if (lines < 2) return "genetic map " + f_map + " needs at least two rows";
-        InFile f;
-        e = f.open(f_map);
-        if (!e.empty()) return e;
-        Reader rd(f.fp);
-        std::string a, b, c;
-        rd.token(a);
-        rd.token(b);
-        rd.token(c);
-        mbp.resize(lines);
-        mgen.resize(lines);
-        for (long long s = 0; s < lines; s++) { // "%lf %f %lf"
-            if (!(rd.token(a) && rd.token(b) && rd.token(c))) return "genetic map " + f_map + ": short row " + std::to_string(s + 1);
-            mbp[s] = (int)strtod(a.c_str(), nullptr);
-            mgen[s] = strtod(c.c_str(), nullptr);
-        }
-    }
-    std::vector<double> r(L), rpos((size_t)L + 1);
-    {
-        size_t ir = 0, ib = 0;
-        size_t map_pos = 0;
-        if (mbp[map_pos] > bp_pos[ib]) {
-            rpos[ir++] = mgen[map_pos] * 1e-2;
-            ib++;
-        }
-        for (; ir < rpos.size();) {
-            while (mbp[map_pos + 1] <= bp_pos[ib] && map_pos < mbp.size() - 2) map_pos++;
-            if (mbp[map_pos + 1] - mbp[map_pos] < 0) return "genetic map is not sorted by position";
-            if (mbp[map_pos + 1] - mbp[map_pos] == 0 || mbp[map_pos] > bp_pos[ib]) {
-                rpos[ir] = mgen[map_pos] * 1e-2;
-            } else {
-                rpos[ir] = ((bp_pos[ib] - mbp[map_pos]) / ((double)(mbp[map_pos + 1] - mbp[map_pos])) * (mgen[map_pos + 1] - mgen[map_pos]) +
-                            mgen[map_pos]) *
-                           1e-2;
-            }
-            ir++;
-            ib++;
-        }
-        const double lower_bound = 1e-10; // data.cpp:4
-        for (int s = 0; s < L; s++) {
-            r[s] = rpos[s + 1] - rpos[s];
-            if (r[s] < lower_bound) r[s] = lower_bound;
-            r[s] *= 2500;
-        }
+        for (int s = 0; s <= L; s++) rpos[s] = gm.morgans(t.bp[s]);
+        for (int s = 0; s < L; s++) r[s] = std::max(rpos[s + 1] - rpos[s], 1e-10) * 2500;
     }
 
     // ---- per-chunk position files (data.cpp:485-516) ----
     for (int c = 0; c < num_chunks; c++) {
         const std::string base = out + "/chunk_" + std::to_string(c);
-        const int s0 = section_boundary_start[c];
-        const unsigned int L_chunk = (unsigned)(section_boundary_end[c] - s0), L1 = L_chunk + 1;
-        FILE *fp_pos = fopen((base + ".bp").c_str(), "wb"), *fp_dist = fopen((base + ".dist").c_str(), "wb");
-        FILE *fp_rpos = fopen((base + ".rpos").c_str(), "wb"), *fp_r = fopen((base + ".r").c_str(), "wb");
-        bool ok = fp_pos && fp_dist && fp_rpos && fp_r;
-        ok = ok && put(fp_pos, &L_chunk, 1) && put(fp_dist, &L_chunk, 1) && put(fp_rpos, &L1, 1) && put(fp_r, &L_chunk, 1);
-        ok = ok && put(fp_pos, &bp_pos[s0], L_chunk) && put(fp_dist, &dist[s0], L_chunk) && put(fp_rpos, &rpos[s0], (size_t)L_chunk + 1) &&
-             put(fp_r, &r[s0], L_chunk);
-        for (FILE *f : {fp_pos, fp_dist, fp_rpos, fp_r})
-            if (f) fclose(f);
-        if (!ok) return "cannot write the position files of chunk " + std::to_string(c);
+        const int s0 = plan[c].file_begin;
+        const unsigned Lc = (unsigned)(plan[c].end - s0);
+        OutFile fbp(base + ".bp"), fdist(base + ".dist"), frpos(base + ".rpos"), fr(base + ".r");
+        fbp.put(Lc).put(&t.bp[s0], Lc);
+        fdist.put(Lc).put(&dist[s0], Lc);
+        frpos.put(Lc + 1).put(&rpos[s0], (size_t)Lc + 1);
+        fr.put(Lc).put(&r[s0], Lc);
+        for (OutFile *f : {&fbp, &fdist, &frpos, &fr}) {
+            std::string e = f->finish();
+            if (!e.empty()) return e;
+        }
     }
 
     if (info) {
         info->N = N;
         info->L = L;
         info->num_chunks = num_chunks;
-        info->max_windows = max_windows_per_section;
-        info->actual_min_memory_gb = actual_min_memory_size;
+        info->max_windows = tot.max_new_windows;
+        info->actual_min_memory_gb = peak_gb;
         info->warnings = warn.str();
     }
     return "";

@@ -892,6 +892,14 @@ int rp_paint_from_host(int device, int N, int L, const char *hap, const double *
 int rp_make_chunks(const char *haps, const char *sample, const char *map, const char *dist, const char *out_dir,
                    int transversion, float memory_gb, int *n_chunks, char *warnings, size_t warnings_cap)
 {
+    const char *hb = getenv("RELATE_HAPBITS");
+    return rp_make_chunks_ex(haps, sample, map, dist, out_dir, transversion, memory_gb, (hb && atoi(hb) != 0) ? RP_MC_HAPBITS : 0u,
+                             n_chunks, warnings, warnings_cap);
+}
+
+int rp_make_chunks_ex(const char *haps, const char *sample, const char *map, const char *dist, const char *out_dir,
+                      int transversion, float memory_gb, unsigned mc_flags, int *n_chunks, char *warnings, size_t warnings_cap)
+{
     if (!haps || !sample || !map || !out_dir) return fail(RP_EINVAL, "Needed: haps, sample, map, output.");
     const std::string out = out_dir;
     struct stat sb;
@@ -899,7 +907,8 @@ int rp_make_chunks(const char *haps, const char *sample, const char *map, const 
         return fail(RP_EINVAL, "Error: Directory " + out + " already exists. Relate will use this directory to store temporary files.");
     if (mkdir(out.c_str(), 0700) != 0) return fail(RP_EIO, "could not create directory " + out);
     rp::MakeChunksInfo info;
-    const std::string err = rp::make_chunks(haps, sample, map, dist ? dist : "unspecified", out, transversion == 0, memory_gb, &info);
+    const std::string err = rp::make_chunks(haps, sample, map, dist ? dist : "unspecified", out, transversion == 0, memory_gb, &info,
+                                            (mc_flags & RP_MC_HAPBITS) != 0);
     if (!err.empty()) return fail(err.rfind("Failed to open", 0) == 0 || err.rfind("cannot", 0) == 0 ? RP_EIO : RP_EINVAL, err);
     if (n_chunks) *n_chunks = info.num_chunks;
     if (warnings && warnings_cap > 0) {
@@ -1465,6 +1474,23 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     }
     const size_t nchar = (size_t)hc.L * hc.N;
     const unsigned hw = io_thread_budget();
+    // chunk_<c>.hapbits (written by this library's MakeChunks on request): the genotype rows already in the painter's
+    // bit layout, 1/8 of the bytes of chunk_<c>.hap and nothing to pack.  Used when its header matches; removed once the
+    // chunk has been painted (the reference's Finalize cannot delete a directory that holds a file it does not know).
+    const std::string bits_path = std::string(out_dir) + "/chunk_" + std::to_string(chunk_index) + ".hapbits";
+    int bits_fd = open(bits_path.c_str(), O_RDONLY);
+    if (bits_fd >= 0) {
+        rp::HapBitsHeader h{};
+        struct stat sb;
+        const int want_wps = (((hc.N + 31) / 32) + 3) / 4 * 4;
+        const bool ok = pread(bits_fd, &h, sizeof h, 0) == (ssize_t)sizeof h && memcmp(h.magic, rp::hapbits_magic(), 8) == 0 && h.N == hc.N &&
+                        h.L == hc.L && h.wps == want_wps && fstat(bits_fd, &sb) == 0 &&
+                        (size_t)sb.st_size >= sizeof h + (size_t)h.L * h.wps * 4;
+        if (!ok) {
+            close(bits_fd);
+            bits_fd = -1;
+        }
+    }
     HapFeed feed;
     const size_t ring_cap = (size_t)(getenv("RP_RING_KB") ? atoi(getenv("RP_RING_KB")) : 65536) << 10; // tests shrink it
     // a slice = whole SNP rows worth about RP_SLICE_KB of genotype chars on disk; in the ring it is 1/8 of that
@@ -1509,11 +1535,22 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
                         std::this_thread::yield();
                     }
                 const int row0 = i * feed.rows, nrows = std::min(feed.rows, hc.L - row0);
-                raw.resize((size_t)feed.rows * hc.N);
-                ok = ok && rp::read_hap_range(hap_fd, (size_t)row0 * hc.N, (size_t)nrows * hc.N, raw.data());
-                if (ok) {
-                    uint32_t *dst = reinterpret_cast<uint32_t *>(const_cast<char *>(feed.src(i)));
-                    for (int rr = 0; rr < nrows; rr++) pack_row_host(raw.data() + (size_t)rr * hc.N, hc.N, dst + (size_t)rr * wps, wps, feed.padbit);
+                uint32_t *dst = reinterpret_cast<uint32_t *>(const_cast<char *>(feed.src(i)));
+                if (bits_fd >= 0) { // packed rows straight from the sidecar
+                    char *d8 = reinterpret_cast<char *>(dst);
+                    size_t left = (size_t)nrows * wps * 4, off = sizeof(rp::HapBitsHeader) + (size_t)row0 * wps * 4;
+                    while (ok && left > 0) {
+                        const ssize_t got = pread(bits_fd, d8, left, (off_t)off);
+                        if (got <= 0) ok = false;
+                        else { d8 += got; off += (size_t)got; left -= (size_t)got; }
+                    }
+                    if (ok && feed.padbit && (hc.N & 31)) // phantom slots of the partial last word (tau > 1)
+                        for (int rr = 0; rr < nrows; rr++) dst[(size_t)rr * wps + (hc.N >> 5)] |= ~0u << (hc.N & 31);
+                } else {
+                    raw.resize((size_t)feed.rows * hc.N);
+                    ok = ok && rp::read_hap_range(hap_fd, (size_t)row0 * hc.N, (size_t)nrows * hc.N, raw.data());
+                    if (ok)
+                        for (int rr = 0; rr < nrows; rr++) pack_row_host(raw.data() + (size_t)rr * hc.N, hc.N, dst + (size_t)rr * wps, wps, feed.padbit);
                 }
                 feed.ready[i].store(ok ? 1 : -1, std::memory_order_release);
             }
@@ -1714,6 +1751,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     for (auto &t : threads) t.join();
     for (auto &t : readers) t.join();
     close(hap_fd);
+    if (bits_fd >= 0) close(bits_fd);
     pool.finish();
     if (pool.failed() && first_rc == RP_OK) {
         first_rc = RP_EIO;
@@ -1727,6 +1765,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         if (first_rc == RP_OK && !err.empty()) return fail(RP_EIO, err);
     }
     if (first_rc != RP_OK) return fail(first_rc, first_err);
+    if (bits_fd >= 0) unlink(bits_path.c_str());
     if (per_device) *per_device = dstats;
     if (stats) {
         memset(stats, 0, sizeof *stats);

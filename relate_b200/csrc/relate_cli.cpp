@@ -241,7 +241,7 @@ int paint(const Args &a, int chunk_index, int last_chunk = -1, std::ostream &log
 }
 
 // pipeline/MakeChunks.cpp:14-117 behind the C ABI
-int make_chunks(const Args &a)
+int make_chunks(const Args &a, bool paint_follows = false)
 {
     bool help = false;
     if (!a.count("haps") || !a.count("sample") || !a.count("map") || !a.count("output")) {
@@ -259,9 +259,12 @@ int make_chunks(const Args &a)
     char warnings[4096];
     warnings[0] = 0;
     const float mem = a.count("memory") ? strtof(a.get("memory").c_str(), nullptr) : 5.0f;
-    const int rc = rp_make_chunks(a.get("haps").c_str(), a.get("sample").c_str(), a.get("map").c_str(),
-                                  a.count("dist") ? a.get("dist").c_str() : nullptr, a.get("output").c_str(),
-                                  a.count("transversion") ? 1 : 0, mem, nullptr, warnings, sizeof warnings);
+    // under --mode All this build's Paint is certain to follow: leave it the bit-packed genotype rows (chunk_<c>.hapbits)
+    const char *hb = getenv("RELATE_HAPBITS");
+    const unsigned mcf = (paint_follows || (hb && atoi(hb) != 0)) ? RP_MC_HAPBITS : 0u;
+    const int rc = rp_make_chunks_ex(a.get("haps").c_str(), a.get("sample").c_str(), a.get("map").c_str(),
+                                     a.count("dist") ? a.get("dist").c_str() : nullptr, a.get("output").c_str(),
+                                     a.count("transversion") ? 1 : 0, mem, mcf, nullptr, warnings, sizeof warnings);
     if (rc != RP_OK) {
         std::cerr << rp_last_error() << std::endl;
         return 1;
@@ -337,7 +340,7 @@ int main(int argc, char **argv)
         if (a.count("chunk_index")) {
             start_chunk = end_chunk = atoi(a.get("chunk_index").c_str());
         } else {
-            int rc = make_chunks(a);
+            int rc = make_chunks(a, /*paint_follows=*/true);
             if (rc != 0) return rc;
             int hdr[3];
             if (!read_ints(out + "/parameters.bin", hdr, 3)) {

@@ -14,7 +14,7 @@ import pytest
 
 from conftest import GOLDEN, ROOT
 from oracle import oracle
-from relate_b200 import capi, synth
+from relate_b200 import capi, chunkio, synth
 
 EXE = os.path.join(ROOT, "relate_b200", "bin", "relate")
 
@@ -149,3 +149,29 @@ def test_errors_do_not_exit(tmp_path):
     with pytest.raises(capi.PaintError) as e:
         capi.make_chunks(hp2, sp2, mp, os.path.join(d, "o3"))
     assert "not sorted" in str(e.value)
+
+
+def test_hapbits_sidecar_holds_the_packed_rows_and_changes_nothing_else(tmp_path):
+    """RP_MC_HAPBITS: chunk_<c>.hapbits = the rows of chunk_<c>.hap in the painter's bit layout (bit n&31 of word n>>5,
+    rows padded to 16 bytes); every other file is what MakeChunks writes without the option."""
+    import struct
+    d = str(tmp_path)
+    N, L = 70, 1200
+    hap, bp = synth.block_kingman(N, L, 9)
+    hp, sp = write_haps(d, hap, bp)
+    mp = write_map(d, bp)
+    capi.make_chunks(hp, sp, mp, os.path.join(d, "plain"), memory_gb=0.001)
+    capi.make_chunks(hp, sp, mp, os.path.join(d, "bits"), memory_gb=0.001, hapbits=True)
+    a, b = dir_md5(os.path.join(d, "plain")), dir_md5(os.path.join(d, "bits"))
+    side = {k: v for k, v in b.items() if k.endswith(".hapbits")}
+    assert side and {k: v for k, v in b.items() if k not in side} == a
+    for name in side:
+        c = int(name.split("_")[1].split(".")[0])
+        ch = chunkio.read_chunk(os.path.join(d, "bits"), c)
+        buf = open(os.path.join(d, "bits", name), "rb").read()
+        magic, n, l, wps, _ = struct.unpack_from("<8siiii", buf, 0)
+        assert magic == b"RPHBITS1" and (n, l) == (ch.N, ch.L) and wps == ((ch.N + 31) // 32 + 3) // 4 * 4
+        rows = np.frombuffer(buf, "<u4", l * wps, 24).reshape(l, wps)
+        want = np.zeros((l, wps * 32), np.uint8)
+        want[:, :ch.N] = ch.hap == ord("1")
+        assert np.array_equal(rows, np.packbits(want, axis=1, bitorder="little").view("<u4"))

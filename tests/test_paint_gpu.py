@@ -819,3 +819,35 @@ def test_small_batches_and_the_copy_pipeline_give_the_same_files(tmp_path, monke
     for w in range(5):
         assert filecmp.cmp(str(tmp_path / "one" / "chunk_0" / "paint" / f"relate_{w}.bin"),
                            str(tmp_path / "many" / "chunk_0" / "paint" / f"relate_{w}.bin"), shallow=False)
+
+
+@pytest.mark.parametrize("painting", ["0.001,1", "0.7,1"])
+def test_paint_chunk_reads_the_hapbits_sidecar_and_removes_it(tmp_path, painting):
+    """rp_make_chunks_ex(RP_MC_HAPBITS) leaves chunk_<c>.hapbits; the stage reads the packed rows from it (no chars, no
+    packing; the phantom bits of a partial last word are set by the reader when theta > 1/2) and writes the same bytes
+    as from chunk_<c>.hap; afterwards the directory holds exactly the reference's files again."""
+    N, L = 300, 2500   # N % 32 != 0
+    hap, bp = synth.block_kingman(N, L, 51)
+    hp, sp = chunkio.write_haps_sample(str(tmp_path / "in"), hap, bp)
+    mp = str(tmp_path / "in.map")
+    chunkio.write_uniform_map(mp, bp)
+    for tag, bits in (("plain", False), ("bits", True)):
+        capi.make_chunks(hp, sp, mp, str(tmp_path / tag), memory_gb=0.002, hapbits=bits)
+    assert os.path.exists(str(tmp_path / "bits" / "chunk_0.hapbits"))
+    before = set(os.listdir(str(tmp_path / "plain")))
+    sa = capi.paint_chunk(str(tmp_path / "plain"), 0, painting)
+    sb = capi.paint_chunk(str(tmp_path / "bits"), 0, painting)
+    assert sb["h2d_bytes"] == sa["h2d_bytes"]
+    W = chunkio.read_chunk(str(tmp_path / "plain"), 0).W
+    assert W >= 3
+    for w in range(W):
+        assert filecmp.cmp(str(tmp_path / "plain" / "chunk_0" / "paint" / f"relate_{w}.bin"),
+                           str(tmp_path / "bits" / "chunk_0" / "paint" / f"relate_{w}.bin"), shallow=False)
+    assert set(os.listdir(str(tmp_path / "bits"))) == before | {"chunk_0"}
+
+
+def test_duplicate_device_indices_are_refused(tmp_path):
+    synth.make_chunk_dir(str(tmp_path / "o"), 64, 400, seed=3, n_windows=2)
+    with pytest.raises(capi.PaintError) as e:
+        capi.paint_chunk(str(tmp_path / "o"), 0, "0.001,1", devices=[0, 0])
+    assert e.value.code == -1 and "twice" in str(e.value)
