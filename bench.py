@@ -243,10 +243,14 @@ def window_repaint_measure(chunk, rpos, W, peaks):
         win.distance(lo + 11 * i, out=dpin)
     ms_dp = 1e3 * (time.perf_counter() - t0) / nd
     win.close()
-    bytes_alg = 3.0 * 4.0 * N_HAP * rows + 2.0 * 4.0 * N_HAP * N_HAP
+    ck = 4.0  # checkpoint spacing of the single-warp one-word teams (paint_api.cu)
+    bytes_alg = 4.0 * N_HAP * rows + 2.0 * 4.0 * N_HAP * N_HAP            # compulsory: the posterior rows out, the stepping stones in
+    bytes_design = (4.0 + 8.0 / ck) * N_HAP * rows + 2.0 * 4.0 * N_HAP * N_HAP  # + every ck-th alpha row written and read back
     peak = peaks.get("hbm_gbs") or 6500.0
     return {"window": w, "posterior_rows": int(rows), "repaint_kernel_ms": ms, "algorithmic_bytes": bytes_alg,
             "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9, "peak_gbs": peak, "frac": bytes_alg / (ms * 1e-3) / 1e9 / peak,
+            "design_traffic_bytes": bytes_design, "design_traffic_gbs": bytes_design / (ms * 1e-3) / 1e9,
+            "round1_design_traffic_bytes": 3.0 * 4.0 * N_HAP * rows + 2.0 * 4.0 * N_HAP * N_HAP,
             "bound": "hbm", "distance_call_ms": ms_d, "distance_call_pinned_ms": ms_dp,
             "distance_call": "rp_window_distance: distance_kernel + D2H of the N x N float matrix, host wall clock",
             "source": "stepping stones resident in HBM (rp_window_open_resident), no paint-file round trip"}

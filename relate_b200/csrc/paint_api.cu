@@ -1010,7 +1010,7 @@ struct rp_window {
     int w = 0, start = 0, end = 0;
     long long rows = 0;
     int pitch = 0, tt = 0, wpt = 0; // row layout of `top` (RepaintParams::pitch)
-    DevBuf top, ls, rowoff, rpos, d, ab, be, lsa, lsb;
+    DevBuf top, ls, scal, rowoff, rpos, d, ab, be, lsa, lsb;
 };
 
 // alpha == nullptr: take the stepping stones of window w from the chunk's HBM buffers (last paint covered all targets)
@@ -1061,6 +1061,7 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     win->wpt = lp.wpt;
     win->pitch = lp.threads * lp.wpt * 32 + 32;
     if ((rc = win->top.ensure((size_t)win->rows * win->pitch * 4)) || (rc = win->ls.ensure((size_t)win->rows * 4)) ||
+        (rc = win->scal.ensure((size_t)win->rows * 8)) ||
         (rc = win->rowoff.ensure(((size_t)N + 1) * 8)) || (rc = win->rpos.ensure(((size_t)L + 1) * 8)) ||
         (rc = win->d.ensure(nn * 4)) || (rc = win->ab.ensure(nn * 4)) || (rc = win->be.ensure(nn * 4)) ||
         (rc = win->lsa.ensure((size_t)N * 4)) || (rc = win->lsb.ensure((size_t)N * 4)))
@@ -1098,6 +1099,7 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     P.alpha_begin = win->ab.as<float>(); P.beta_end = win->be.as<float>();
     P.ls_alpha = win->lsa.as<float>(); P.ls_beta = win->lsb.as<float>();
     P.top = win->top.as<float>(); P.ls = win->ls.as<float>();
+    P.scal = win->scal.as<float2>();
     P.pitch = win->pitch;
     P.rowoff = win->rowoff.as<long long>();
     P.queue = c->queue.as<int>();
@@ -1111,8 +1113,7 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     P.cf.upper = (float)(1.0 / 1e-10);
     P.log_ntheta = log(ntheta); P.log_small = log(0.01); P.Nm1 = N - 1.0;
     int occ = 0, ctas = 0;
-    auto launch = [&](auto kern, int ring_rows) -> int {
-        const size_t smem = (size_t)ring_rows * lp.threads * lp.wpt * 128; // shared-memory ring of alpha rows
+    auto launch = [&](auto kern, size_t smem) -> int { // smem: checkpoint ring + recomputed rows of one team
         RP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, lp.threads, smem));
         if (occ < 1) return fail(RP_ECUDA, "repaint kernel does not fit on an SM");
@@ -1121,10 +1122,17 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
         RP_CUDA(cudaGetLastError());
         return RP_OK;
     };
-    if (lp.wpt == 1) rc = lp.multi ? launch(rp::repaint_kernel<1, true>, rp::RepaintRing<1, true>::kRows)
-                                   : launch(rp::repaint_kernel<1, false>, rp::RepaintRing<1, false>::kRows);
-    else rc = lp.multi ? launch(rp::repaint_kernel<2, true>, rp::RepaintRing<2, true>::kRows)
-                       : launch(rp::repaint_kernel<2, false>, rp::RepaintRing<2, false>::kRows);
+    // checkpoint spacing: 4 rows for one-word single-warp teams (HBM traffic 12N -> 6N bytes per row), 2 for two-word and
+    // multi-warp teams (registers; rows of tens of KB of shared memory each): 12N -> 8N.  RP_REPAINT_CK=8 selects 8 for one-word single-warp teams.
+    const bool ck8 = getenv("RP_REPAINT_CK") && atoi(getenv("RP_REPAINT_CK")) == 8;
+    if (lp.wpt == 1) {
+        if (lp.multi) rc = launch(rp::repaint_kernel<1, true, 2>, rp::RepaintSmem<2>::bytes(lp.threads, 1));
+        else if (ck8) rc = launch(rp::repaint_kernel<1, false, 8>, rp::RepaintSmem<8>::bytes(32, 1));
+        else rc = launch(rp::repaint_kernel<1, false, 4>, rp::RepaintSmem<4>::bytes(32, 1));
+    } else {
+        if (lp.multi) rc = launch(rp::repaint_kernel<2, true, 2>, rp::RepaintSmem<2>::bytes(lp.threads, 2));
+        else rc = launch(rp::repaint_kernel<2, false, 2>, rp::RepaintSmem<2>::bytes(32, 2)); // (4 rows spill: 2 x 64 state registers)
+    }
     if (rc != RP_OK) return bail(rc);
     RP_CUDAW(cudaEventRecord(c->ev[2], s));
     RP_CUDAW(cudaStreamSynchronize(s));
@@ -1218,7 +1226,7 @@ void rp_window_close(rp_window *win)
     } else {
         cudaSetDevice(win->device);
     }
-    for (DevBuf *b : {&win->top, &win->ls, &win->rowoff, &win->rpos, &win->d, &win->ab, &win->be, &win->lsa, &win->lsb}) b->release();
+    for (DevBuf *b : {&win->top, &win->ls, &win->scal, &win->rowoff, &win->rpos, &win->d, &win->ab, &win->be, &win->lsa, &win->lsb}) b->release();
     delete win;
 }
 

@@ -1203,6 +1203,7 @@ struct RepaintParams {
     float *top;              // posterior rows, target k at row offset rowoff[k]; `pitch` floats per row
     int pitch;               // T*WPT*32 + 32 for the launch's team size T (see the row layout below)
     float *ls;               // per-row log-scales, same row indexing
+    float2 *scal;            // per row: the additive term R that formed the alpha row and the rescaling factor applied to it
     const long long *rowoff; // [N+1] prefix of (ib-ia+1)
     int *queue;
     PaintConsts<float> cf;
@@ -1223,10 +1224,21 @@ template <typename V, int D> struct Ahead {
 };
 
 extern __shared__ __align__(16) unsigned char rp_dyn_smem[];
-// rows of the shared-memory ring per team: bytes = kRows * (threads * WPT * 128)
-template <int WPT, bool MULTI> struct RepaintRing { static constexpr int kRows = MULTI ? 3 : (WPT == 1 ? 6 : 3); };
+// Shared memory of a team in the backward sweep: a ring of 2 checkpoint rows (cp.async from HBM) + CK-1 recomputed
+// rows, each threads * WPT * 128 bytes, + one 32-float tail line per row.
+template <int CK> struct RepaintSmem {
+    static constexpr int kSlots = 2 + (CK - 1);
+    static size_t bytes(int threads, int wpt) { return (size_t)kSlots * ((size_t)threads * wpt * 128 + 128); }
+};
 
-template <int WPT, bool MULTI>
+// Checkpointed window repaint.  The forward sweep keeps only every CK-th alpha row in HBM (in its final place in `top`)
+// plus two scalars per row: the additive term R that formed the row and the rescaling factor applied to it (1 if
+// none).  The backward sweep walks the window in blocks of CK rows from the end: it takes the block's checkpoint from
+// a cp.async ring, recomputes the CK-1 rows behind it into shared memory with the stored scalars -- the same two
+// roundings per element as in the forward sweep, hence the same bits -- and then runs the backward recursion over the
+// block, writing the posterior rows.  HBM traffic per row: 4N (posterior) + 8N/CK (checkpoint written and read back)
+// instead of 12N; the recomputation costs 2 FP32 ops per element on a kernel whose FMA pipe was 12 % busy.
+template <int WPT, bool MULTI, int CK>
 #ifndef RP_REPAINT_MINB
 #define RP_REPAINT_MINB 8
 #endif
@@ -1277,6 +1289,12 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
         return S;
     };
 
+    // shared-memory rows: piece e of (thread t, word j) of slot s at float4 index ((s*WPT + j)*8 + e)*TT + t (every thread
+    // writes and reads only its own pieces: no barrier); tail elements behind the rows
+    constexpr int NSLOT = RepaintSmem<CK>::kSlots;
+    float4 *srow = reinterpret_cast<float4 *>(rp_dyn_smem);
+    float *stail = reinterpret_cast<float *>(srow + (size_t)NSLOT * WPT * 8 * TT);
+
     for (;;) {
         int k;
         if (MULTI) {
@@ -1290,14 +1308,15 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             k = __shfl_sync(0xffffffffu, k, 0);
         }
         if (k >= P.nt) break;
-        const int i0 = P.ia[(size_t)k * P.W + P.w], i1 = P.ib[(size_t)k * P.W + P.w];
-        const int m = i1 - i0;                      // rows 0..m
-        const EntF *pe = ents + P.off[k] + i0;      // entry of row i is pe[i]
-        const double *pnor = P.nor + P.off[k] + i0;
+        const int i0w = P.ia[(size_t)k * P.W + P.w], i1w = P.ib[(size_t)k * P.W + P.w];
+        const int m = i1w - i0w;                     // rows 0..m
+        const EntF *pe = ents + P.off[k] + i0w;      // entry of row i is pe[i]
+        const double *pnor = P.nor + P.off[k] + i0w;
         float *top = P.top + (size_t)P.rowoff[k] * P.pitch;
         const size_t pitch = (size_t)P.pitch;
         const int tail_off = TT * WPT * 32;
         float *lsrow = P.ls + P.rowoff[k];
+        float2 *sc = P.scal + P.rowoff[k];           // per row: (R that formed it, rescaling factor applied to it)
         const int rot = k & 31, wk = k >> 5;
         T ownmul[WPT];
 #pragma unroll
@@ -1314,10 +1333,8 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             if (rho > 0.99) { rho = 0.99; nor_last = P.log_small + P.log_ntheta; }
             c_last = rho / ((1.0 - rho) * P.Nm1);
         }
-        // Inputs of a row, fetched two rows ahead of their use (their table entry four rows ahead; one row was not
-        // enough once the row traffic itself ran near the HBM rate): this thread's genotype words, the word holding
-        // the target's own allele, the tail word.  expand() turns them into the rotated
-        // mismatch bits; td = target's own allele mask.
+        // Inputs of a row: this thread's genotype words, the word holding the target's own allele, the tail word.
+        // expand() turns them into the rotated mismatch bits; td = target's own allele mask.
         struct RowIn { uint32_t w[WPT]; uint32_t kw, tw; };
         auto fetch = [&](int site) -> RowIn {
             RowIn in;
@@ -1336,10 +1353,41 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             }
             tmw = ~in.tw & td;
         };
-
-        // ---------------- forward: alpha rows -> top ----------------
+        // one forward step of the state (a, tl):  x <- (x + R) * (mis ? tau : 1), target forced to 0
         V2 a[WPT][16];
         T tl = 0.f;
+        auto advance = [&](const RowIn &in, T R, V2 &S0, V2 &S1) {
+            uint32_t mw[WPT], tmw;
+            expand(in, mw, tmw);
+#pragma unroll
+            for (int j = 0; j < WPT; j++) {
+                const T Rj = R * vmul[j];
+                const V2 R2 = make_float2(Rj, Rj);
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    V2 v = RT::add2(a[j][e], R2);
+                    if (mw[j] & (1u << (2 * e))) v.x *= tau;
+                    if (mw[j] & (2u << (2 * e))) v.y *= tau;
+                    if (e == 0) v.x *= ownmul[j];
+                    a[j][e] = v;
+                    if (e & 1) S1 = RT::add2(S1, v); else S0 = RT::add2(S0, v);
+                }
+            }
+            if (tail_warp) {
+                T v = tl + R;
+                if (tmw & lanebit) v *= tau;
+                tl = v * tailmul;
+            }
+        };
+        auto scale_state = [&](T inv) {
+#pragma unroll
+            for (int j = 0; j < WPT; j++)
+#pragma unroll
+                for (int e = 0; e < 16; e++) { a[j][e].x *= inv; a[j][e].y *= inv; }
+            tl *= inv;
+        };
+
+        // ---------------- forward: checkpoint rows -> top, per-row scalars -> scal ----------------
         {   // row 0 = alpha_begin, target zeroed (:757-779)
             const float *ab = P.alpha_begin + (size_t)k * N;
 #pragma unroll
@@ -1364,22 +1412,22 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
                 }
             if (tail_lane) row[tail_off + lane] = tl;
         };
-        auto local_sum = [&]() -> T {
+        int par = 0; // alternates the partial-sum buffer between consecutive reductions
+        store_row(top);
+        T S;
+        {
             V2 S0 = make_float2(0.f, 0.f), S1 = S0;
 #pragma unroll
             for (int j = 0; j < WPT; j++)
 #pragma unroll
                 for (int e = 0; e < 16; e++) { if (e & 1) S1 = RT::add2(S1, a[j][e]); else S0 = RT::add2(S0, a[j][e]); }
             S0 = RT::add2(S0, S1);
-            return S0.x + S0.y + tl;
-        };
-        int par = 0; // alternates the partial-sum buffer between consecutive reductions
-        store_row(top);
-        T S = reduce(local_sum(), par ^= 1);
+            S = reduce(S0.x + S0.y + tl, par ^= 1);
+        }
         double prev_ls = (double)P.ls_alpha[k];
         if (t == 0) lsrow[0] = P.ls_alpha[k];
         T R = S * pe[0].c;
-        // entries past the window's slice belong to the chunk-level table or its 4-entry padding; nor is padded too
+        // entries past the window's slice belong to the chunk-level table or its padding; nor is padded too
         Ahead<EntF, 2> entq;
         Ahead<RowIn, 2> inq;
         Ahead<T, 2> cq;
@@ -1393,41 +1441,19 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             const RowIn cin = inq.pop_push(fetch(ent.site)); // inputs of row i; row i+2's are requested
             const T ccur = cq.pop_push(ent.c);               // c of row i
             const double nor_cur = norq.pop_push(pnor[i + 2]); // pnor[i-1]
-            uint32_t mw[WPT], tmw;
-            expand(cin, mw, tmw);
             V2 S0 = make_float2(0.f, 0.f), S1 = S0;
-#pragma unroll
-            for (int j = 0; j < WPT; j++) {
-                const T Rj = R * vmul[j];
-                const V2 R2 = make_float2(Rj, Rj);
-#pragma unroll
-                for (int e = 0; e < 16; e++) {
-                    V2 v = RT::add2(a[j][e], R2);
-                    if (mw[j] & (1u << (2 * e))) v.x *= tau;
-                    if (mw[j] & (2u << (2 * e))) v.y *= tau;
-                    if (e == 0) v.x *= ownmul[j];
-                    a[j][e] = v;
-                    if (e & 1) S1 = RT::add2(S1, v); else S0 = RT::add2(S0, v);
-                }
-            }
+            const T Rrow = R;
+            advance(cin, Rrow, S0, S1);
             S0 = RT::add2(S0, S1);
             T Sl = S0.x + S0.y;
-            if (tail_warp) {
-                T v = tl + R;
-                if (tmw & lanebit) v *= tau;
-                tl = v * tailmul;
-                Sl += tl;
-            }
+            if (tail_warp) Sl += tl;
             S = reduce(Sl, par ^= 1);
             prev_ls += nor_cur;
             float lsi = (float)prev_ls;
+            T inv = 1.f;
             if (S < K.lower || S > K.upper) { // :865-876
-                const T inv = 1.f / S;
-#pragma unroll
-                for (int j = 0; j < WPT; j++)
-#pragma unroll
-                    for (int e = 0; e < 16; e++) { a[j][e].x *= inv; a[j][e].y *= inv; }
-                tl *= inv;
+                inv = 1.f / S;
+                scale_state(inv);
                 const double lg = log((double)S);
                 prev_ls += lg;
                 lsi = (float)((double)lsi + lg);
@@ -1436,11 +1462,14 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
                 R = S;
             }
             R *= (i == m) ? (T)c_last : ccur;
-            store_row(top + (size_t)i * pitch);
-            if (t == 0) lsrow[i] = lsi;
+            if (i % CK == 0) store_row(top + (size_t)i * pitch);
+            if (t == 0) {
+                lsrow[i] = lsi;
+                sc[i] = make_float2(Rrow, inv);
+            }
         }
 
-        // ---------------- backward: top[i] = alpha_i * beta_i, in place ----------------
+        // ---------------- backward: top[i] = alpha_i * beta_i ----------------
         // carried in g = b * m_s as in the painter; b_i = g_{i+1} + R' is the plain beta the reference multiplies in.
         // The posterior row is taken BEFORE a rescale of this step while its log-scale receives +log(B) (:1033-1061).
         const T chk = K.ntheta, resc_R = K.inv_ntheta; // B = ntheta * sum g;  R' after a rescale is 1/ntheta
@@ -1448,130 +1477,177 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
         T gt = 0.f;
         T Rp = 0.f;
         double prevb = (double)P.ls_beta[k];
-        // alpha rows of the backward sweep come through a ring of RING rows in shared memory, filled by cp.async RING
-        // rows ahead of their use (the kernel has one row-sized load per step and one team per target, so bytes in
-        // flight = teams x rows ahead; with a single row in registers it ran at the latency-bound 2.6 TB/s).  Every
-        // thread copies and later reads only its own 16-byte pieces (piece e of thread t sits at [e][t]: conflict-free),
-        // so the ring needs no barrier, only cp.async.wait_group.
-        float4 *ring = reinterpret_cast<float4 *>(rp_dyn_smem);
-        constexpr int RING = RepaintRing<WPT, MULTI>::kRows;
-        auto ring_issue = [&](int i, int rslot) { // request row i (nothing if i < 0); always closes one group
-            if (i >= 0) {
-                const float4 *src = reinterpret_cast<const float4 *>(top + (size_t)i * pitch) + t;
+        if (MULTI) __syncthreads(); // (sc / lsrow of this target were written by thread 0)
+        else __syncwarp();
+        auto spiece = [&](int slot, int j, int e) -> float4 * { return srow + ((size_t)(slot * WPT + j) * 8 + e) * TT + t; };
+        auto ck_issue = [&](int jb, int slot) { // request the checkpoint row of block jb (nothing if jb < 0); always closes one group
+            if (jb >= 0) {
+                const float4 *src = reinterpret_cast<const float4 *>(top + (size_t)jb * CK * pitch) + t;
 #pragma unroll
                 for (int j = 0; j < WPT; j++)
                     if (valid[j]) {
 #pragma unroll
                         for (int e = 0; e < 8; e++) {
-                            const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + ((size_t)(rslot * WPT + j) * 8 + e) * TT + t);
+                            const unsigned dst = (unsigned)__cvta_generic_to_shared(spiece(slot, j, e));
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)(j * 8 + e) * TT) : "memory");
                         }
                     }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        const int nblk = m / CK; // index of the last block
+        ck_issue(nblk, nblk & 1);
+        ck_issue(nblk - 1, (nblk - 1) & 1);
+        // per-block inputs, requested one block ahead: the rows' genotype words, their forward scalars, the checkpoint's tail
+        RowIn nin[CK];
+        float2 nsc[CK];
+        float ntail;
+        auto block_request = [&](int jb) {
+            const int b0 = max(jb, 0) * CK;
 #pragma unroll
-        for (int d = 0; d < RING; d++) ring_issue(m - d, d);
-        int rslot = 0;
-        // the same streams walking down; plus the row's log-scale (written by the forward sweep), the tail element's
-        // alpha and pnor[i+1] (used for rows i <= m-2), three rows ahead, row indices clamped at 0
-        Ahead<float, 3> lsq, tailq;
+            for (int r = 0; r < CK; r++) {
+                nin[r] = fetch(pe[min(b0 + r, m)].site); // (rows past m are never used)
+                nsc[r] = sc[min(b0 + r, m)];
+            }
+            ntail = tail_lane ? top[(size_t)b0 * pitch + tail_off + lane] : 0.f;
+        };
+        block_request(nblk);
+        // small per-row streams walking down: c of the row, its log-scale (written by the forward sweep) and pnor[i+1]
+        Ahead<float, 3> lsq;
         Ahead<double, 3> norbq;
-        auto tail_at = [&](int i) -> float { return tail_lane ? top[(size_t)max(i, 0) * pitch + tail_off + lane] : 0.f; };
-        entq.q[0] = pe[m - 2]; entq.q[1] = pe[m - 3];
-        inq.q[0] = fetch(pe[m].site); inq.q[1] = fetch(pe[m - 1].site);
         cq.q[0] = pe[m].c; cq.q[1] = pe[m - 1].c;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             lsq.q[d] = lsrow[max(m - d, 0)];
-            tailq.q[d] = tail_at(m - d);
             norbq.q[d] = pnor[max(m - d + 1, 0)];
         }
-        for (int i = m; i >= 0; i--) {
-            float *row = top + (size_t)i * pitch;
-            const EntF ent = entq.pop_push(pe[i - 4]);       // = pe[i-2]
-            const RowIn cin = inq.pop_push(fetch(ent.site)); // inputs of row i; row i-2's are requested
-            const T ccur = cq.pop_push(ent.c);
-            const float ls_cur = lsq.pop_push(lsrow[max(i - 3, 0)]);
-            const float tail_a = tailq.pop_push(tail_at(i - 3));
-            const double norb_cur = norbq.pop_push(pnor[max(i - 2, 0)]); // pnor[i+1]
-            uint32_t mw[WPT], tmw;
-            expand(cin, mw, tmw);
-            V2 S0 = make_float2(0.f, 0.f), S1 = S0;
-            if (i == m) { // b_m = beta_end (:895-909)
-                const float *be = P.beta_end + (size_t)k * N;
+        for (int jb = nblk; jb >= 0; jb--) {
+            const int b0 = jb * CK;
+            const int nb = min(CK, m - b0 + 1); // rows b0 .. b0+nb-1
+            RowIn cin[CK];
+            float2 csc[CK];
 #pragma unroll
-                for (int j = 0; j < WPT; j++)
+            for (int r = 0; r < CK; r++) { cin[r] = nin[r]; csc[r] = nsc[r]; }
+            const float ctail = ntail;
+            block_request(jb - 1);
+            const int cs = jb & 1;
+            asm volatile("cp.async.wait_group 1;" ::: "memory"); // this block's checkpoint has landed (the next one may be in flight)
+            // ---- recompute rows b0+1 .. b0+nb-1 from the checkpoint ----
 #pragma unroll
-                    for (int e = 0; e < 16; e++) {
-                        const int n0 = (t * WPT + j) * 32;
-                        g[j][e] = make_float2(valid[j] ? be[n0 + ((2 * e + rot) & 31)] : 0.f,
-                                              valid[j] ? be[n0 + ((2 * e + 1 + rot) & 31)] : 0.f);
-                    }
-                if (tail_lane) gt = be[P.nfw * 32 + lane];
-            }
-            asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory"); // row i has landed
-#pragma unroll
-            for (int j = 0; j < WPT; j++) {
-                const T Rj = (i == m) ? 0.f : Rp * vmul[j];
-                const V2 R2 = make_float2(Rj, Rj);
-                float4 *o = reinterpret_cast<float4 *>(row) + (size_t)(j * 8) * TT + t;
+            for (int j = 0; j < WPT; j++)
 #pragma unroll
                 for (int e2 = 0; e2 < 8; e2++) {
-                    const float4 av = valid[j] ? ring[((size_t)(rslot * WPT + j) * 8 + e2) * TT + t] : make_float4(0.f, 0.f, 0.f, 0.f); // alpha_i
-                    V2 b0 = RT::add2(g[j][2 * e2], R2), b1 = RT::add2(g[j][2 * e2 + 1], R2);
-                    if (e2 == 0) b0.x *= ownmul[j]; // b[k] = 0
-                    if (valid[j]) o[(size_t)e2 * TT] = make_float4(av.x * b0.x, av.y * b0.y, av.z * b1.x, av.w * b1.y);
-                    if (mw[j] & (1u << (4 * e2))) b0.x *= tau;
-                    if (mw[j] & (2u << (4 * e2))) b0.y *= tau;
-                    if (mw[j] & (4u << (4 * e2))) b1.x *= tau;
-                    if (mw[j] & (8u << (4 * e2))) b1.y *= tau;
-                    g[j][2 * e2] = b0;
-                    g[j][2 * e2 + 1] = b1;
-                    S0 = RT::add2(S0, b0);
-                    S1 = RT::add2(S1, b1);
+                    const float4 v = valid[j] ? *spiece(cs, j, e2) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    a[j][2 * e2] = make_float2(v.x, v.y);
+                    a[j][2 * e2 + 1] = make_float2(v.z, v.w);
+                }
+            tl = ctail;
+            if (tail_lane) stail[cs * 32 + lane] = tl;
+#pragma unroll
+            for (int r = 1; r < CK; r++) {
+                if (r < nb) {
+                    V2 d0 = make_float2(0.f, 0.f), d1 = d0;
+                    advance(cin[r], csc[r].x, d0, d1);
+                    if (csc[r].y != 1.f) scale_state(csc[r].y);
+#pragma unroll
+                    for (int j = 0; j < WPT; j++)
+                        if (valid[j]) {
+#pragma unroll
+                            for (int e2 = 0; e2 < 8; e2++)
+                                *spiece(2 + (r - 1), j, e2) = make_float4(a[j][2 * e2].x, a[j][2 * e2].y, a[j][2 * e2 + 1].x, a[j][2 * e2 + 1].y);
+                        }
+                    if (tail_lane) stail[(2 + (r - 1)) * 32 + lane] = tl;
                 }
             }
-            ring_issue(i - RING, rslot); // the slot just consumed receives row i-RING
-            rslot = (rslot + 1 == RING) ? 0 : rslot + 1;
-            S0 = RT::add2(S0, S1);
-            T Sl = S0.x + S0.y;
-            if (tail_warp) {
-                T b = ((i == m) ? gt : gt + Rp) * tailmul;
-                if (tail_lane) row[tail_off + lane] = tail_a * b;
-                if (tmw & lanebit) b *= tau;
-                gt = b;
-                Sl += b;
-            }
-            const T G = reduce(Sl, par ^= 1);
-            const T B = chk * G;
-            // log-scale of the row (thread 0): float accumulations exactly as the reference orders them
-            float lsi = 0.f;
-            if (t == 0) {
-                lsi = ls_cur;
-                if (i == m) lsi = lsi + P.ls_beta[k];
-                else {
-                    prevb += (i + 1 == m) ? nor_last : norb_cur;
-                    lsi = (float)((double)lsi + prevb);
+            // ---- backward over the block ----
+#pragma unroll
+            for (int r = CK - 1; r >= 0; r--) {
+                if (r < nb) {
+                    const int i = b0 + r;
+                    const int slot = (r == 0) ? cs : 2 + (r - 1);
+                    float *row = top + (size_t)i * pitch;
+                    const T ccur = cq.pop_push(pe[i - 2].c);
+                    const float ls_cur = lsq.pop_push(lsrow[max(i - 3, 0)]);
+                    const double norb_cur = norbq.pop_push(pnor[max(i - 2, 0)]); // pnor[i+1]
+                    uint32_t mw[WPT], tmw;
+                    expand(cin[r], mw, tmw);
+                    V2 S0 = make_float2(0.f, 0.f), S1 = S0;
+                    if (i == m) { // b_m = beta_end (:895-909)
+                        const float *be = P.beta_end + (size_t)k * N;
+#pragma unroll
+                        for (int j = 0; j < WPT; j++)
+#pragma unroll
+                            for (int e = 0; e < 16; e++) {
+                                const int n0 = (t * WPT + j) * 32;
+                                g[j][e] = make_float2(valid[j] ? be[n0 + ((2 * e + rot) & 31)] : 0.f,
+                                                      valid[j] ? be[n0 + ((2 * e + 1 + rot) & 31)] : 0.f);
+                            }
+                        if (tail_lane) gt = be[P.nfw * 32 + lane];
+                    }
+#pragma unroll
+                    for (int j = 0; j < WPT; j++) {
+                        const T Rj = (i == m) ? 0.f : Rp * vmul[j];
+                        const V2 R2 = make_float2(Rj, Rj);
+                        float4 *o = reinterpret_cast<float4 *>(row) + (size_t)(j * 8) * TT + t;
+#pragma unroll
+                        for (int e2 = 0; e2 < 8; e2++) {
+                            const float4 av = valid[j] ? *spiece(slot, j, e2) : make_float4(0.f, 0.f, 0.f, 0.f); // alpha_i
+                            V2 b0v = RT::add2(g[j][2 * e2], R2), b1v = RT::add2(g[j][2 * e2 + 1], R2);
+                            if (e2 == 0) b0v.x *= ownmul[j]; // b[k] = 0
+                            if (valid[j]) o[(size_t)e2 * TT] = make_float4(av.x * b0v.x, av.y * b0v.y, av.z * b1v.x, av.w * b1v.y);
+                            if (mw[j] & (1u << (4 * e2))) b0v.x *= tau;
+                            if (mw[j] & (2u << (4 * e2))) b0v.y *= tau;
+                            if (mw[j] & (4u << (4 * e2))) b1v.x *= tau;
+                            if (mw[j] & (8u << (4 * e2))) b1v.y *= tau;
+                            g[j][2 * e2] = b0v;
+                            g[j][2 * e2 + 1] = b1v;
+                            S0 = RT::add2(S0, b0v);
+                            S1 = RT::add2(S1, b1v);
+                        }
+                    }
+                    S0 = RT::add2(S0, S1);
+                    T Sl = S0.x + S0.y;
+                    if (tail_warp) {
+                        const float tail_a = tail_lane ? stail[slot * 32 + lane] : 0.f;
+                        T b = ((i == m) ? gt : gt + Rp) * tailmul;
+                        if (tail_lane) row[tail_off + lane] = tail_a * b;
+                        if (tmw & lanebit) b *= tau;
+                        gt = b;
+                        Sl += b;
+                    }
+                    const T G = reduce(Sl, par ^= 1);
+                    const T B = chk * G;
+                    // log-scale of the row (thread 0): float accumulations exactly as the reference orders them
+                    float lsi = 0.f;
+                    if (t == 0) {
+                        lsi = ls_cur;
+                        if (i == m) lsi = lsi + P.ls_beta[k];
+                        else {
+                            prevb += (i + 1 == m) ? nor_last : norb_cur;
+                            lsi = (float)((double)lsi + prevb);
+                        }
+                    }
+                    if (i < m && (B < K.lower || B > K.upper)) {
+                        const T inv = 1.f / B;
+#pragma unroll
+                        for (int j = 0; j < WPT; j++)
+#pragma unroll
+                            for (int e = 0; e < 16; e++) { g[j][e].x *= inv; g[j][e].y *= inv; }
+                        gt *= inv;
+                        const double lg = log((double)B);
+                        prevb += lg;
+                        lsi = (float)((double)lsi + lg);
+                        Rp = resc_R;
+                    } else {
+                        Rp = G;
+                    }
+                    Rp *= (i == m) ? (T)c_last : ccur;
+                    if (t == 0) lsrow[i] = lsi;
                 }
             }
-            if (i < m && (B < K.lower || B > K.upper)) {
-                const T inv = 1.f / B;
-#pragma unroll
-                for (int j = 0; j < WPT; j++)
-#pragma unroll
-                    for (int e = 0; e < 16; e++) { g[j][e].x *= inv; g[j][e].y *= inv; }
-                gt *= inv;
-                const double lg = log((double)B);
-                prevb += lg;
-                lsi = (float)((double)lsi + lg);
-                Rp = resc_R;
-            } else {
-                Rp = G;
-            }
-            Rp *= (i == m) ? (T)c_last : ccur;
-            if (t == 0) lsrow[i] = lsi;
+            ck_issue(jb - 2, cs); // the ring slot just consumed receives the checkpoint of block jb-2
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
 }
 

@@ -832,7 +832,7 @@ def test_paint_chunk_reads_the_hapbits_sidecar_and_removes_it(tmp_path, painting
     mp = str(tmp_path / "in.map")
     chunkio.write_uniform_map(mp, bp)
     for tag, bits in (("plain", False), ("bits", True)):
-        capi.make_chunks(hp, sp, mp, str(tmp_path / tag), memory_gb=0.002, hapbits=bits)
+        capi.make_chunks(hp, sp, mp, str(tmp_path / tag), memory_gb=0.004, hapbits=bits)
     assert os.path.exists(str(tmp_path / "bits" / "chunk_0.hapbits"))
     before = set(os.listdir(str(tmp_path / "plain")))
     sa = capi.paint_chunk(str(tmp_path / "plain"), 0, painting)
