@@ -260,6 +260,37 @@ def chunk_wb(chunk):
     return chunk._wb
 
 
+def resident_leg(out_dir, device, N, reps=3):
+    """Chunk files -> first N x N distance matrix on the host without any paint file (the consumer-side product path of
+    INTEGRATION.md section 4): rp_chunk_load + rp_paint_targets_device(all targets) + rp_window_open_resident(window 0)
+    + rp_window_distance(first SNP of the window), host wall clock per repetition."""
+    import numpy as np
+    from relate_b200 import capi, chunkio
+    rpos = chunkio.read_chunk(out_dir, 0).rpos
+    d = capi.pinned_empty((N, N), np.float32)
+    runs, parts = [], {}
+    for _ in range(1 + reps):
+        t0 = time.perf_counter()
+        with capi.DeviceChunk.load(out_dir, 0, PAINTING, device=device) as c:
+            t1 = time.perf_counter()
+            st = c.paint_targets_device(0, N)
+            t2 = time.perf_counter()
+            with capi.Window.open_resident(c, 0, rpos) as win:
+                t3 = time.perf_counter()
+                win.distance(0, out=d)
+                t4 = time.perf_counter()
+                rows, ms_rep = win.rows, win.stats["ms_paint"]
+        runs.append(time.perf_counter() - t0)
+        parts = {"ms_load_h2d_pack": 1e3 * (t1 - t0), "ms_paint_call": 1e3 * (t2 - t1), "ms_paint_kernel": st["ms_paint"],
+                 "ms_window_open": 1e3 * (t3 - t2), "ms_repaint_kernel": ms_rep, "ms_distance_call": 1e3 * (t4 - t3)}
+    warm = sorted(runs[1:])
+    assert np.isfinite(d).all() and float(np.abs(np.diag(d)).max()) == 0.0
+    return {"call": "rp_chunk_load -> rp_paint_targets_device(0..N) -> rp_window_open_resident(0) -> rp_window_distance(snp 0): "
+                    "chunk files in, first N x N distance matrix on the host, no paint files",
+            "seconds": warm[len(warm) // 2], "runs_ms": [round(1e3 * t, 2) for t in runs], "first_call_ms": 1e3 * runs[0],
+            "window0_posterior_rows": int(rows), "breakdown_ms": parts}
+
+
 def _md5_files(paths):
     """md5 over the concatenation order-independent digest list of the files (hashed in parallel threads)."""
     import hashlib
@@ -358,6 +389,12 @@ def sharded_leg(name, devices, peaks, reps=3):
                       "entries": nent, "entries_not_bit_identical": ndiff, "worst_rel_diff_decoded_stepping_stones": worst_vec,
                       "lens": "oracle/lens.py: ro_repaint_section + ro_matrix_row (pinned bit-identical to oracle/_ref/dlens) on the "
                               "decoded GPU records vs the fp64 oracle's stepping stones after the codec's collapse"}
+        if name == "config4":   # VERDICT r01 task 5: Paint + window-open wall on ONE GPU without paint files
+            try:
+                shutil.rmtree(os.path.join(out_dir, "chunk_0"), ignore_errors=True)
+                res["e2e_resident_1gpu"] = resident_leg(out_dir, devices[0], N, reps=2)
+            except Exception as e:
+                res["e2e_resident_1gpu"] = {"error": f"{type(e).__name__}: {e}"}
         return res
     finally:
         os.environ.pop("RP_IO_THREADS", None)
@@ -534,6 +571,10 @@ def main():
                 line["sharded_config4"] = sharded["config4"]
             if world == 1:
                 line["window_repaint"] = window_repaint_measure(chunk, rpos, W, peaks)
+                try:
+                    line["e2e_resident"] = dict(resident_leg(out_dir, local_rank, N_HAP), workload=WORKLOAD)
+                except Exception as e:
+                    line["e2e_resident"] = {"error": f"{type(e).__name__}: {e}"}
             if world == 1 and not args.no_cpu_baseline:
                 cb = cpu_baseline_sample()
                 line["cpu_baseline"] = cb

@@ -1498,20 +1498,29 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
         const int nblk = m / CK; // index of the last block
         ck_issue(nblk, nblk & 1);
         ck_issue(nblk - 1, (nblk - 1) & 1);
-        // per-block inputs, requested one block ahead: the rows' genotype words, their forward scalars, the checkpoint's tail
+        // per-block inputs, requested one block ahead: the rows' genotype words, their forward scalars, the checkpoint's
+        // tail; the rows' site indices (which the word loads depend on) two blocks ahead
         RowIn nin[CK];
         float2 nsc[CK];
         float ntail;
-        auto block_request = [&](int jb) {
+        int nsite[CK]; // sites of the block after next (the one block_request will serve next)
+        auto sites_request = [&](int jb) {
+            const int b0 = max(jb, 0) * CK;
+#pragma unroll
+            for (int r = 0; r < CK; r++) nsite[r] = pe[min(b0 + r, m)].site;
+        };
+        auto block_request = [&](int jb) { // uses nsite = the sites of block jb
             const int b0 = max(jb, 0) * CK;
 #pragma unroll
             for (int r = 0; r < CK; r++) {
-                nin[r] = fetch(pe[min(b0 + r, m)].site); // (rows past m are never used)
+                nin[r] = fetch(nsite[r]); // (rows past m are never used)
                 nsc[r] = sc[min(b0 + r, m)];
             }
             ntail = tail_lane ? top[(size_t)b0 * pitch + tail_off + lane] : 0.f;
         };
+        sites_request(nblk);
         block_request(nblk);
+        sites_request(nblk - 1);
         // small per-row streams walking down: c of the row, its log-scale (written by the forward sweep) and pnor[i+1]
         Ahead<float, 3> lsq;
         Ahead<double, 3> norbq;
@@ -1530,6 +1539,7 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             for (int r = 0; r < CK; r++) { cin[r] = nin[r]; csc[r] = nsc[r]; }
             const float ctail = ntail;
             block_request(jb - 1);
+            sites_request(jb - 2);
             const int cs = jb & 1;
             asm volatile("cp.async.wait_group 1;" ::: "memory"); // this block's checkpoint has landed (the next one may be in flight)
             // ---- recompute rows b0+1 .. b0+nb-1 from the checkpoint ----

@@ -9,7 +9,10 @@
 //     every other stage delegated to the reference binary;
 //   * every other mode is handed to the reference binary unchanged (exec).
 // The reference binary is found via $RELATE_REFERENCE_BIN, else "<dir of this exe>/Relate.ref".
-// Extra flags of this build (stripped before delegating): --gpus a,b,c   --fp64   --chunks a-b
+// Extra flags of this build (stripped before delegating): --gpus a,b,c   --fp64   --chunks a-b   --resident
+// `--resident` (modes BuildTopology and All) runs BuildTopology in `Relate_gpu` — the reference linked with this repo's
+// binding of DistanceMeasure::GetMatrix (relate_b200/integration/; found via $RELATE_GPU_BIN, else next to this
+// executable) — with the stepping stones kept in HBM: no paint files are written or read.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +25,7 @@
 #include <sstream>
 #include <string>
 #include <sys/resource.h>
+#include <sys/stat.h>
 #include <sys/time.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -68,6 +72,7 @@ const Flag kFlags[] = {
     {"gpus", 0, true, "(relate_b200) Comma-separated CUDA device indices for --mode Paint. Default: all visible."},
     {"fp64", 0, false, "(relate_b200) fp64 state in the painting kernel (verification mode)."},
     {"chunks", 0, true, "(relate_b200) --mode Paint: paint chunks a-b (instead of --chunk_index), whole chunks per GPU."},
+    {"resident", 0, false, "(relate_b200) BuildTopology / All: distance matrices from stepping stones resident in HBM (needs Relate_gpu); no paint files."},
 };
 
 void print_help()
@@ -135,7 +140,7 @@ bool parse(int argc, char **argv, Args &a, std::string &err)
         }
         a.present.insert(f->name);
         a.val[f->name] = value;
-        const bool ours = !strcmp(f->name, "gpus") || !strcmp(f->name, "fp64") || !strcmp(f->name, "chunks");
+        const bool ours = !strcmp(f->name, "gpus") || !strcmp(f->name, "fp64") || !strcmp(f->name, "chunks") || !strcmp(f->name, "resident");
         if (!ours) {
             a.passthrough.push_back(std::string("--") + f->name);
             if (f->has_value) a.passthrough.push_back(value);
@@ -155,8 +160,20 @@ std::string reference_binary(const char *argv0)
     return dir + "/Relate.ref";
 }
 
-// run the reference binary with `args`; returns its exit status (or 127)
-int run_reference(const std::string &bin, const std::vector<std::string> &args)
+// the reference linked with this repo's GetMatrix binding (relate_b200/integration/Makefile); "" if there is none
+std::string gpu_consumer_binary(const char *argv0)
+{
+    std::string p;
+    if (const char *e = getenv("RELATE_GPU_BIN")) p = e;
+    else {
+        const std::string ref = reference_binary(argv0);
+        p = ref.substr(0, ref.rfind('/') + 1) + "Relate_gpu";
+    }
+    return access(p.c_str(), X_OK) == 0 ? p : std::string();
+}
+
+// run the reference binary (or Relate_gpu) with `args`; returns its exit status (or 127).  resident: RELATE_GPU_RESIDENT=1
+int run_reference(const std::string &bin, const std::vector<std::string> &args, bool resident = false)
 {
     if (access(bin.c_str(), X_OK) != 0) {
         std::cerr << "relate: this build implements --mode Paint only; set RELATE_REFERENCE_BIN (or place the reference binary at "
@@ -169,6 +186,7 @@ int run_reference(const std::string &bin, const std::vector<std::string> &args)
     av.push_back(nullptr);
     pid_t pid = fork();
     if (pid == 0) {
+        if (resident) setenv("RELATE_GPU_RESIDENT", "1", 1);
         execv(bin.c_str(), av.data());
         _exit(127);
     }
@@ -331,6 +349,23 @@ int main(int argc, char **argv)
         return paint(a, atoi(a.get("chunk_index").c_str()));
     }
 
+    const bool resident = a.count("resident") != 0;
+    std::string gpu_bin;
+    if (resident) {
+        gpu_bin = gpu_consumer_binary(argv[0]);
+        if (gpu_bin.empty()) {
+            std::cerr << "relate: --resident needs Relate_gpu (make -C relate_b200/integration REF=<reference checkout>; or set RELATE_GPU_BIN)." << std::endl;
+            return 1;
+        }
+    }
+    if (mode == "BuildTopology" && resident) { // Relate.cpp:81-115 with the distance matrices from the GPU
+        if (a.count("output") && !a.count("help")) {
+            const std::string cdir = a.get("output") + "/chunk_" + (a.count("chunk_index") ? a.get("chunk_index") : std::string("0"));
+            mkdir(cdir.c_str(), 0700); // (the directory Paint would have created; BuildTopology writes its .anc/.mut there)
+        }
+        return run_reference(gpu_bin, a.passthrough, true);
+    }
+
     if (mode == "All") { // Relate.cpp:190-296 with Paint native
         if (a.count("help") || !a.count("output") ||
             (!a.count("chunk_index") && (!a.count("haps") || !a.count("sample") || !a.count("map"))))
@@ -340,7 +375,7 @@ int main(int argc, char **argv)
         if (a.count("chunk_index")) {
             start_chunk = end_chunk = atoi(a.get("chunk_index").c_str());
         } else {
-            int rc = make_chunks(a, /*paint_follows=*/true);
+            int rc = make_chunks(a, /*paint_follows=*/!resident); // (with --resident no Paint stage runs that would consume the sidecar)
             if (rc != 0) return rc;
             int hdr[3];
             if (!read_ints(out + "/parameters.bin", hdr, 3)) {
@@ -372,14 +407,22 @@ int main(int argc, char **argv)
             }
             const int num_sections = hdr[2] - 1;
             const std::string cs = std::to_string(c), ls = std::to_string(num_sections - 1);
-            if (!ahead) ahead = start_paint(c);
-            int rc = ahead->rc.get();
-            std::cerr << ahead->log.str();
-            ahead.reset();
-            if (rc) return rc;
-            if (c < end_chunk) ahead = start_paint(c + 1);
-            // (an error return below waits for the background painter: a std::async future joins in its destructor)
-            if ((rc = run_reference(ref, with_mode(a, "BuildTopology", {"--chunk_index", cs, "--first_section", "0", "--last_section", ls})))) return rc;
+            int rc = 0;
+            if (resident) {
+                // no Paint stage and no paint files: BuildTopology (Relate_gpu) paints the chunk inside its own process
+                // and opens every window from the stepping stones it keeps in HBM
+                mkdir((out + "/chunk_" + cs).c_str(), 0700);
+                if ((rc = run_reference(gpu_bin, with_mode(a, "BuildTopology", {"--chunk_index", cs, "--first_section", "0", "--last_section", ls}), true))) return rc;
+            } else {
+                if (!ahead) ahead = start_paint(c);
+                rc = ahead->rc.get();
+                std::cerr << ahead->log.str();
+                ahead.reset();
+                if (rc) return rc;
+                if (c < end_chunk) ahead = start_paint(c + 1);
+                // (an error return below waits for the background painter: a std::async future joins in its destructor)
+                if ((rc = run_reference(ref, with_mode(a, "BuildTopology", {"--chunk_index", cs, "--first_section", "0", "--last_section", ls})))) return rc;
+            }
             if ((rc = run_reference(ref, with_mode(a, "FindEquivalentBranches", {"--chunk_index", cs})))) return rc;
             if (a.count("postprocess")) {
                 if ((rc = run_reference(ref, with_mode(a, "PostProcess", {"--chunk_index", cs})))) return rc;

@@ -1,16 +1,19 @@
-// bt_gpu_shim.cpp — the reference-side binding of INTEGRATION.md section 4, made real for the tests.
+// distance_measure_gpu.cpp — the reference-side binding that lets `Relate --mode BuildTopology` take its distance
+// matrices from the GPU.  PRODUCT artefact: relate_b200/integration/Makefile links it with a
+// reference checkout into `Relate_gpu`; this repo's CLI runs that binary for `--mode BuildTopology` / `--mode All`
+// when it is present, and with `--resident` Paint -> d_ij never touches the disk.
 //
-// TEST INFRASTRUCTURE ONLY (see oracle/Makefile, target _ref/Relate_gpu).  The UNMODIFIED reference is compiled
-// from /root/reference as for _ref/Relate; in a copy of its anc_builder.o the one symbol
-// DistanceMeasure::GetMatrix(int) is weakened (objcopy --weaken-symbol), and this file supplies the strong
-// definition: the body a maintainer would write to let BuildTopology take its distance matrices from the GPU
-// (rp_window_open_files = RePaintSection for every target of the window, src/fast_painting.cpp:620-1092 as driven by
-// DistanceMeasure::GetTopologyWithRepaint, src/anc_builder.cpp:48-106; rp_window_distance = GetMatrix,
-// src/anc_builder.cpp:108-207).  Everything else of `Relate --mode BuildTopology` (MinMatch tree building, mutation
-// mapping, the .anc/.mut writers) is the reference's own code, so "identical downstream topologies from GPU d_ij"
-// is checked by the reference itself.
+// It is the body a maintainer would give DistanceMeasure::GetMatrix(int) (src/anc_builder.cpp:108-207, which calls
+// GetTopologyWithRepaint, :48-106): rp_window_open_files / rp_window_open_resident = RePaintSection for every target of
+// the window (src/fast_painting.cpp:620-1092), rp_window_distance = GetMatrix.  The reference's sources are not edited
+// and none of them is copied: the class is used through the reference's own header, and at link time the one symbol
+// DistanceMeasure::GetMatrix(int) is weakened in a copy of the reference's anc_builder.o (objcopy --weaken-symbol) so
+// that this strong definition wins.  Everything else of BuildTopology (MinMatch tree building, mutation mapping, the
+// .anc/.mut writers) stays the reference's own code.
 //
-// No reference source is copied: the class is used through the reference's own header.
+//   RELATE_GPU_RESIDENT=1   no paint files: paint every target once inside this process, keep the stepping stones in
+//                           HBM and open each window from there (bit-identical matrices to the file round trip)
+//   RELATE_GPU_DEVICE=<i>   CUDA device (default 0)
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -19,7 +22,7 @@
 #include "anc_builder.hpp"
 #include "data.hpp"
 
-#include "../include/relate_paint.h"
+#include "relate_paint.h" // this repo's include/
 
 namespace {
 
@@ -69,7 +72,8 @@ void open_chunk(Data &data)
     if (fread(g.wb.data(), 4, nb, fp) != (size_t)nb) exit(1);
     fclose(fp);
     // the chunk as BuildTopology holds it: theta from --painting, r already multiplied by rho
-    if (rp_chunk_create(0, data.N, data.L, &data.sequence[0][0], data.r.data(), g.wb.data(), nb, data.theta, 0,
+    const int device = getenv("RELATE_GPU_DEVICE") ? atoi(getenv("RELATE_GPU_DEVICE")) : 0;
+    if (rp_chunk_create(device, data.N, data.L, &data.sequence[0][0], data.r.data(), g.wb.data(), nb, data.theta, 0,
                         &g.chunk) != RP_OK)
         die("rp_chunk_create");
     g.data = &data;

@@ -803,6 +803,17 @@ def test_cli_mode_all_with_paint_ahead_equals_reference_all(tmp_path, have_ref):
     same = sum(clade_sets(pa[x], 16) == clade_sets(pb[x], 16) for x in shared)
     print(f"--mode All fp32 vs reference: {len(ta)} / {len(tb)} trees, {len(shared)} at shared positions, {same} with identical clade sets")
     assert len(shared) >= 0.98 * len(ta) and same >= 0.98 * len(shared)
+    # the file-less product path: `--resident` runs BuildTopology in Relate_gpu (the reference linked with the GetMatrix
+    # binding of relate_b200/integration/) with the stepping stones kept in HBM: no Paint stage, no paint files, and
+    # the same bytes as the fp32 file path above
+    if os.access(oracle.REF_RELATE_GPU, os.X_OK):
+        p = subprocess.run([EXE] + common + ["-o", "gres", "--resident"], cwd=d, capture_output=True, text=True,
+                           env=dict(env, RELATE_GPU_BIN=oracle.REF_RELATE_GPU))
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert "Painting sequences..." not in p.stderr
+        for ext in ("anc", "mut"):
+            assert filecmp.cmp(os.path.join(d, f"g32.{ext}"), os.path.join(d, f"gres.{ext}"), shallow=False), ext
+        assert not os.path.exists(os.path.join(d, "gres"))
 
 
 def test_small_batches_and_the_copy_pipeline_give_the_same_files(tmp_path, monkeypatch):
