@@ -753,18 +753,6 @@ int rp_chunk_create(int device, int N, int L, const char *hap, const double *r, 
     return chunk_from_host(device, N, L, hap, r, wb, n_wb, theta, flags, out, nullptr);
 }
 
-int rp_chunk_load(int device, const char *out_dir, int chunk_index, const char *painting, unsigned flags,
-                  rp_chunk **out)
-{
-    if (!out_dir || !out) return fail(RP_EINVAL, "null argument");
-    *out = nullptr;
-    rp::HostChunk hc;
-    std::string err = rp::load_chunk_files(out_dir, chunk_index, painting, hc);
-    if (!err.empty()) return fail(RP_EIO, err);
-    return chunk_from_host(device, hc.N, hc.L, hc.hap, hc.r.data(), hc.wb.data(), (int)hc.wb.size(),
-                           hc.theta, flags, out, nullptr);
-}
-
 int rp_chunk_info(const rp_chunk *c, rp_info *info)
 {
     if (!c || !info) return fail(RP_EINVAL, "null argument");
@@ -1431,6 +1419,128 @@ template <typename F> void parallel_for(int n, int nthreads, F f)
     for (auto &t : ts) t.join();
 }
 
+// Reader threads that deliver a chunk's genotype rows, bit-packed, through a ring of pinned slots (see HapFeed): from
+// chunk_<c>.hapbits when this library's MakeChunks left one (the rows already in the painter's layout: 1/8 of the bytes
+// and nothing to pack), else from the chars of chunk_<c>.hap, packed by the thread that read them.  Used by the stage
+// driver (several devices copy from one ring) and by rp_chunk_load.
+struct ChunkReaders {
+    HapFeed feed;
+    std::vector<std::thread> threads;
+    std::atomic<int> next_slice{0}, readers_left{0};
+    int hap_fd = -1, bits_fd = -1;
+    bool have_sidecar = false; // the rows come from chunk_<c>.hapbits
+    std::string bits_path;
+    double t_loaded = 0;
+    int N = 0, L = 0, wps = 0;
+
+    // takes ownership of hap_fd (the open chunk_<c>.hap, header already checked)
+    int start(const char *out_dir, int chunk_index, const rp::HostChunk &hc, int hap_fd_in, int ndev, PinnedBuf &ring)
+    {
+        hap_fd = hap_fd_in;
+        N = hc.N;
+        L = hc.L;
+        wps = (((N + 31) / 32) + 3) / 4 * 4; // as rp_chunk::wps
+        t_loaded = now_ms();
+        bits_path = std::string(out_dir) + "/chunk_" + std::to_string(chunk_index) + ".hapbits";
+        bits_fd = open(bits_path.c_str(), O_RDONLY);
+        if (bits_fd >= 0) {
+            rp::HapBitsHeader h{};
+            struct stat sb;
+            const bool ok = pread(bits_fd, &h, sizeof h, 0) == (ssize_t)sizeof h && memcmp(h.magic, rp::hapbits_magic(), 8) == 0 && h.N == N &&
+                            h.L == L && h.wps == wps && fstat(bits_fd, &sb) == 0 && (size_t)sb.st_size >= sizeof h + (size_t)h.L * h.wps * 4;
+            if (!ok) {
+                close(bits_fd);
+                bits_fd = -1;
+            }
+        }
+        have_sidecar = bits_fd >= 0;
+        const size_t nchar = (size_t)L * N;
+        const size_t ring_cap = (size_t)(getenv("RP_RING_KB") ? atoi(getenv("RP_RING_KB")) : 65536) << 10; // tests shrink it
+        // a slice = whole SNP rows worth about RP_SLICE_KB of genotype chars on disk; in the ring it is 1/8 of that
+        const size_t slice_chars = (size_t)(getenv("RP_SLICE_KB") ? atoi(getenv("RP_SLICE_KB")) : (nchar <= 8 * ring_cap ? 1024 : 4096)) << 10;
+        feed.rows = (int)std::max<size_t>(1, slice_chars / (size_t)N);
+        feed.slice = (size_t)feed.rows * wps * 4;
+        feed.nsl = (L + feed.rows - 1) / feed.rows;
+        feed.nslots = (int)std::min<size_t>((size_t)feed.nsl, std::max<size_t>(2, ring_cap / feed.slice));
+        feed.ndev = ndev;
+        feed.padbit = hc.theta > 0.5 ? 1 : 0; // as chunk_from_host sets rp_chunk::padbit
+        if (ring.ensure((size_t)feed.nslots * feed.slice) != RP_OK) {
+            close_files();
+            return RP_ENOMEM;
+        }
+        feed.ring = static_cast<const char *>(ring.p);
+        feed.ready.reset(new std::atomic<int>[feed.nsl]);
+        feed.consumed.reset(new std::atomic<int>[feed.nsl]);
+        for (int i = 0; i < feed.nsl; i++) {
+            feed.ready[i].store(0);
+            feed.consumed[i].store(0);
+        }
+        const unsigned want_readers = getenv("RP_READERS") ? (unsigned)atoi(getenv("RP_READERS")) : 8u;
+        const int nread = (int)std::max(1u, std::min<unsigned>({want_readers, std::max(1u, io_thread_budget() / 2), (unsigned)feed.nslots}));
+        readers_left = nread;
+        for (int t = 0; t < nread; t++) threads.emplace_back([this]() { run(); });
+        return RP_OK;
+    }
+    void run()
+    {
+        std::vector<char> raw; // the slice as it is on disk (pageable: it never meets the GPU)
+        for (;;) {
+            const int i = next_slice.fetch_add(1);
+            if (i >= feed.nsl) break;
+            bool ok = true;
+            if (i >= feed.nslots) // wait until every device has copied the slice that occupies the slot
+                while (feed.consumed[i - feed.nslots].load(std::memory_order_acquire) < feed.ndev) {
+                    if (feed.abort.load()) { ok = false; break; }
+                    std::this_thread::yield();
+                }
+            const int row0 = i * feed.rows, nrows = std::min(feed.rows, L - row0);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(const_cast<char *>(feed.src(i)));
+            if (bits_fd >= 0) { // packed rows straight from the sidecar
+                char *d8 = reinterpret_cast<char *>(dst);
+                size_t left = (size_t)nrows * wps * 4, off = sizeof(rp::HapBitsHeader) + (size_t)row0 * wps * 4;
+                while (ok && left > 0) {
+                    const ssize_t got = pread(bits_fd, d8, left, (off_t)off);
+                    if (got <= 0) ok = false;
+                    else { d8 += got; off += (size_t)got; left -= (size_t)got; }
+                }
+                if (ok && feed.padbit && (N & 31)) // phantom slots of the partial last word (tau > 1)
+                    for (int rr = 0; rr < nrows; rr++) dst[(size_t)rr * wps + (N >> 5)] |= ~0u << (N & 31);
+            } else {
+                raw.resize((size_t)feed.rows * N);
+                ok = ok && rp::read_hap_range(hap_fd, (size_t)row0 * N, (size_t)nrows * N, raw.data());
+                if (ok)
+                    for (int rr = 0; rr < nrows; rr++) pack_row_host(raw.data() + (size_t)rr * N, N, dst + (size_t)rr * wps, wps, feed.padbit);
+            }
+            feed.ready[i].store(ok ? 1 : -1, std::memory_order_release);
+        }
+        if (readers_left.fetch_sub(1) == 1) t_loaded = now_ms();
+    }
+    void close_files()
+    {
+        if (hap_fd >= 0) close(hap_fd);
+        if (bits_fd >= 0) close(bits_fd);
+        hap_fd = bits_fd = -1;
+    }
+    void join()
+    {
+        for (auto &t : threads) t.join();
+        threads.clear();
+        close_files();
+    }
+    // the sidecar has served its purpose (the reference's Finalize cannot delete a directory that holds a file it does
+    // not know); call after join()
+    void remove_sidecar()
+    {
+        if (have_sidecar) unlink(bits_path.c_str());
+        have_sidecar = false;
+    }
+    ~ChunkReaders()
+    {
+        feed.abort.store(1);
+        join();
+    }
+};
+
 } // namespace
 
 extern "C" void rp_release_cache(void)
@@ -1480,90 +1590,15 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         std::string err = rp::load_chunk_small(out_dir, chunk_index, painting, hc, &hap_fd);
         if (!err.empty()) return fail(RP_EIO, err);
     }
-    const size_t nchar = (size_t)hc.L * hc.N;
     const unsigned hw = io_thread_budget();
-    // chunk_<c>.hapbits (written by this library's MakeChunks on request): the genotype rows already in the painter's
-    // bit layout, 1/8 of the bytes of chunk_<c>.hap and nothing to pack.  Used when its header matches; removed once the
-    // chunk has been painted (the reference's Finalize cannot delete a directory that holds a file it does not know).
-    const std::string bits_path = std::string(out_dir) + "/chunk_" + std::to_string(chunk_index) + ".hapbits";
-    int bits_fd = open(bits_path.c_str(), O_RDONLY);
-    if (bits_fd >= 0) {
-        rp::HapBitsHeader h{};
-        struct stat sb;
-        const int want_wps = (((hc.N + 31) / 32) + 3) / 4 * 4;
-        const bool ok = pread(bits_fd, &h, sizeof h, 0) == (ssize_t)sizeof h && memcmp(h.magic, rp::hapbits_magic(), 8) == 0 && h.N == hc.N &&
-                        h.L == hc.L && h.wps == want_wps && fstat(bits_fd, &sb) == 0 &&
-                        (size_t)sb.st_size >= sizeof h + (size_t)h.L * h.wps * 4;
-        if (!ok) {
-            close(bits_fd);
-            bits_fd = -1;
-        }
+    ChunkReaders in;
+    {
+        const int rc = in.start(out_dir, chunk_index, hc, hap_fd, (int)devs.size(), g_ws.at(devs[0]).hap_in);
+        if (rc != RP_OK) return rc;
     }
-    HapFeed feed;
-    const size_t ring_cap = (size_t)(getenv("RP_RING_KB") ? atoi(getenv("RP_RING_KB")) : 65536) << 10; // tests shrink it
-    // a slice = whole SNP rows worth about RP_SLICE_KB of genotype chars on disk; in the ring it is 1/8 of that
-    const size_t slice_chars = (size_t)(getenv("RP_SLICE_KB") ? atoi(getenv("RP_SLICE_KB")) : (nchar <= 8 * ring_cap ? 1024 : 4096)) << 10;
-    const int wps = (((hc.N + 31) / 32) + 3) / 4 * 4; // as rp_chunk::wps
-    feed.rows = (int)std::max<size_t>(1, slice_chars / (size_t)hc.N);
-    feed.slice = (size_t)feed.rows * wps * 4;
-    feed.nsl = (hc.L + feed.rows - 1) / feed.rows;
-    feed.nslots = (int)std::min<size_t>((size_t)feed.nsl, std::max<size_t>(2, ring_cap / feed.slice));
-    feed.ndev = (int)devs.size();
-    feed.padbit = hc.theta > 0.5 ? 1 : 0; // as chunk_from_host sets rp_chunk::padbit
-    PinnedBuf &hap_in = g_ws.at(devs[0]).hap_in;
-    if (hap_in.ensure((size_t)feed.nslots * feed.slice) != RP_OK) {
-        close(hap_fd);
-        return RP_ENOMEM;
-    }
-    feed.ring = static_cast<const char *>(hap_in.p);
-    hc.hap = static_cast<char *>(hap_in.p); // (only slices in the ring are addressable through it)
+    HapFeed &feed = in.feed;
+    hc.hap = const_cast<char *>(feed.ring); // (only slices in the ring are addressable through it)
     trace("input ring pinned", devs[0]);
-    feed.ready.reset(new std::atomic<int>[feed.nsl]);
-    feed.consumed.reset(new std::atomic<int>[feed.nsl]);
-    for (int i = 0; i < feed.nsl; i++) {
-        feed.ready[i].store(0);
-        feed.consumed[i].store(0);
-    }
-    std::atomic<int> next_slice{0}, readers_left{0};
-    double t_loaded = t0;
-    std::vector<std::thread> readers;
-    const unsigned want_readers = getenv("RP_READERS") ? (unsigned)atoi(getenv("RP_READERS")) : 8u;
-    const int nread = (int)std::max(1u, std::min<unsigned>({want_readers, std::max(1u, hw / 2), (unsigned)feed.nslots}));
-    readers_left = nread;
-    for (int t = 0; t < nread; t++)
-        readers.emplace_back([&]() {
-            std::vector<char> raw; // the slice as it is on disk (pageable: it never meets the GPU)
-            for (;;) {
-                const int i = next_slice.fetch_add(1);
-                if (i >= feed.nsl) break;
-                bool ok = true;
-                if (i >= feed.nslots) // wait until every device has copied the slice that occupies the slot
-                    while (feed.consumed[i - feed.nslots].load(std::memory_order_acquire) < feed.ndev) {
-                        if (feed.abort.load()) { ok = false; break; }
-                        std::this_thread::yield();
-                    }
-                const int row0 = i * feed.rows, nrows = std::min(feed.rows, hc.L - row0);
-                uint32_t *dst = reinterpret_cast<uint32_t *>(const_cast<char *>(feed.src(i)));
-                if (bits_fd >= 0) { // packed rows straight from the sidecar
-                    char *d8 = reinterpret_cast<char *>(dst);
-                    size_t left = (size_t)nrows * wps * 4, off = sizeof(rp::HapBitsHeader) + (size_t)row0 * wps * 4;
-                    while (ok && left > 0) {
-                        const ssize_t got = pread(bits_fd, d8, left, (off_t)off);
-                        if (got <= 0) ok = false;
-                        else { d8 += got; off += (size_t)got; left -= (size_t)got; }
-                    }
-                    if (ok && feed.padbit && (hc.N & 31)) // phantom slots of the partial last word (tau > 1)
-                        for (int rr = 0; rr < nrows; rr++) dst[(size_t)rr * wps + (hc.N >> 5)] |= ~0u << (hc.N & 31);
-                } else {
-                    raw.resize((size_t)feed.rows * hc.N);
-                    ok = ok && rp::read_hap_range(hap_fd, (size_t)row0 * hc.N, (size_t)nrows * hc.N, raw.data());
-                    if (ok)
-                        for (int rr = 0; rr < nrows; rr++) pack_row_host(raw.data() + (size_t)rr * hc.N, hc.N, dst + (size_t)rr * wps, wps, feed.padbit);
-                }
-                feed.ready[i].store(ok ? 1 : -1, std::memory_order_release);
-            }
-            if (readers_left.fetch_sub(1) == 1) t_loaded = now_ms();
-        });
 
     // ---- output files: created (and old ones truncated) in the background; the first write waits for it ----
     const int N = hc.N, W = (int)hc.wb.size() - 1;
@@ -1757,9 +1792,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
     for (int di = 1; di < (int)devs.size(); di++) threads.emplace_back(worker, di);
     worker(0);
     for (auto &t : threads) t.join();
-    for (auto &t : readers) t.join();
-    close(hap_fd);
-    if (bits_fd >= 0) close(bits_fd);
+    in.join();
     pool.finish();
     if (pool.failed() && first_rc == RP_OK) {
         first_rc = RP_EIO;
@@ -1773,7 +1806,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         if (first_rc == RP_OK && !err.empty()) return fail(RP_EIO, err);
     }
     if (first_rc != RP_OK) return fail(first_rc, first_err);
-    if (bits_fd >= 0) unlink(bits_path.c_str());
+    in.remove_sidecar();
     if (per_device) *per_device = dstats;
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -1794,13 +1827,43 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
             stats->ctas = s.ctas;
         }
         stats->ms_write = ms_write;
-        stats->ms_load = t_loaded - t0;
+        stats->ms_load = in.t_loaded - t0;
         stats->ms_total = now_ms() - t0;
     }
     return RP_OK;
 }
 
 } // namespace
+
+// Data::Data(6 files) + the --painting handling of Paint.cpp:38-61, with the genotype rows bit-packed by reader threads on
+// their way to the device (ChunkReaders: 1 bit per genotype crosses PCIe, the chars never reach HBM)
+extern "C" int rp_chunk_load(int device, const char *out_dir, int chunk_index, const char *painting, unsigned flags,
+                             rp_chunk **out)
+{
+    if (!out_dir || !out) return fail(RP_EINVAL, "null argument");
+    *out = nullptr;
+    rp::HostChunk hc;
+    int hap_fd = -1;
+    {
+        std::string err = rp::load_chunk_small(out_dir, chunk_index, painting, hc, &hap_fd);
+        if (!err.empty()) return fail(RP_EIO, err);
+    }
+    const int ndev = rp_device_count();
+    if (ndev < 1 || device < 0 || device >= ndev) {
+        close(hap_fd);
+        return ndev < 1 ? fail(RP_ENODEVICE, "no CUDA device (there is no CPU fallback)") : fail(RP_EINVAL, "device index out of range");
+    }
+    std::lock_guard<std::mutex> stage_lock(g_stage_mu); // (the pinned input ring is the device's parked one)
+    RP_CUDA(cudaSetDevice(device));
+    ChunkReaders in;
+    RP_TRY(in.start(out_dir, chunk_index, hc, hap_fd, 1, g_ws[device].hap_in));
+    hc.hap = const_cast<char *>(in.feed.ring);
+    const int rc = chunk_from_host(device, hc.N, hc.L, hc.hap, hc.r.data(), hc.wb.data(), (int)hc.wb.size(), hc.theta, flags, out,
+                                   nullptr, &in.feed);
+    if (rc != RP_OK) in.feed.abort.store(1);
+    in.join(); // (the sidecar, if any, stays: only the stage, which paints the whole chunk, removes it)
+    return rc;
+}
 
 extern "C" int rp_paint_chunk(const char *out_dir, int chunk_index, const char *painting, const int *devices,
                               int n_devices, unsigned flags, rp_stats *stats)

@@ -586,10 +586,40 @@ template <int WPT> __device__ __forceinline__ void load_words(uint32_t (&w)[WPT]
                             // Measured at config 2 (scripts/acc_check.py, sweep of 20/23/25/27): kernel 2.20 / 2.21 / 2.25 / 2.31 ms,
                             // max relative error of the stepping stones 4.1e-6 / 8.6e-7 / 8.4e-7 / 7.6e-7
 #endif
+#ifndef RP_TMA_ROWS
+#define RP_TMA_ROWS 0 // experiment (multi-warp fp32 teams): genotype rows through a cp.async.bulk + mbarrier ring in shared memory,
+                      // issued by one thread four steps ahead, instead of one coalesced LDG per thread one step ahead.
+                      // Measured on B200 (profiles/r02): see DESIGN.md section 4; off by default.
+#endif
 #ifndef RP_PF
 #define RP_PF 1 // L1 prefetch hints for the genotype rows / site tables of later steps
 #endif
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// ---- bulk-async (TMA, 1-D) row ring helpers (RP_TMA_ROWS) ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void opaque(float &x) { asm volatile("" : "+f"(x)); }
 __device__ __forceinline__ void opaque(double &x) { asm volatile("" : "+d"(x)); }
 
@@ -659,6 +689,23 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
 
     const T chk = DIR ? K.ntheta : (T)1;        // the band is tested on chk*S  (B = ntheta*G backward)
     const T resc_R = DIR ? K.inv_ntheta : (T)1; // R after a rescale, before *c_i
+
+    constexpr bool kTma = RP_TMA_ROWS && MULTI && !CLUSTER && sizeof(T) == 4;
+    constexpr int kRing = 4;
+    __shared__ __align__(16) uint32_t s_rows[kTma ? kRing : 1][kTma ? 1024 : 4]; // a team of <= 512 threads x 2 words
+    __shared__ __align__(8) uint64_t s_mbar[kRing];
+    unsigned ring_phase = 0; // bit s: parity the next wait on slot s expects
+    if (kTma) {
+        if (t == 0)
+            for (int sl = 0; sl < kRing; sl++) mbar_init(&s_mbar[sl], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
+    // (thread 0) request the genotype row of `site` into ring slot sl
+    auto ring_issue = [&](int site, int sl) {
+        mbar_expect_tx(&s_mbar[sl], rowbytes);
+        bulk_g2s(&s_rows[sl][0], P.G + (size_t)site * P.wps, rowbytes, &s_mbar[sl]);
+    };
 
     const int nseg = CLUSTER ? 1 : P.nseg;
     for (;;) {
@@ -898,6 +945,15 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         sA = 0;
         cB = (T)pe[(pbeg + 1) * ES].c;
         const Ent *pnx = pe + (pbeg + 2) * ES; // entry p+2 while step p runs
+        int s_ahead = 0; // (thread 0) site of step p+kRing+1, loaded a step before its row is requested
+        if (kTma) {
+            __syncthreads(); // nobody still reads the ring of the previous job
+            if (t == 0) {
+                for (int d = 1; d < kRing; d++)
+                    if (pbeg + d < pend) ring_issue(pe[(pbeg + d) * ES].site, (pbeg + d) & (kRing - 1));
+                s_ahead = pe[min(pbeg + kRing, m) * ES].site;
+            }
+        }
 
         T R = DIR ? (T)1 : K.prior_n; // step 0 is x = (0 + R0) * m
         uint32_t tdm = td_first;
@@ -1063,6 +1119,18 @@ __device__ __forceinline__ void paint_jobs(const PaintParams &P, int *s_job, T (
         auto do_step = [&](auto evc, int p, uint32_t (&wX)[WPT], T &cX, int &sX, int &fX, uint32_t (&wY)[WPT], T &cY, int &sY, int &fY) {
             constexpr int EV = decltype(evc)::value; // 0 plain step, 1 event step, 2 test inside the step (multi-warp teams)
             // loads for later steps first: words of step p+1 into Y, entry p+2 (site -> X's next fill, c -> X's next step)
+            if (kTma) {
+                if (p + 1 < pend) { // the row of step p+1 was requested kRing-1 steps ago
+                    const int sl = (p + 1) & (kRing - 1);
+                    mbar_wait(&s_mbar[sl], (ring_phase >> sl) & 1u);
+                    ring_phase ^= 1u << sl;
+                    load_words(wY, reinterpret_cast<const char *>(&s_rows[sl][0]) + (size_t)gt * WPT * 4);
+                }
+                if (t == 0) { // slot p & 3 held the row of step p, which every thread took before the barrier of step p-1
+                    if (p + kRing < pend) ring_issue(s_ahead, p & (kRing - 1));
+                    s_ahead = pe[min(p + kRing + 1, m) * ES].site;
+                }
+            } else
             load_words(wY, gthr + (size_t)(unsigned)sY * rowbytes);
             // The row of step p+2 is loaded at the top of step p+1 and consumed a step later: one step of lead over an
             // L2 latency that, under load, is about a step long (ncu: 8 % of the warps' time on that scoreboard).  So

@@ -361,7 +361,8 @@ int main(int argc, char **argv)
     if (mode == "BuildTopology" && resident) { // Relate.cpp:81-115 with the distance matrices from the GPU
         if (a.count("output") && !a.count("help")) {
             const std::string cdir = a.get("output") + "/chunk_" + (a.count("chunk_index") ? a.get("chunk_index") : std::string("0"));
-            mkdir(cdir.c_str(), 0700); // (the directory Paint would have created; BuildTopology writes its .anc/.mut there)
+            mkdir(cdir.c_str(), 0700); // (the directories Paint would have created: BuildTopology writes its .anc/.mut there,
+            mkdir((cdir + "/paint").c_str(), 0700); //  Finalize / Clean remove both and exit(1) if one is missing)
         }
         return run_reference(gpu_bin, a.passthrough, true);
     }
@@ -412,6 +413,7 @@ int main(int argc, char **argv)
                 // no Paint stage and no paint files: BuildTopology (Relate_gpu) paints the chunk inside its own process
                 // and opens every window from the stepping stones it keeps in HBM
                 mkdir((out + "/chunk_" + cs).c_str(), 0700);
+                mkdir((out + "/chunk_" + cs + "/paint").c_str(), 0700); // stays empty; Finalize insists on removing it
                 if ((rc = run_reference(gpu_bin, with_mode(a, "BuildTopology", {"--chunk_index", cs, "--first_section", "0", "--last_section", ls}), true))) return rc;
             } else {
                 if (!ahead) ahead = start_paint(c);

@@ -115,20 +115,29 @@ def test_dij_through_reference_getmatrix_on_full_config2(ref_runs):
     work = [(side, sec) for sec in range(W) for side in ("ref", "gpu")]
     with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 2)) as ex:  # ~5 GB of posterior per process
         outs = dict(zip(work, ex.map(lens, work)))
-    worst, nmat, nbig = 0.0, 0, 0
+    # GetMatrix adds the record's FLOAT log-scale to fast_log(posterior): d is quantised to the spacing of that float, which
+    # at L = 50 000 (|log-scale| up to ~8 000) is 4.9e-4, above the 6.9e-4/2 the survey measured its gate against at
+    # L = 20 000.  With fp32 state the stored log-scale of a record differs from the reference's by one such step in a
+    # fraction of a percent of the records (alpha's and beta's can both), so the gate is the survey's, but not below
+    # two steps of the coarsest log-scale in the window.
+    worst, worst_excess, nmat, nbig = 0.0, 0.0, 0, 0
     for sec in range(W):
+        recs = chunkio.read_paint_file(os.path.join(j["dir"], "ref", "o", "chunk_0", "paint", f"relate_{sec}.bin"), N)
+        ls_max = max(max(abs(float(ra.logscale)), abs(float(rb.logscale))) for _, _, ra, rb in recs)
+        tol = max(DTOL, 2.0 * float(np.spacing(np.float32(ls_max))))
         a, b = read_dlens(outs[("ref", sec)]), read_dlens(outs[("gpu", sec)])
         assert a.keys() == b.keys() and len(a) >= 5
         for snp in a:
             d = np.abs(a[snp].astype(np.float64) - b[snp])
             worst = max(worst, float(d.max()))
+            worst_excess = max(worst_excess, float(d.max()) / tol)
             nbig += int((d > 1e-4 * np.maximum(a[snp], 1.0)).sum())
             nmat += 1
         os.remove(outs[("ref", sec)])
         os.remove(outs[("gpu", sec)])
-    print(f"config 2 d_ij lens: {nmat} matrices over {W} windows, worst |dd| = {worst:.3e} (gate {DTOL:.2e}), "
-          f"{nbig} of {nmat * N * N} entries beyond 1e-4*max(d,1)")
-    assert worst <= DTOL
+    print(f"config 2 d_ij lens: {nmat} matrices over {W} windows, worst |dd| = {worst:.3e} (survey gate {DTOL:.2e}; "
+          f"worst / max(gate, 2 log-scale steps) = {worst_excess:.2f}), {nbig} of {nmat * N * N} entries beyond 1e-4*max(d,1)")
+    assert worst_excess <= 1.0
 
 
 def test_config4_shape_64_targets_vs_oracle():
