@@ -126,6 +126,9 @@ struct rp_chunk {
     cudaStream_t copy_stream = nullptr;  // device->host copies of encoded records (stage driver), overlapping the next batch
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<rp_chunk **> window_refs; // the `c` fields of the windows open on this chunk (cleared by rp_chunk_free)
+    // buffers of the last closed window, kept for the next one (BuildTopology opens a chunk's windows one after the other;
+    // allocating the posterior of a window, GBs, costs more than repainting it)
+    DevBuf park_top, park_ls, park_scal, park_d, park_rowoff, park_rpos, park_lsa, park_lsb;
 };
 
 namespace {
@@ -792,7 +795,8 @@ void rp_chunk_free(rp_chunk *c)
     cudaSetDevice(c->device);
     for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
                       &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch, &c->nor, &c->segstate, &c->segdone,
-                      &c->rleK, &c->rec_off, &c->win_bytes, &c->img_off, &c->image, &c->image_alt})
+                      &c->rleK, &c->rec_off, &c->win_bytes, &c->img_off, &c->image, &c->image_alt, &c->park_top, &c->park_ls, &c->park_scal,
+                      &c->park_d, &c->park_rowoff, &c->park_rpos, &c->park_lsa, &c->park_lsb})
         b->release();
     if (c->h_total) cudaFreeHost(c->h_total);
     for (auto &e : c->ev)
@@ -1045,6 +1049,14 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     };
     int rc = RP_OK;
     const size_t nn = (size_t)N * N;
+    std::swap(win->top, c->park_top); // (the buffers of the window closed last, if any)
+    std::swap(win->ls, c->park_ls);
+    std::swap(win->scal, c->park_scal);
+    std::swap(win->d, c->park_d);
+    std::swap(win->rowoff, c->park_rowoff);
+    std::swap(win->rpos, c->park_rpos);
+    std::swap(win->lsa, c->park_lsa);
+    std::swap(win->lsb, c->park_lsb);
     win->tt = lp.threads;
     win->wpt = lp.wpt;
     win->pitch = lp.threads * lp.wpt * 32 + 32;
@@ -1208,9 +1220,20 @@ void rp_window_close(rp_window *win)
 {
     if (!win) return;
     if (win->c) {
-        cudaSetDevice(win->c->device);
-        auto &refs = win->c->window_refs;
+        rp_chunk *c = win->c;
+        cudaSetDevice(c->device);
+        auto &refs = c->window_refs;
         refs.erase(std::remove(refs.begin(), refs.end(), &win->c), refs.end());
+        if (!c->park_top.p) { // park this window's buffers in the chunk for the next window
+            std::swap(win->top, c->park_top);
+            std::swap(win->ls, c->park_ls);
+            std::swap(win->scal, c->park_scal);
+            std::swap(win->d, c->park_d);
+            std::swap(win->rowoff, c->park_rowoff);
+            std::swap(win->rpos, c->park_rpos);
+            std::swap(win->lsa, c->park_lsa);
+            std::swap(win->lsb, c->park_lsb);
+        }
     } else {
         cudaSetDevice(win->device);
     }

@@ -115,16 +115,18 @@ def test_dij_through_reference_getmatrix_on_full_config2(ref_runs):
     work = [(side, sec) for sec in range(W) for side in ("ref", "gpu")]
     with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 2)) as ex:  # ~5 GB of posterior per process
         outs = dict(zip(work, ex.map(lens, work)))
-    # GetMatrix adds the record's FLOAT log-scale to fast_log(posterior): d is quantised to the spacing of that float, which
-    # at L = 50 000 (|log-scale| up to ~8 000) is 4.9e-4, above the 6.9e-4/2 the survey measured its gate against at
-    # L = 20 000.  With fp32 state the stored log-scale of a record differs from the reference's by one such step in a
-    # fraction of a percent of the records (alpha's and beta's can both), so the gate is the survey's, but not below
-    # two steps of the coarsest log-scale in the window.
+    # GetMatrix forms d = -(fast_log(posterior) + logscale) - rowmin in FLOAT arithmetic (anc_builder.cpp:123-131,190-192): every
+    # entry is rounded to the float spacing at |logscale| (2.44e-4 below 4096, 4.9e-4 above), and so is the row minimum.
+    # With fp32 state the stored log-scale of a record differs from the reference's by one such step in a fraction of a
+    # percent of the records, the posterior by ~1e-6: an entry can land one step away through each of the three roundings
+    # (the sum, the shifted log-scale, the minimum).  Measured on the full config 2 chunk: worst |dd| = 7.324e-4 = exactly 3
+    # steps, 804 of 41 000 000 entries beyond 1e-4*max(d,1).  The gate is the survey's 6.9e-4 (its probe at L = 20 000 saw
+    # one step), but not below three steps of the coarsest log-scale in the window.
     worst, worst_excess, nmat, nbig = 0.0, 0.0, 0, 0
     for sec in range(W):
         recs = chunkio.read_paint_file(os.path.join(j["dir"], "ref", "o", "chunk_0", "paint", f"relate_{sec}.bin"), N)
         ls_max = max(max(abs(float(ra.logscale)), abs(float(rb.logscale))) for _, _, ra, rb in recs)
-        tol = max(DTOL, 2.0 * float(np.spacing(np.float32(ls_max))))
+        tol = max(DTOL, 3.0 * float(np.spacing(np.float32(ls_max))) * (1 + 1e-6))
         a, b = read_dlens(outs[("ref", sec)]), read_dlens(outs[("gpu", sec)])
         assert a.keys() == b.keys() and len(a) >= 5
         for snp in a:
@@ -136,7 +138,7 @@ def test_dij_through_reference_getmatrix_on_full_config2(ref_runs):
         os.remove(outs[("ref", sec)])
         os.remove(outs[("gpu", sec)])
     print(f"config 2 d_ij lens: {nmat} matrices over {W} windows, worst |dd| = {worst:.3e} (survey gate {DTOL:.2e}; "
-          f"worst / max(gate, 2 log-scale steps) = {worst_excess:.2f}), {nbig} of {nmat * N * N} entries beyond 1e-4*max(d,1)")
+          f"worst / max(gate, 3 float steps at |log-scale|) = {worst_excess:.2f}), {nbig} of {nmat * N * N} entries beyond 1e-4*max(d,1)")
     assert worst_excess <= 1.0
 
 
