@@ -288,7 +288,7 @@ def resident_leg(out_dir, device, N, reps=3):
     assert np.isfinite(d).all() and float(np.abs(np.diag(d)).max()) == 0.0
     return {"call": "rp_chunk_load -> rp_paint_targets_device(0..N) -> rp_window_open_resident(0) -> rp_window_distance(snp 0): "
                     "chunk files in, first N x N distance matrix on the host, no paint files",
-            "seconds": warm[len(warm) // 2], "runs_ms": [round(1e3 * t, 2) for t in runs], "first_call_ms": 1e3 * runs[0],
+            "seconds": warm[(len(warm) - 1) // 2], "runs_ms": [round(1e3 * t, 2) for t in runs], "first_call_ms": 1e3 * runs[0],
             "window0_posterior_rows": int(rows), "breakdown_ms": parts}
 
 
@@ -393,7 +393,7 @@ def sharded_leg(name, devices, peaks, reps=3):
         if name == "config4":   # VERDICT r01 task 5: Paint + window-open wall on ONE GPU without paint files
             try:
                 shutil.rmtree(os.path.join(out_dir, "chunk_0"), ignore_errors=True)
-                res["e2e_resident_1gpu"] = resident_leg(out_dir, devices[0], N, reps=2)
+                res["e2e_resident_1gpu"] = resident_leg(out_dir, devices[0], N, reps=3)
             except Exception as e:
                 res["e2e_resident_1gpu"] = {"error": f"{type(e).__name__}: {e}"}
         return res

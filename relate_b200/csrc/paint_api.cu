@@ -65,19 +65,66 @@ void trace(const char *what, int dev = -1)
     if (on) fprintf(stderr, "[rp %9.2f ms] dev %d: %s\n", now_ms() - t_first, dev, what);
 }
 
+// Device memory released by a DevBuf is parked per device and handed out again to the next request it fits: cudaMalloc /
+// cudaFree of the GB-sized buffers of this path (a window's posterior is 5 GB at config 2 and 100 GB at config 4) cost tens
+// to hundreds of milliseconds each and synchronise the device.  rp_release_cache() returns everything to the driver; an
+// allocation that fails empties the pool and tries once more.
+class DevicePool {
+  public:
+    void *take(int dev, size_t want, size_t *got)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto &m = free_[dev];
+        auto it = m.lower_bound(want);
+        if (it == m.end() || it->first > want + want / 2 + (1u << 20)) return nullptr; // (do not burn a much larger block)
+        void *p = it->second;
+        *got = it->first;
+        held_ -= it->first;
+        m.erase(it);
+        return p;
+    }
+    void give(int dev, void *p, size_t cap)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        free_[dev].emplace(cap, p);
+        held_ += cap;
+    }
+    void flush() // frees every parked block (on whatever device it lives)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto &kv : free_) {
+            cudaSetDevice(kv.first);
+            for (auto &b : kv.second) cudaFree(b.second);
+            kv.second.clear();
+        }
+        cudaSetDevice(cur);
+        held_ = 0;
+    }
+
+  private:
+    std::mutex mu_;
+    std::map<int, std::multimap<size_t, void *>> free_;
+    size_t held_ = 0;
+};
+DevicePool g_pool;
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    int dev = 0;
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return RP_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
+        release();
+        cudaGetDevice(&dev);
         size_t want = bytes + bytes / 8 + 256;
+        if ((p = g_pool.take(dev, bytes, &cap)) != nullptr) return RP_OK;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             cudaGetLastError();
+            g_pool.flush();
             want = bytes;
             e = cudaMalloc(&p, want);
         }
@@ -91,7 +138,7 @@ struct DevBuf {
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) g_pool.give(dev, p, cap);
         p = nullptr;
         cap = 0;
     }
@@ -1576,6 +1623,7 @@ extern "C" void rp_release_cache(void)
         kv.second.hap_in.release();
     }
     g_ws.clear();
+    g_pool.flush(); // device memory parked by freed chunks and windows goes back to the driver
 }
 
 namespace {
@@ -1593,6 +1641,43 @@ int check_devices(const int *devices, int n_devices, std::vector<int> &devs)
         for (size_t j = 0; j < i; j++)
             if (devs[j] == devs[i]) return fail(RP_EINVAL, "device " + std::to_string(devs[i]) + " listed twice");
     }
+    return RP_OK;
+}
+
+// Sizes the per-batch work buffers of a chunk once, for batches of B targets: growing one of them later means cudaFree +
+// cudaMalloc, which synchronises the device and so serialises a batch's painting with the previous batch's copies.
+int reserve_for_batches(rp_chunk *c, int B)
+{
+    const int N = c->N, W = c->W;
+    RP_CUDA(cudaSetDevice(c->device));
+    RP_TRY(c->counts.ensure((size_t)N * 4));
+    const int th = 256, wpb = th / 32;
+    rp::count_sites_kernel<<<(unsigned)((N + wpb - 1) / wpb), th, 0, c->stream>>>(c->GT.as<uint32_t>(), c->lw, c->L, 0, N, c->counts.as<int>());
+    RP_CUDA(cudaGetLastError());
+    std::vector<int> cnt((size_t)N);
+    RP_CUDA(cudaMemcpyAsync(cnt.data(), c->counts.p, (size_t)N * 4, cudaMemcpyDeviceToHost, c->stream));
+    RP_CUDA(cudaStreamSynchronize(c->stream));
+    long long umax = 0;
+    for (int k0 = 0; k0 < N; k0 += B) {
+        long long u = 0;
+        for (int k = k0; k < std::min(N, k0 + B); k++) u += cnt[(size_t)k];
+        umax = std::max(umax, u);
+    }
+    const bool fp64 = (c->flags & RP_FP64) != 0;
+    const size_t entsz = fp64 ? sizeof(rp::EntD) : sizeof(rp::EntF);
+    const size_t nw = (size_t)std::min(B, N) * W;
+    RP_TRY(c->ent.ensure(((size_t)umax + 8) * entsz));
+    RP_TRY(c->off.ensure(((size_t)B + 1) * 8));
+    for (DevBuf *b : {&c->ia, &c->ib, &c->sb, &c->se, &c->lsa, &c->lsb}) RP_TRY(b->ensure(nw * 4));
+    for (DevBuf *b : {&c->lsA, &c->lsB}) RP_TRY(b->ensure(nw * 8));
+    RP_TRY(c->alpha.ensure(nw * N * 4));
+    RP_TRY(c->beta.ensure(nw * N * 4));
+    RP_TRY(c->rleK.ensure(nw * 2 * 4));
+    RP_TRY(c->rec_off.ensure(nw * 8));
+    // record images: 64 + 8*(Ka+Kb) bytes per (target, window); Ka+Kb is typically 0.6-1.2 N (a larger batch grows the buffer)
+    const size_t img = nw * (64 + (size_t)10 * N);
+    RP_TRY(c->image.ensure(img));
+    RP_TRY(c->image_alt.ensure(img));
     return RP_OK;
 }
 
@@ -1644,13 +1729,19 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         return "";
     }).share();
 
-    // batch size: bound the pinned staging per device (2 buffers: pinning memory costs ~0.3 s/GB), keep every GPU busy
+    // Batch size.  A batch is one launch of the paint kernel on one device: it should hold a few waves of chains (a
+    // multi-warp team is one CTA: 444-740 resident teams per device; 63 batches of 160 targets left config 4 at 0.45 of the
+    // nominal issue rate against 0.57 for a well filled grid), there should be up to 4 batches per device so that copying
+    // and writing one batch overlaps painting the next, and its stepping stones (2*W*N floats per target) plus the two
+    // record images should not take more than ~24 GB of HBM.
     const size_t per_target = (size_t)2 * W * N * 4;
-    long long bsz = (long long)((512ull << 20) / per_target);
+    const long long ndev_ll = (long long)devs.size();
+    const long long fill = N > 2048 ? 700 : 1000; // targets for ~3 waves of teams (two chains per target)
+    const long long per_dev = std::max<long long>(1, std::min<long long>(4, N / (ndev_ll * fill)));
+    long long bsz = (N + ndev_ll * per_dev - 1) / (ndev_ll * per_dev);
+    bsz = std::min<long long>(bsz, (long long)((8ull << 30) / per_target));
     bsz = std::max<long long>(bsz, 64);
     bsz = std::min<long long>(bsz, N);
-    if ((int)devs.size() > 1)
-        bsz = std::min<long long>(bsz, std::max<long long>(64, (N + 2 * (long long)devs.size() - 1) / (2 * (long long)devs.size())));
     if (const char *fb = getenv("RP_BATCH_TARGETS")) bsz = std::max(1, std::min(N, atoi(fb))); // tests: force small batches
     const int B = (int)bsz;
     const int nbatch = (N + B - 1) / B;
@@ -1702,6 +1793,7 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
                                  flags, &c, &st, &feed);
         trace("chunk resident (H2D + bit-pack)", devs[di]);
         if (rc != RP_OK) feed.abort.store(1); // readers must not wait for this device's copies
+        if (rc == RP_OK) rc = reserve_for_batches(c, B);
         if (rc == RP_OK) rc = ws.out.ensure(kOutPiece * kOutPieces);
         rings[di].reset(new OutRing());
         OutRing &ring = *rings[di];

@@ -116,7 +116,8 @@ def test_dij_through_reference_getmatrix_on_full_config2(ref_runs):
     with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 2)) as ex:  # ~5 GB of posterior per process
         outs = dict(zip(work, ex.map(lens, work)))
     # GetMatrix forms d = -(fast_log(posterior) + logscale) - rowmin in FLOAT arithmetic (anc_builder.cpp:123-131,190-192): every
-    # entry is rounded to the float spacing at |logscale| (2.44e-4 below 4096, 4.9e-4 above), and so is the row minimum.
+    # entry is rounded to the float spacing at the row's |logscale| (alpha's + beta's: 2.44e-4 in [2048, 4096)), and so is the
+    # row minimum.
     # With fp32 state the stored log-scale of a record differs from the reference's by one such step in a fraction of a
     # percent of the records, the posterior by ~1e-6: an entry can land one step away through each of the three roundings
     # (the sum, the shifted log-scale, the minimum).  Measured on the full config 2 chunk: worst |dd| = 7.324e-4 = exactly 3
@@ -125,7 +126,8 @@ def test_dij_through_reference_getmatrix_on_full_config2(ref_runs):
     worst, worst_excess, nmat, nbig = 0.0, 0.0, 0, 0
     for sec in range(W):
         recs = chunkio.read_paint_file(os.path.join(j["dir"], "ref", "o", "chunk_0", "paint", f"relate_{sec}.bin"), N)
-        ls_max = max(max(abs(float(ra.logscale)), abs(float(rb.logscale))) for _, _, ra, rb in recs)
+        # (a posterior row's log-scale is the sum of the alpha-side and the beta-side ones, fast_painting.cpp:887-905)
+        ls_max = max(abs(float(ra.logscale)) + abs(float(rb.logscale)) for _, _, ra, rb in recs)
         tol = max(DTOL, 3.0 * float(np.spacing(np.float32(ls_max))) * (1 + 1e-6))
         a, b = read_dlens(outs[("ref", sec)]), read_dlens(outs[("gpu", sec)])
         assert a.keys() == b.keys() and len(a) >= 5
