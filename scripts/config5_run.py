@@ -72,13 +72,16 @@ def main():
     ap.add_argument("--workdir", default="/dev/shm" if os.path.isdir("/dev/shm") else None)
     ap.add_argument("--cpu-snps", type=int, default=3000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--memory", type=float, default=0.0, help="--memory for MakeChunks (default: what makes a chunk take snps-per-chunk new SNPs)")
+    ap.add_argument("--max-live", type=int, default=0, help="paintings alive at a time (default: one per GPU)")
     ap.add_argument("--keep-log", default=None)
     args = ap.parse_args()
     N, C, per = args.N, args.chunks, args.snps_per_chunk
     L = C * per
     # chunk capacity = (memory*1e9/4 - (2N^2+3N)) / N new SNPs (data.cpp:129-139)
-    memory = (per * N + 2.0 * N * N + 3.0 * N) * 4.0 / 1e9 * 1.000001
+    memory = args.memory if args.memory > 0 else (per * N + 2.0 * N * N + 3.0 * N) * 4.0 / 1e9 * 1.000001
     ndev = capi.lib().rp_device_count()
+    live = min(ndev, args.max_live) if args.max_live > 0 else ndev
     tmp = tempfile.mkdtemp(prefix="relate_config5_", dir=args.workdir)
     out = {"config": f"config 5 (shrunk): N={N} x L={L} SNPs, --memory {memory:.4f} -> {C} chunks of {per} new SNPs (+20000 overlap), "
                      f"--painting {PAINTING}; {ndev} GPU(s); BASELINE.json names N=5000 (one chunk's paint files would be ~100 GB)",
@@ -104,8 +107,8 @@ def main():
         # ---- Paint, waves of one chunk per GPU, paint files deleted after each wave ----
         waves, paint_bytes, t_paint = [], 0, 0.0
         agg = {k: 0.0 for k in ("ms_paint", "ms_prep", "ms_rle", "ms_d2h", "ms_write", "ms_load")}
-        for c0 in range(0, n_chunks, ndev):
-            c1 = min(n_chunks, c0 + ndev) - 1
+        for c0 in range(0, n_chunks, live):
+            c1 = min(n_chunks, c0 + live) - 1
             t0 = time.perf_counter()
             st = capi.paint_chunks(odir, c0, c1, PAINTING, devices=list(range(ndev)))
             dt = time.perf_counter() - t0
@@ -123,7 +126,7 @@ def main():
             print(f"wave chunks {c0}-{c1}: {dt:.2f} s, {nb / 1e9:.1f} GB of paint files, kernels {st['ms_paint']:.0f} ms on the busiest GPU", flush=True)
         assert not any(f.endswith(".hapbits") for f in os.listdir(odir)), "sidecars must be consumed"
         out.update({"s_paint_all_chunks": t_paint, "cells_per_s": cells / t_paint, "paint_file_bytes_total": paint_bytes,
-                    "max_live_paintings": ndev, "ms_paint_kernels_sum_of_busiest_gpu_per_wave": agg["ms_paint"], "waves": waves})
+                    "max_live_paintings": live, "ms_paint_kernels_sum_of_busiest_gpu_per_wave": agg["ms_paint"], "waves": waves})
         # ---- CPU baseline: concurrent reference Paint processes on sample chunks ----
         if not args.no_cpu and oracle.have_reference():
             cores = os.cpu_count() or 1
