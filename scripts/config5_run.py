@@ -14,8 +14,9 @@ What runs:
      reference (what RelateParallel.sh's disabled `parallelize $chunks` would do, :416-425,548-549) on sample chunks
      of the same N (first `--cpu-snps` SNPs of the chromosome), rate extrapolated to the full chunks and labelled so.
 
-N defaults to 2000, not BASELINE's 5000: at N = 5000 one chunk's paint files are ~100 GB (500 windows x 2 x N^2 x 4 B) and
-eight live paintings do not fit this box's disk or RAM disk; at N = 2000 they are ~9 GB each.  Stated in the output.
+N defaults to 2000, not BASELINE's 5000: at N = 5000 one chunk's paint files are ~100 GB (500 windows x 2 x N^2 x 4 B), so
+live paintings need hundreds of GB of (RAM) disk: `--N 5000 --memory 1.74 --max-live 4 --cpu-snps 600` is the at-size run
+(--memory 1.74 makes the 500-window cap close a chunk after ~50 000 new SNPs: 20 chunks).  Stated in the output.
 """
 import argparse
 import json
@@ -83,8 +84,9 @@ def main():
     ndev = capi.lib().rp_device_count()
     live = min(ndev, args.max_live) if args.max_live > 0 else ndev
     tmp = tempfile.mkdtemp(prefix="relate_config5_", dir=args.workdir)
-    out = {"config": f"config 5 (shrunk): N={N} x L={L} SNPs, --memory {memory:.4f} -> {C} chunks of {per} new SNPs (+20000 overlap), "
-                     f"--painting {PAINTING}; {ndev} GPU(s); BASELINE.json names N=5000 (one chunk's paint files would be ~100 GB)",
+    out = {"config": f"config 5{' (shrunk: BASELINE.json names N=5000)' if N < 5000 else ''}: N={N} x L={L} SNPs, --memory {memory:.4f} "
+                     f"(aiming at {C} chunks of {per} new SNPs + the 20000-SNP overlap), --painting {PAINTING}; {ndev} GPU(s), "
+                     f"at most {live} paintings alive",
            "workdir": tmp}
     try:
         t0 = time.perf_counter()
