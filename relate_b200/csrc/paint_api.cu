@@ -156,9 +156,10 @@ struct rp_chunk {
     double theta = 0.001;
     int sm_count = 148;
     std::vector<int> wb;
+    std::vector<long long> site_prefix; // [N+1] prefix of D_k = visited sites per target (counted once when the chunk is loaded)
     rp_tune tune{};
     // resident
-    DevBuf G, GT, r, Phi, Plo, wbdev, chars;
+    DevBuf G, GT, r, Phi, Plo, wbdev, chars, cnt_all; // cnt_all: D_k of every target
     // per-paint work buffers (grown on demand, reused)
     DevBuf counts, off, ent, ia, ib, lsA, lsB, sb, se, alpha, beta, lsa, lsb, queue, scratch, nor, segstate, segdone;
     // record encoder (device RLE): run counts, byte offsets, the W file images of the last batch
@@ -491,8 +492,17 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
                                                                  c->GT.as<uint32_t>(), c->lw);
         RP_CUDAB(cudaGetLastError());
     }
+    // D_k of every target, once per chunk: a paint call then knows its table size without counting and without a
+    // device->host round trip in front of its kernels
+    RP_TRYB(c->cnt_all.ensure((size_t)N * 4));
+    rp::count_sites_kernel<<<(unsigned)((N + 7) / 8), 256, 0, c->stream>>>(c->GT.as<uint32_t>(), c->lw, L, 0, N, c->cnt_all.as<int>());
+    RP_CUDAB(cudaGetLastError());
+    std::vector<int> h_cnt((size_t)N);
+    RP_CUDAB(cudaMemcpyAsync(h_cnt.data(), c->cnt_all.p, (size_t)N * 4, cudaMemcpyDeviceToHost, c->stream));
     RP_CUDAB(cudaEventRecord(c->ev[2], c->stream));
     RP_CUDAB(cudaStreamSynchronize(c->stream));
+    c->site_prefix.assign((size_t)N + 1, 0);
+    for (int k = 0; k < N; k++) c->site_prefix[(size_t)k + 1] = c->site_prefix[(size_t)k] + h_cnt[(size_t)k];
     if (!reused) chars.release(); // a parked workspace keeps its staging buffer for the next chunk
     if (st) {
         float a = 0, b = 0;
@@ -501,7 +511,7 @@ int chunk_from_host(int device, int N, int L, const char *hap, const double *r, 
         st->ms_h2d += a;
         st->ms_prep += b;
         st->h2d_bytes += (feed ? (long long)L * c->wps * 4 : (long long)nchar) + (long long)L * 8 + (long long)(L + 1) * 16 + (long long)n_wb * 4;
-        st->launches += feed ? 1 : 2;
+        st->launches += feed ? 2 : 3;
         st->ms_total += now_ms() - t0;
     }
     *out = c;
@@ -542,14 +552,10 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
     RP_CUDA(cudaEventRecord(c->ev[0], s));
     const int th = 256, wpb = th / 32;
     const unsigned gw = (unsigned)((nt + wpb - 1) / wpb);
-    rp::count_sites_kernel<<<gw, th, 0, s>>>(c->GT.as<uint32_t>(), c->lw, c->L, k0, nt, c->counts.as<int>());
+    rp::scan_counts_kernel<<<1, 1024, 0, s>>>(c->cnt_all.as<int>() + k0, nt, c->off.as<long long>());
     RP_CUDA(cudaGetLastError());
-    rp::scan_counts_kernel<<<1, 1024, 0, s>>>(c->counts.as<int>(), nt, c->off.as<long long>());
-    RP_CUDA(cudaGetLastError());
-    launches += 2;
-    RP_CUDA(cudaMemcpyAsync(c->h_total, c->off.as<long long>() + nt, 8, cudaMemcpyDeviceToHost, s));
-    RP_CUDA(cudaStreamSynchronize(s));
-    const long long U = *c->h_total;
+    launches += 1;
+    const long long U = c->site_prefix[(size_t)k1] - c->site_prefix[(size_t)k0];
     c->last_sites = U;
     // the paint kernel's prefetch reads up to 3 entries past either end of a target's list: pad both ends
     const size_t entsz = fp64 ? sizeof(rp::EntD) : sizeof(rp::EntF);
@@ -678,7 +684,6 @@ int paint_device(rp_chunk *c, int k0, int k1, rp_stats *st, bool run_paint = tru
         st->team_threads = lp.threads;
         st->words_per_thread = lp.wpt;
         st->ctas = ctas;
-        st->d2h_bytes += 8;
     }
     return RP_OK;
 }
@@ -840,7 +845,7 @@ void rp_chunk_free(rp_chunk *c)
     if (!c) return;
     for (rp_chunk **ref : c->window_refs) *ref = nullptr; // windows left open fail with RP_EINVAL instead of dangling
     cudaSetDevice(c->device);
-    for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
+    for (DevBuf *b : {&c->G, &c->GT, &c->r, &c->Phi, &c->Plo, &c->wbdev, &c->chars, &c->cnt_all, &c->counts, &c->off, &c->ent, &c->ia, &c->ib,
                       &c->lsA, &c->lsB, &c->sb, &c->se, &c->alpha, &c->beta, &c->lsa, &c->lsb, &c->queue, &c->scratch, &c->nor, &c->segstate, &c->segdone,
                       &c->rleK, &c->rec_off, &c->win_bytes, &c->img_off, &c->image, &c->image_alt, &c->park_top, &c->park_ls, &c->park_scal,
                       &c->park_d, &c->park_rowoff, &c->park_rpos, &c->park_lsa, &c->park_lsb})
@@ -1546,7 +1551,8 @@ struct ChunkReaders {
             feed.consumed[i].store(0);
         }
         const unsigned want_readers = getenv("RP_READERS") ? (unsigned)atoi(getenv("RP_READERS")) : 8u;
-        const int nread = (int)std::max(1u, std::min<unsigned>({want_readers, std::max(1u, io_thread_budget() / 2), (unsigned)feed.nslots}));
+        // (a chunk is read, painted and written one after the other, so readers and writers may each use the whole budget)
+        const int nread = (int)std::max(1u, std::min<unsigned>({want_readers, io_thread_budget(), (unsigned)feed.nslots}));
         readers_left = nread;
         for (int t = 0; t < nread; t++) threads.emplace_back([this]() { run(); });
         return RP_OK;
@@ -1650,19 +1656,8 @@ int reserve_for_batches(rp_chunk *c, int B)
 {
     const int N = c->N, W = c->W;
     RP_CUDA(cudaSetDevice(c->device));
-    RP_TRY(c->counts.ensure((size_t)N * 4));
-    const int th = 256, wpb = th / 32;
-    rp::count_sites_kernel<<<(unsigned)((N + wpb - 1) / wpb), th, 0, c->stream>>>(c->GT.as<uint32_t>(), c->lw, c->L, 0, N, c->counts.as<int>());
-    RP_CUDA(cudaGetLastError());
-    std::vector<int> cnt((size_t)N);
-    RP_CUDA(cudaMemcpyAsync(cnt.data(), c->counts.p, (size_t)N * 4, cudaMemcpyDeviceToHost, c->stream));
-    RP_CUDA(cudaStreamSynchronize(c->stream));
     long long umax = 0;
-    for (int k0 = 0; k0 < N; k0 += B) {
-        long long u = 0;
-        for (int k = k0; k < std::min(N, k0 + B); k++) u += cnt[(size_t)k];
-        umax = std::max(umax, u);
-    }
+    for (int k0 = 0; k0 < N; k0 += B) umax = std::max(umax, c->site_prefix[(size_t)std::min(N, k0 + B)] - c->site_prefix[(size_t)k0]);
     const bool fp64 = (c->flags & RP_FP64) != 0;
     const size_t entsz = fp64 ? sizeof(rp::EntD) : sizeof(rp::EntF);
     const size_t nw = (size_t)std::min(B, N) * W;
