@@ -595,6 +595,7 @@ template <int WPT> __device__ __forceinline__ void load_words(uint32_t (&w)[WPT]
 #define RP_PF 1 // L1 prefetch hints for the genotype rows / site tables of later steps
 #endif
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // ---- bulk-async (TMA, 1-D) row ring helpers (RP_TMA_ROWS) ----
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
 {
@@ -1505,6 +1506,10 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
         cq.q[0] = pe[1].c; cq.q[1] = pe[2].c;
         norq.q[0] = pnor[0]; norq.q[1] = pnor[1]; norq.q[2] = pnor[2];
         for (int i = 1; i <= m; i++) {
+            if ((i & 15) == 1 && i + 48 <= m) { // table lines (16 entries each) three lines ahead: under load a DRAM round trip is
+                prefetch_l2(pe + i + 47);       // longer than the two rows of lead of the streams below
+                prefetch_l2(pnor + i + 47);
+            }
             const EntF ent = entq.pop_push(pe[i + 4]);       // = pe[i+2]
             const RowIn cin = inq.pop_push(fetch(ent.site)); // inputs of row i; row i+2's are requested
             const T ccur = cq.pop_push(ent.c);               // c of row i
@@ -1608,6 +1613,13 @@ __global__ void __launch_bounds__(MULTI ? (WPT == 1 ? 512 : 256) : 32, MULTI ? 1
             const float ctail = ntail;
             block_request(jb - 1);
             sites_request(jb - 2);
+            if (jb >= 6) { // the small per-row streams of the block five blocks down, into L2 (one line each covers several blocks)
+                const int pb = (jb - 5) * CK;
+                prefetch_l2(pe + pb);
+                prefetch_l2(sc + pb);
+                prefetch_l2(pnor + pb);
+                prefetch_l2(lsrow + pb);
+            }
             const int cs = jb & 1;
             asm volatile("cp.async.wait_group 1;" ::: "memory"); // this block's checkpoint has landed (the next one may be in flight)
             // ---- recompute rows b0+1 .. b0+nb-1 from the checkpoint ----
