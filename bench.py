@@ -441,7 +441,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-        cpu_group = dist.new_group(backend="gloo")   # ranks park here (no spinning GPU kernel) during rank 0's sharded leg
+        cpu_group = sharding.cpu_barrier_group()     # ranks park here (no spinning GPU kernel) during rank 0's sharded leg
 
     tmp = tempfile.mkdtemp(prefix=f"relate_bench_r{rank}_")
     try:

@@ -10,7 +10,7 @@ import pytest
 
 from conftest import ROOT, unpack_golden
 from oracle import oracle
-from relate_b200 import capi, sharding
+from relate_b200 import capi
 
 
 def header_symbols():
@@ -128,15 +128,3 @@ def test_cli_delegates_other_modes_to_reference(tmp_path, have_ref):
     assert "Needed: haps, sample, map, output." in p.stdout  # the reference's own usage text
 
 
-def test_balanced_target_ranges():
-    rng = np.random.default_rng(1)
-    counts = rng.integers(100, 1000, size=1001)
-    for world in (1, 2, 3, 8):
-        rs = sharding.balanced_target_ranges(counts, world)
-        assert rs[0][0] == 0 and rs[-1][1] == len(counts)
-        assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
-        loads = [counts[a:b].sum() for a, b in rs]
-        assert max(loads) - min(loads) <= 2 * counts.max()
-    assert sharding.balanced_target_ranges([5, 5], 4)[-1][1] == 2
-    got = [sharding.chunks_for_rank(20, r, 8, sizes=np.arange(20) + 1) for r in range(8)]
-    assert sorted(sum(got, [])) == list(range(20))

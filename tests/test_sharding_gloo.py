@@ -22,16 +22,19 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    counts = np.random.default_rng(7).integers(50, 500, size=333)
-    a, b = sharding.balanced_target_ranges(counts, world)[rank]
-    my_sites = float(counts[a:b].sum())
+    # what bench.py does with N ranks: every rank paints its own chunk (here: a stand-in count of visited sites and a
+    # device time), then max / sum over ranks, and a host-side group to wait on while rank 0 runs the strong-scaling leg
+    counts = np.random.default_rng(7 + rank).integers(50, 500, size=333)
+    my_sites = float(counts.sum())
     my_ms = 10.0 + rank  # stand-in for this rank's device time
     dist.barrier()
     (t_max,) = sharding.allreduce_scalars([my_ms], "max")
-    sites, ntargets = sharding.allreduce_scalars([my_sites, float(b - a)], "sum")
-    chunks = sharding.chunks_for_rank(5, rank, world)
-    q.put((rank, t_max, sites, ntargets, chunks, float(counts.sum())))
-    dist.barrier()
+    (sites,) = sharding.allreduce_scalars([my_sites], "sum")
+    g = sharding.cpu_barrier_group()
+    assert g is not None
+    dist.barrier(group=g)
+    q.put((rank, t_max, sites, my_sites))
+    dist.barrier(group=g)
     dist.destroy_process_group()
 
 
@@ -47,10 +50,7 @@ def test_two_rank_sharding_and_reduction():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    allchunks = []
-    for rank, t_max, sites, ntargets, chunks, total in out:
+    total = sum(mine for _, _, _, mine in out)
+    for rank, t_max, sites, mine in out:
         assert t_max == 11.0            # max over ranks
-        assert sites == total           # every target painted exactly once
-        assert ntargets == 333
-        allchunks += chunks
-    assert sorted(allchunks) == list(range(5))
+        assert sites == total           # sum over ranks
