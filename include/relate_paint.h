@@ -202,7 +202,9 @@ int rp_window_distance(rp_window *win, int snp, float *d);
 long long rp_window_rows(const rp_window *win);
 void rp_window_close(rp_window *win);
 
-/* rp_paint_chunk parks device buffers, pinned staging and streams per device between calls; this frees them. */
+/* rp_paint_chunk parks device buffers, pinned staging and streams per device between calls, and device memory released
+ * by freed chunks and closed windows is kept in a per-device pool for the next allocation it fits (allocating a window's
+ * posterior, GBs, costs more than repainting it); this returns all of it to the driver. */
 void rp_release_cache(void);
 
 /* ---- small pieces exposed for the parity tests -------------------------------------- */

@@ -1176,10 +1176,13 @@ static int window_open_impl(rp_chunk *c, int w, const float *alpha, const float 
     };
     // checkpoint spacing: 4 rows for one-word single-warp teams (HBM traffic 12N -> 6N bytes per row), 2 for two-word and
     // multi-warp teams (registers; rows of tens of KB of shared memory each): 12N -> 8N.  RP_REPAINT_CK=8 selects 8 for one-word single-warp teams.
-    const bool ck8 = getenv("RP_REPAINT_CK") && atoi(getenv("RP_REPAINT_CK")) == 8;
+    const int ck_env = getenv("RP_REPAINT_CK") ? atoi(getenv("RP_REPAINT_CK")) : 0;
+    const bool ck8 = ck_env == 8;
     if (lp.wpt == 1) {
         if (lp.multi) rc = launch(rp::repaint_kernel<1, true, 2>, rp::RepaintSmem<2>::bytes(lp.threads, 1));
         else if (ck8) rc = launch(rp::repaint_kernel<1, false, 8>, rp::RepaintSmem<8>::bytes(32, 1));
+        else if (ck_env == 2) rc = launch(rp::repaint_kernel<1, false, 2>, rp::RepaintSmem<2>::bytes(32, 1));
+        else if (ck_env == 3) rc = launch(rp::repaint_kernel<1, false, 3>, rp::RepaintSmem<3>::bytes(32, 1));
         else rc = launch(rp::repaint_kernel<1, false, 4>, rp::RepaintSmem<4>::bytes(32, 1));
     } else {
         if (lp.multi) rc = launch(rp::repaint_kernel<2, true, 2>, rp::RepaintSmem<2>::bytes(lp.threads, 2));
