@@ -320,7 +320,15 @@ def sharded_leg(name, devices, peaks, reps=3):
     N, L = cfg["N"], cfg["L"]
     cells = float(N) * N * L
     nominal = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6
-    tmp = tempfile.mkdtemp(prefix=f"relate_{name}_")
+    # GBs of paint files per call: on a disk-backed file system the kernel's write-back of the dirty pages of earlier calls
+    # throttles the later ones (measured: 190 -> 280 ms per config-3 call within one process); a RAM disk, when there is one
+    # with room, times the stage itself.  RELATE_BENCH_TMP overrides.
+    W_est = {"config3": 22, "config4": 40}[name]
+    need_est = 2.2 * W_est * N * N * 4 + 2.0 * N * L
+    workdir = os.environ.get("RELATE_BENCH_TMP")
+    if not workdir and os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2 * need_est + (16 << 30):
+        workdir = "/dev/shm"
+    tmp = tempfile.mkdtemp(prefix=f"relate_{name}_", dir=workdir)
     os.environ["RP_IO_THREADS"] = str(os.cpu_count() or 8)   # this leg owns the host: the other ranks are parked
     try:
         out_dir = os.path.join(tmp, "o")
@@ -348,7 +356,7 @@ def sharded_leg(name, devices, peaks, reps=3):
         res = {"config": f"{name}: synthetic block-Kingman N={N} x L={L}, one chunk, --memory {cfg['memory']:g} (W={W} windows, "
                          f"U={st['sites']} visited sites), --painting {PAINTING}; targets sharded over {len(devices)} GPU(s) by "
                          f"rp_paint_chunk (equal-count batches pulled from one counter), chunk files -> paint files",
-               "n_devices": len(devices), "scaling": "strong",
+               "n_devices": len(devices), "scaling": "strong", "workdir": os.path.dirname(tmp) or tmp,
                "ms_stage": 1e3 * t_stage, "ms_stage_runs": [round(1e3 * t, 1) for t, _ in runs], "ms_stage_first_call": 1e3 * runs[0][0],
                "cells_per_s": cells / t_stage, "ms_paint_max": st["ms_paint"], "kernel_cells_per_s": cells / (st["ms_paint"] * 1e-3),
                "kernel": f"paint_kernel<float,{st['words_per_thread']},multi> teams of {st['team_threads']} threads",

@@ -1777,7 +1777,9 @@ int paint_chunk_stage(const char *out_dir, int chunk_index, const char *painting
         cv.wait(lk, [&] { return upto > b || first_rc != RP_OK; });
         return first_rc == RP_OK;
     };
-    WritePool pool((int)std::max(2u, std::min(16u, hw)));
+    // writers: each pwrite is one thread's copy into the page cache (a few GB/s); pieces in flight belong to different files
+    const unsigned want_writers = getenv("RP_WRITERS") ? (unsigned)atoi(getenv("RP_WRITERS")) : 16u;
+    WritePool pool((int)std::max(2u, std::min(want_writers, hw)));
     std::vector<std::unique_ptr<OutRing>> rings(devs.size());
 
     auto worker = [&](int di) {

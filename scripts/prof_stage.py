@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from relate_b200 import synth, capi
 N, L, mem = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3])
 calls = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-tmp = tempfile.mkdtemp(prefix="relate_stage_")
+tmp = tempfile.mkdtemp(prefix="relate_stage_", dir=os.environ.get("RELATE_TMP"))
 try:
     synth.make_chunk_dir(os.path.join(tmp, "o"), N, L, seed=2, memory_gb=mem)
     ndev = capi.lib().rp_device_count()
