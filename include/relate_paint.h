@@ -202,6 +202,37 @@ int rp_window_distance(rp_window *win, int snp, float *d);
 long long rp_window_rows(const rp_window *win);
 void rp_window_close(rp_window *win);
 
+/* ---- tree builder (consumer side, SURVEY.md 8 "next" row f4) -----------------------------------------
+ *   rp_minmatch_create      <- MinMatch::MinMatch(Data&)                       src/tree_builder.cpp:38-56
+ *   rp_minmatch_quickbuild  <- MinMatch::QuickBuild(d, tree, sample_ages)      src/tree_builder.cpp:1060-1303
+ *                              MinMatch::QuickBuild(d, tree, sample_ages, d_prior)            :2357-2646
+ *                              (with Initialize :58-146 / :1646-1735, Coalesce :295-598 / :1843-2070, InitializeSym
+ *                              :254-293, CoalesceSym :967-1058) in the form BuildTopology uses them without
+ *                              --sample_ages: sample_ages empty, no template tree.
+ * One handle = one reference MinMatch object: what survives from tree to tree inside it (min_values_CF, the lineage
+ * names of reset candidates) survives in the handle, so a sequence of calls yields the sequence of trees the
+ * reference builds — AncesTreeBuilder::BuildTopology creates one object per window (src/anc_builder.cpp:422).
+ * The tree comes back as its merge list: merges[2t], merges[2t+1] = labels of child_left, child_right of node N+t
+ * (t = 0..N-2), i.e. exactly what QuickBuild stores into tree.nodes (:1268-1274).  The lists are IDENTICAL to the
+ * reference's for identical input matrices (same float arithmetic, same order of std::mt19937 draws).
+ * d (and d_prior) are N x N row-major floats; neither is modified (the reference modifies d in place and its caller
+ * does not read it again). */
+typedef struct rp_minmatch rp_minmatch;
+typedef struct rp_minmatch_stats {
+    float ms_kernel;          /* device time of the tree kernel (CUDA events on the handle's stream) */
+    long long draws;          /* random numbers drawn = feasible pairs met                          */
+    int first_fallback_step;  /* first merge without a mutually minimal pair (-1: none)              */
+    int fallback_steps;       /* merges taken while the symmetric fallback matrix was in use         */
+    int launches;
+} rp_minmatch_stats;
+int rp_minmatch_create(int device, int N, double theta, rp_minmatch **out);
+void rp_minmatch_destroy(rp_minmatch *mm);
+/* d, d_prior on the host (d_prior NULL: the three-argument QuickBuild); merges: int [2*(N-1)] on the host */
+int rp_minmatch_quickbuild(rp_minmatch *mm, const float *d, const float *d_prior, int *merges, rp_minmatch_stats *stats);
+/* same with the matrices already in this device's memory (e.g. left there by the distance kernel) */
+int rp_minmatch_quickbuild_device(rp_minmatch *mm, const float *dev_d, const float *dev_prior, int *merges,
+                                  rp_minmatch_stats *stats);
+
 /* rp_paint_chunk parks device buffers, pinned staging and streams per device between calls, and device memory released
  * by freed chunks and closed windows is kept in a per-device pool for the next allocation it fits (allocating a window's
  * posterior, GBs, costs more than repainting it); this returns all of it to the driver. */

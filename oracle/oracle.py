@@ -128,3 +128,74 @@ def read_distances(path: str) -> dict:
         out[snp] = np.frombuffer(buf, "<f4", N * N, off + 4).reshape(N, N)
         off += 4 + 4 * N * N
     return out
+
+
+# ---- MinMatch (tree builder) : oracle restatement and the reference-linked tree lens --------------------------------
+REF_QBLENS = os.path.join(HERE, "_ref", "qblens")
+
+
+class MinMatchOracle:
+    """oracle/minmatch_oracle.c: one MinMatch object (state survives from tree to tree as in the reference)."""
+
+    def __init__(self, N: int, theta: float):
+        l = lib()
+        l.mmo_create.restype = C.c_void_p
+        l.mmo_create.argtypes = [C.c_int, C.c_double]
+        l.mmo_destroy.argtypes = [C.c_void_p]
+        l.mmo_quickbuild.restype = C.c_int
+        l.mmo_quickbuild.argtypes = [C.c_void_p] * 5
+        self.N, self._l = N, l
+        self._h = l.mmo_create(N, theta)
+
+    def quickbuild(self, d: np.ndarray, prior: np.ndarray | None = None):
+        """-> (merges int32 [N-1, 2], info dict).  d is not modified (a copy is)."""
+        N = self.N
+        dd = np.array(d, dtype=np.float32, order="C", copy=True).reshape(N, N)
+        pp = None if prior is None else np.ascontiguousarray(prior, dtype=np.float32).reshape(N, N)
+        merges = np.empty((N - 1, 2), np.int32)
+        info = (C.c_long * 2)()
+        rc = self._l.mmo_quickbuild(self._h, dd.ctypes.data, None if pp is None else pp.ctypes.data, merges.ctypes.data, info)
+        if rc:
+            raise RuntimeError(f"mmo_quickbuild failed: {rc}")
+        return merges, dict(draws=int(info[0]), first_sym_step=int(info[1]))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.mmo_destroy(self._h)
+            self._h = None
+
+
+def write_tree_lens_input(path: str, N: int, theta: float, trees) -> None:
+    """trees: list of (d, prior-or-None) -> the input format of oracle/_ref/qblens."""
+    import struct
+    with open(path, "wb") as f:
+        f.write(struct.pack("<idi", N, theta, len(trees)))
+        for d, prior in trees:
+            f.write(struct.pack("<i", 0 if prior is None else 1))
+            f.write(np.ascontiguousarray(d, dtype="<f4").tobytes())
+            if prior is not None:
+                f.write(np.ascontiguousarray(prior, dtype="<f4").tobytes())
+
+
+def reference_quickbuild(N: int, theta: float, trees, workdir: str, repeat: int = 1):
+    """The reference's own MinMatch::QuickBuild (oracle/_ref/qblens) on a list of (d, prior) -> (list of merges, seconds)."""
+    inp, out = os.path.join(workdir, "qb_in.bin"), os.path.join(workdir, "qb_out.bin")
+    write_tree_lens_input(inp, N, theta, trees)
+    r = subprocess.run([REF_QBLENS, inp, out, str(repeat)], check=True, capture_output=True, text=True)
+    secs = float(r.stderr.strip().split("QuickBuild")[1].split()[0])
+    m = np.fromfile(out, "<i4").reshape(len(trees), N - 1, 2)
+    return [m[t] for t in range(len(trees))], secs
+
+
+def prior_from_merges(merges: np.ndarray, N: int, val: float) -> np.ndarray:
+    """The `dist` matrix AncesTreeBuilder::BuildTopology derives from the previous tree (src/anc_builder.cpp:581-606):
+    dist[i][j] += val for every internal clade that contains i but not j."""
+    members = [np.array([k]) for k in range(N)] + [None] * (N - 1)
+    dist = np.zeros((N, N), np.float32)
+    for t, (a, b) in enumerate(merges):
+        mem = np.concatenate([members[a], members[b]])
+        members[N + t] = mem
+        add = np.full(N, np.float32(val), np.float32)
+        add[mem] = 0
+        dist[mem] += add[None, :]
+    return dist

@@ -44,6 +44,11 @@ class RpStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
 
 
+class RpMinMatchStats(C.Structure):
+    _fields_ = [("ms_kernel", C.c_float), ("draws", C.c_longlong), ("first_fallback_step", C.c_int),
+                ("fallback_steps", C.c_int), ("launches", C.c_int)]
+
+
 class RpTune(C.Structure):
     _fields_ = [("words_per_thread", C.c_int), ("ctas_per_sm", C.c_int), ("reserved", C.c_int * 6)]
 
@@ -83,6 +88,10 @@ SYMBOLS = {
                                  C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
     "rp_make_chunks_ex": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_float, C.c_uint,
                                     C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
+    "rp_minmatch_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.POINTER(_P)]),
+    "rp_minmatch_destroy": (None, [_P]),
+    "rp_minmatch_quickbuild": (C.c_int, [_P, _P, _P, _P, C.POINTER(RpMinMatchStats)]),
+    "rp_minmatch_quickbuild_device": (C.c_int, [_P, _P, _P, _P, C.POINTER(RpMinMatchStats)]),
     "rp_rle_encode": (C.c_int, [_P, C.c_int, _P, _P]),
     "rp_fast_log_device": (C.c_int, [C.c_int, _P, _P, C.c_int]),
     "rp_debug_pack_host": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int]),
@@ -273,6 +282,45 @@ class Window:
 
     def __exit__(self, *a):
         self.close()
+
+
+class MinMatch:
+    """One tree builder (``rp_minmatch_*``) = one reference ``MinMatch`` object: state survives from tree to tree."""
+
+    def __init__(self, N: int, theta: float, device: int = 0):
+        self.N = N
+        self._h = _P()
+        check(lib().rp_minmatch_create(device, N, theta, C.byref(self._h)))
+
+    def quickbuild(self, d: np.ndarray, prior: np.ndarray | None = None):
+        """-> (merges int32 [N-1, 2], stats dict); d / prior: float32 [N, N] on the host, not modified."""
+        N = self.N
+        d = np.ascontiguousarray(d, dtype=np.float32)
+        assert d.shape == (N, N)
+        if prior is not None:
+            prior = np.ascontiguousarray(prior, dtype=np.float32)
+            assert prior.shape == (N, N)
+        merges = np.empty((N - 1, 2), np.int32)
+        st = RpMinMatchStats()
+        check(lib().rp_minmatch_quickbuild(self._h, _ptr(d), _ptr(prior), _ptr(merges), C.byref(st)))
+        return merges, {n: getattr(st, n) for n, _ in st._fields_}
+
+    def close(self):
+        if self._h:
+            lib().rp_minmatch_destroy(self._h)
+            self._h = _P()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def paint_from_host(hap, r, wb, theta=0.001, device=0, fp64=False, k_begin=0, k_end=None, out=None,

@@ -36,6 +36,12 @@ int fail(int code, const std::string &msg)
     return code;
 }
 
+} // namespace
+namespace rp {
+int api_fail(int code, const std::string &msg) { return fail(code, msg); } // for the other translation units (minmatch.cu)
+}
+namespace {
+
 #define RP_CUDA(call)                                                                                      \
     do {                                                                                                   \
         cudaError_t e_ = (call);                                                                           \
