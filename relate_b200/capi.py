@@ -89,6 +89,7 @@ SYMBOLS = {
     "rp_make_chunks_ex": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_float, C.c_uint,
                                     C.POINTER(C.c_int), C.c_char_p, C.c_size_t]),
     "rp_minmatch_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.POINTER(_P)]),
+    "rp_minmatch_create_thresholds": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(_P)]),
     "rp_minmatch_destroy": (None, [_P]),
     "rp_minmatch_quickbuild": (C.c_int, [_P, _P, _P, _P, C.POINTER(RpMinMatchStats)]),
     "rp_minmatch_quickbuild_device": (C.c_int, [_P, _P, _P, _P, C.POINTER(RpMinMatchStats)]),

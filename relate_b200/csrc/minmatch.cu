@@ -717,7 +717,14 @@ struct rp_minmatch {
 
 extern "C" int rp_minmatch_create(int device, int N, double theta, rp_minmatch **out)
 {
-    if (!out || N < 2 || !(theta > 0 && theta < 1)) return rp::api_fail(RP_EINVAL, "rp_minmatch_create: bad argument");
+    if (!(theta > 0 && theta < 1)) return rp::api_fail(RP_EINVAL, "rp_minmatch_create: bad argument");
+    return rp_minmatch_create_thresholds(device, N, (float)(-0.2 * std::log(theta / (1.0 - theta))),    // tree_builder.cpp:43
+                                         (float)(-0.001 * std::log(theta / (1.0 - theta))), out);        // :44
+}
+
+extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold, float threshold_cf, rp_minmatch **out)
+{
+    if (!out || N < 2) return rp::api_fail(RP_EINVAL, "rp_minmatch_create: bad argument");
     int ndev = 0;
     MM_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return rp::api_fail(RP_ENODEVICE, "rp_minmatch_create: no such device");
@@ -727,8 +734,8 @@ extern "C" int rp_minmatch_create(int device, int N, double theta, rp_minmatch *
     h->N = N;
     MMState &s = h->s;
     s.N = N;
-    s.thr = (float)(-0.2 * std::log(theta / (1.0 - theta)));    // tree_builder.cpp:43
-    s.thr_cf = (float)(-0.001 * std::log(theta / (1.0 - theta))); // :44
+    s.thr = threshold;
+    s.thr_cf = threshold_cf;
     const size_t nn = (size_t)N * N;
     s.cap = (int)std::max<size_t>((size_t)N + 1, std::min<size_t>(nn / 2 + 1, (size_t)1 << 22));
     if (const char *e = getenv("RP_MINMATCH_CAP")) s.cap = std::max(N + 1, atoi(e));

@@ -71,3 +71,66 @@ def test_handle_state_is_per_handle():
             outs.append([g.quickbuild(d, p)[0] for d, p in trees])
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+# ---- through the reference's BuildTopology (oracle/_ref/Relate_gpu: GetMatrix and QuickBuild bound to the C ABI) ------
+import filecmp  # noqa: E402
+import hashlib  # noqa: E402
+import json  # noqa: E402
+import re  # noqa: E402
+import subprocess  # noqa: E402
+import time  # noqa: E402
+
+from relate_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+need_relate_gpu = pytest.mark.skipif(not os.access(oracle.REF_RELATE_GPU, os.X_OK), reason="oracle/_ref/Relate_gpu did not travel")
+
+
+def _bt(cwd, W, out="o", painting="0.001,1", seed="1", **env):
+    t0 = time.perf_counter()
+    p = subprocess.run([oracle.REF_RELATE_GPU, "--mode", "BuildTopology", "--chunk_index", "0", "--first_section", "0",
+                        "--last_section", str(W - 1), "-o", out, "--painting", painting, "--seed", seed],
+                       cwd=cwd, capture_output=True, text=True, env=dict(os.environ, RELATE_GPU_MINMATCH_STATS="1", **env))
+    assert p.returncode == 0, p.stderr[-2000:]
+    m = re.search(r"QuickBuild: (\d+) trees on the GPU \((\d+) by the reference's code\), ([0-9.]+) s in the call, ([0-9.]+) s in the kernel",
+                  p.stderr)
+    assert m, p.stderr[-2000:]
+    return dict(wall=time.perf_counter() - t0, gpu_trees=int(m.group(1)), ref_trees=int(m.group(2)), call_s=float(m.group(3)),
+                kernel_s=float(m.group(4)))
+
+
+@need_relate_gpu
+def test_buildtopology_trees_on_gpu_example_md5(tmp_path):
+    """Bundled example: GPU Paint -> BuildTopology with GPU d_ij AND GPU trees writes the reference's .anc/.mut (golden md5s);
+    with the built-in cross-check every tree is also compared merge by merge with the reference's QuickBuild."""
+    from conftest import unpack_golden
+    unpack_golden("example_c1", str(tmp_path), out="ex")
+    meta = json.load(open(os.path.join(GOLDEN, "example_c1", "topology_md5.json")))
+    capi.paint_chunk(str(tmp_path / "ex"), 0, meta["painting"])
+    for env in ({}, {"RELATE_GPU_MINMATCH_VERIFY": "1"}):
+        st = _bt(str(tmp_path), meta["W"], out="ex", painting=meta["painting"], seed=str(meta["seed"]), **env)
+        assert st["gpu_trees"] > 0 and st["ref_trees"] == 0
+        for fn, want in meta["md5"].items():
+            got = hashlib.md5(open(os.path.join(str(tmp_path), "ex", "chunk_0", fn), "rb").read()).hexdigest()
+            assert got == want, (fn, env)
+
+
+@need_relate_gpu
+@pytest.mark.parametrize("N,L,W", [(200, 3000, 3), (1000, 3000, 1)])
+def test_buildtopology_gpu_trees_byte_identical_to_cpu_trees(tmp_path, N, L, W):
+    """Same paint files, same GPU distance matrices; trees by the reference's CPU QuickBuild (RELATE_GPU_MINMATCH=0) vs by
+    rp_minmatch_quickbuild: the .anc/.mut files must be byte-identical.  Prints what the tree builder costs each way."""
+    for tag in ("cpu", "gpu"):
+        synth.make_chunk_dir(str(tmp_path / tag / "o"), N, L, seed=31, n_windows=W)
+        capi.paint_chunk(str(tmp_path / tag / "o"), 0, "0.001,1")
+    a = _bt(str(tmp_path / "cpu"), W, RELATE_GPU_MINMATCH="0")
+    b = _bt(str(tmp_path / "gpu"), W)
+    assert a["gpu_trees"] == 0 and b["ref_trees"] == 0 and a["ref_trees"] == b["gpu_trees"] > 0
+    for w in range(W):
+        for ext in ("anc", "mut"):
+            assert filecmp.cmp(str(tmp_path / "cpu" / "o" / "chunk_0" / f"o_{w}.{ext}"),
+                               str(tmp_path / "gpu" / "o" / "chunk_0" / f"o_{w}.{ext}"), shallow=False), (w, ext)
+    print(f"\nBuildTopology N={N} L={L}: {b['gpu_trees']} trees; QuickBuild on the CPU {a['call_s']:.3f} s "
+          f"({1e3 * a['call_s'] / a['ref_trees']:.2f} ms/tree), on the GPU {b['call_s']:.3f} s in the call, {b['kernel_s']:.3f} s in the "
+          f"kernel ({1e3 * b['kernel_s'] / b['gpu_trees']:.2f} ms/tree); BuildTopology wall {a['wall']:.2f} s -> {b['wall']:.2f} s")
