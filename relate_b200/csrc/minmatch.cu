@@ -42,21 +42,27 @@ int api_fail(int code, const std::string &msg); // paint_api.cu: sets rp_last_er
 
 namespace {
 
-constexpr int MM_THREADS = 1024;
-constexpr int MM_WARPS = MM_THREADS / 32;
-constexpr unsigned FINF = 0x7f800000u;            // float +inf
-constexpr unsigned long long DINF = 0x7ff0000000000000ull; // double +inf
+constexpr int MM_MAX_WARPS = 32;
+constexpr unsigned KINF = 0xff800000u;                       // fkey(+inf)
+constexpr unsigned long long DINF = 0x7ff0000000000000ull;   // double +inf
+constexpr int RS_MAX = 8;    // rows that look for a new minimum: up to this many block-wide in one pass
+constexpr int U_MAX = 8;     // members of U: up to this many through the block-wide pair test
+constexpr int PAIR_MAX = 128; // pairs of a step: up to this many ranked / applied in shared memory
+constexpr int IMAX = 0x7fffffff;
 
 struct MMState {
     int N;
     float thr, thr_cf;
+    int force_general; // tests: skip the small-case paths
+    int use_smem;      // the per-cluster arrays fit into shared memory (40 bytes per cluster)
     // matrices (row-major N x N)
     float *d, *cf, *sym;
+    float *dT, *cfT; // transposes, kept in step: a column of d is a row of dT (a warp reading a column touches 32 lines)
     // persistent between trees
     float *minv_cf;
     int *cand_a, *cand_b;
-    unsigned *cand_dist;           // float bits (non-negative: bit order == value order)
-    unsigned long long *cand_tie;  // double bits
+    unsigned *cand_dist;           // fkey(dist): order-preserving key of the float
+    unsigned long long *cand_tie;  // double bits (ties are in [0,1) or +inf: bit order == value order)
     int *csym_a, *csym_b;
     float *csym_dist;
     // per tree
@@ -68,29 +74,43 @@ struct MMState {
     int *cnt;      // pairs per row (n_act + 1 entries), then exclusive offsets
     unsigned *key1;
     unsigned long long *key2;
-    // pair buffer
+    // pair buffer of the general path
     int cap;
     int *pa, *pb;
-    float *pw;
+    unsigned *pw;
     unsigned long long *ptie;
     // output
     int *merges;
-    long long *info; // [0] draws, [1] first step without a candidate (-1), [2] steps on the fallback
+    long long *info; // [0] draws, [1] first step without a candidate (-1), [2] steps on the fallback, [3] steps on the general path
 };
 
 struct MMShared {
     unsigned mt[624];
-    float redf[MM_WARPS];
-    unsigned redu[MM_WARPS];
-    unsigned long long redull[MM_WARPS];
-    int redi[MM_WARPS];
-    int scan[MM_WARPS];
-    int n_rescan, n_u, total, i, j, n_act, p_end;
-    float bf;
-    unsigned bu;
-    unsigned long long bull;
-    int bi;
+    unsigned redu[MM_MAX_WARPS], redu2[MM_MAX_WARPS];
+    unsigned long long redull[MM_MAX_WARPS];
+    int redi[MM_MAX_WARPS];
+    int scan[MM_MAX_WARPS];
+    int n_rescan, total, p_end, pos_i;
+    // rows that look for a new minimum
+    int rs_pos[RS_MAX], rs_cl[RS_MAX], rs_pe[RS_MAX], rs_pl[RS_MAX];
+    unsigned rs_m[RS_MAX];
+    float rs_old[RS_MAX];
+    // U
+    int u_pos[U_MAX], u_cl[U_MAX];
+    float u_minv[U_MAX];
+    // pairs of a small step
+    unsigned long long pk[PAIR_MAX], pt[PAIR_MAX];
+    int pa[PAIR_MAX], pb[PAIR_MAX], prank[PAIR_MAX];
+    unsigned pw[PAIR_MAX];
 };
+
+// order-preserving key of a float (-0 counts as +0): a < b  <=>  fkey(a) < fkey(b)
+__device__ __forceinline__ unsigned fkey(float v)
+{
+    const unsigned b = __float_as_uint(v + 0.0f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float funkey(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
 __device__ __forceinline__ float mix(float si, float a, float sj, float b, float sum)
 {
@@ -106,7 +126,16 @@ __device__ __forceinline__ unsigned temper(unsigned y)
     return y;
 }
 
+// libstdc++ generate_canonical<double, 53>(mt19937): (g1 + g2 * 2^32) / 2^64, as the bits of the double
+__device__ __forceinline__ unsigned long long canonical(unsigned g1, unsigned g2)
+{
+    const double u = __dmul_rn(__dadd_rn(__uint2double_rn(g1), __dmul_rn(__uint2double_rn(g2), 4294967296.0)),
+                               5.42101086242752217003726400434970855712890625e-20);
+    return u >= 1.0 ? 0x3fefffffffffffffull : (unsigned long long)__double_as_longlong(u);
+}
+
 // the next 624 words of std::mt19937 (three dependent thirds)
+template <int TH>
 __device__ void mt_twist(MMShared &sh)
 {
     const int t = threadIdx.x;
@@ -124,52 +153,69 @@ __device__ void mt_twist(MMShared &sh)
     }
 }
 
-__device__ __forceinline__ float block_min(float v, MMShared &sh)
+// two minima at once; every thread gets both (REDUX on order-preserving keys)
+template <int TH>
+__device__ __forceinline__ void block_min2(float &a, float &b, MMShared &sh)
 {
-    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(~0u, v, o));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned ka = __reduce_min_sync(~0u, fkey(a)), kb = __reduce_min_sync(~0u, fkey(b));
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh.redf[threadIdx.x >> 5] = v;
+    if (lane == 0) { sh.redu[warp] = ka; sh.redu2[warp] = kb; }
     __syncthreads();
-    v = sh.redf[threadIdx.x & 31];
-    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(~0u, v, o));
-    return v;
+    ka = __reduce_min_sync(~0u, lane < TH / 32 ? sh.redu[lane] : ~0u);
+    kb = __reduce_min_sync(~0u, lane < TH / 32 ? sh.redu2[lane] : ~0u);
+    a = funkey(ka);
+    b = funkey(kb);
+}
+
+// lexicographic minimum of (a, b, c) over a warp, four REDUX
+__device__ __forceinline__ void warp_lexmin(unsigned &a, unsigned long long &b, int &c)
+{
+    const unsigned m = __reduce_min_sync(~0u, a);
+    bool e = a == m;
+    const unsigned hi = __reduce_min_sync(~0u, e ? (unsigned)(b >> 32) : ~0u);
+    e = e && (unsigned)(b >> 32) == hi;
+    const unsigned lo = __reduce_min_sync(~0u, e ? (unsigned)b : ~0u);
+    e = e && (unsigned)b == lo;
+    c = __reduce_min_sync(~0u, e ? c : IMAX);
+    a = m;
+    b = ((unsigned long long)hi << 32) | lo;
 }
 
 // lexicographic minimum of (a, b, c) over the block; every thread gets the winner
+template <int TH>
 __device__ __forceinline__ void block_lexmin(unsigned &a, unsigned long long &b, int &c, MMShared &sh)
 {
-    auto take = [&](unsigned oa, unsigned long long ob, int oc) {
-        if (oa < a || (oa == a && (ob < b || (ob == b && oc < c)))) { a = oa; b = ob; c = oc; }
-    };
-    for (int o = 16; o; o >>= 1) take(__shfl_xor_sync(~0u, a, o), __shfl_xor_sync(~0u, b, o), __shfl_xor_sync(~0u, c, o));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    warp_lexmin(a, b, c);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) { sh.redu[threadIdx.x >> 5] = a; sh.redull[threadIdx.x >> 5] = b; sh.redi[threadIdx.x >> 5] = c; }
+    if (lane == 0) { sh.redu[warp] = a; sh.redull[warp] = b; sh.redi[warp] = c; }
     __syncthreads();
-    a = sh.redu[threadIdx.x & 31]; b = sh.redull[threadIdx.x & 31]; c = sh.redi[threadIdx.x & 31];
-    for (int o = 16; o; o >>= 1) take(__shfl_xor_sync(~0u, a, o), __shfl_xor_sync(~0u, b, o), __shfl_xor_sync(~0u, c, o));
+    const bool in = lane < TH / 32;
+    a = in ? sh.redu[lane] : ~0u;
+    b = in ? sh.redull[lane] : ~0ull;
+    c = in ? sh.redi[lane] : IMAX;
+    warp_lexmin(a, b, c);
 }
 
 // exclusive prefix sum of arr[0..n) in place; returns the total to every thread
+template <int TH>
 __device__ int block_exscan(int *arr, int n, MMShared &sh)
 {
-    const int t = threadIdx.x, per = (n + MM_THREADS - 1) / MM_THREADS;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, per = (n + TH - 1) / TH;
     const int b = min(t * per, n), e = min(b + per, n);
     int s = 0;
     for (int q = b; q < e; q++) s += arr[q];
     int inc = s;
     for (int o = 1; o < 32; o <<= 1) {
         int u = __shfl_up_sync(~0u, inc, o);
-        if ((t & 31) >= o) inc += u;
+        if (lane >= o) inc += u;
     }
     __syncthreads();
-    if ((t & 31) == 31) sh.scan[t >> 5] = inc;
+    if (lane == 31) sh.scan[warp] = inc;
     __syncthreads();
-    int wbase = 0, total = 0;
-    for (int w = 0; w < MM_WARPS; w++) {
-        int v = sh.scan[w];
-        if (w < (t >> 5)) wbase += v;
-        total += v;
-    }
+    const int wc = lane < TH / 32 ? sh.scan[lane] : 0;
+    const int wbase = __reduce_add_sync(~0u, lane < warp ? wc : 0), total = __reduce_add_sync(~0u, wc);
     int run = wbase + inc - s;
     for (int q = b; q < e; q++) { int v = arr[q]; arr[q] = run; run += v; }
     __syncthreads();
@@ -184,38 +230,49 @@ __device__ __forceinline__ float pair_weight(const MMState &s, bool has_cf, int 
     return __fadd_rn(s.d[x * N + y], s.d[y * N + x]);
 }
 
-enum { ROW_SKIP = 0, ROW_BELOW = 1, ROW_LIST = 2, ROW_ABOVE = 3 };
+enum { ROW_SKIP = 0, ROW_BELOW = 1, ROW_LIST = 2, ROW_ABOVE = 3, ROW_J = 4 };
 
-// Feasible pairs of row p in the reference's order.  EMIT = false: count them; EMIT = true: write them at `base`.
-// Warp-wide for ROW_BELOW / ROW_ABOVE / the j row (all lanes call it), returns the count to every lane.
+// General path.  Feasible pairs of row p in the reference's order.  EMIT = false: count them; EMIT = true: write them at
+// `base`.  Warp-wide (all lanes call it), four 32-element pieces per round so that their loads overlap.
 template <bool EMIT>
 __device__ int row_pairs_warp(const MMState &s, bool has_cf, int n_act, int p, int kind, int ci, int cj, int base)
 {
     const size_t N = s.N;
     const int lane = threadIdx.x & 31;
-    const bool jrow = p == n_act;
+    const bool jrow = kind == ROW_J;
     const int x = jrow ? cj : s.act[p];
     const float mx = s.minv[x];
     const float *dx = s.d + x * N;
     const int q0 = kind == ROW_ABOVE ? p + 1 : 0, q1 = (kind == ROW_BELOW) ? p : n_act;
     int count = 0;
-    for (int qb = q0; qb < q1; qb += 32) {
-        const int q = qb + lane;
-        bool ok = false;
-        int y = -1;
-        if (q < q1) {
-            y = s.act[q];
-            ok = y != ci && y != cj && dx[y] <= mx && s.d[y * N + x] <= s.minv[y];
+    for (int qb = q0; qb < q1; qb += 128) {
+        int y[4];
+        float v[4];
+        bool ok[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int q = qb + 32 * c + lane;
+            y[c] = q < q1 ? s.act[q] : -1;
         }
-        const unsigned m = __ballot_sync(~0u, ok);
-        if (EMIT && ok) {
-            const int r = base + count + __popc(m & ((1u << lane) - 1));
-            // candidate orientation: (row, partner), except for the new cluster's row: (partner, j)   (:565-573)
-            s.pa[r] = jrow ? y : x;
-            s.pb[r] = jrow ? x : y;
-            s.pw[r] = pair_weight(s, has_cf, x, y);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            ok[c] = y[c] >= 0 && y[c] != ci && y[c] != cj;
+            v[c] = ok[c] ? dx[y[c]] : 0.f;
         }
-        count += __popc(m);
+#pragma unroll
+        for (int c = 0; c < 4; c++) ok[c] = ok[c] && v[c] <= mx && s.dT[x * N + y[c]] <= s.minv[y[c]];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const unsigned m = __ballot_sync(~0u, ok[c]);
+            if (EMIT && ok[c]) {
+                const int r = base + count + __popc(m & ((1u << lane) - 1));
+                // candidate orientation: (row, partner), except for the new cluster's row: (partner, j)   (:565-573)
+                s.pa[r] = jrow ? y[c] : x;
+                s.pb[r] = jrow ? x : y[c];
+                s.pw[r] = fkey(pair_weight(s, has_cf, x, y[c]));
+            }
+            count += __popc(m);
+        }
     }
     return count;
 }
@@ -233,11 +290,11 @@ __device__ int row_pairs_list(const MMState &s, bool has_cf, int p, int n_u, int
         const int pu = s.ulist[u];
         if (pu >= p) break;
         const int y = s.act[pu];
-        if (dx[y] <= mx && s.d[y * N + x] <= s.minv[y]) {
+        if (dx[y] <= mx && s.dT[x * N + y] <= s.minv[y]) {
             if (EMIT) {
                 s.pa[base + count] = x;
                 s.pb[base + count] = y;
-                s.pw[base + count] = pair_weight(s, has_cf, x, y);
+                s.pw[base + count] = fkey(pair_weight(s, has_cf, x, y));
             }
             count++;
         }
@@ -245,43 +302,44 @@ __device__ int row_pairs_list(const MMState &s, bool has_cf, int p, int n_u, int
     return count;
 }
 
-// Phases D + E for the rows described by flag[] (init: every row looks above itself): count, rank, draw, apply.
+__device__ __forceinline__ int row_kind(const MMState &s, bool init, int n_act, int p, int ci, int cj)
+{
+    if (init) return ROW_ABOVE;
+    if (p == n_act) return ROW_J;
+    const int k = s.act[p];
+    return (k == ci || k == cj) ? ROW_SKIP : ((s.flag[k] & 4) ? ROW_BELOW : ROW_LIST);
+}
+
+// General path of phases D + E (init: every row looks above itself): count, rank, draw, apply.  Any number of pairs.
+template <int TH>
 __device__ void meet_pairs(const MMState &s, MMShared &sh, bool has_cf, bool init, int n_act, int ci, int cj, int n_u,
                            int &rng_pos, long long &draws)
 {
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int rows = init ? n_act : n_act + 1; // + the new cluster's row
-    // D: counts
-    for (int p = warp; p < rows; p += MM_WARPS) {
-        int kind;
-        if (init) kind = ROW_ABOVE;
-        else if (p == n_act) kind = ROW_LIST + 100; // j row: everybody
-        else {
-            const int k = s.act[p];
-            kind = (k == ci || k == cj) ? ROW_SKIP : ((s.flag[k] & 4) ? ROW_BELOW : ROW_LIST);
-        }
+    for (int p = warp; p < rows; p += (TH / 32)) {
+        const int kind = row_kind(s, init, n_act, p, ci, cj);
         if (kind == ROW_SKIP) { if (lane == 0) s.cnt[p] = 0; continue; }
         if (kind == ROW_LIST) continue; // thread-level below
         const int c = row_pairs_warp<false>(s, has_cf, n_act, p, kind, ci, cj, 0);
         if (lane == 0) s.cnt[p] = c;
     }
     if (!init)
-        for (int p = t; p < n_act; p += MM_THREADS) {
+        for (int p = t; p < n_act; p += TH) {
             const int k = s.act[p];
             if (k == ci || k == cj || (s.flag[k] & 4)) continue;
             s.cnt[p] = n_u ? row_pairs_list<false>(s, has_cf, p, n_u, 0) : 0;
         }
     __syncthreads();
-    const int total = block_exscan(s.cnt, rows, sh);
+    const int total = block_exscan<TH>(s.cnt, rows, sh);
     if (total == 0) return;
-    // E: segments of at most cap pairs (one segment unless a tie-heavy matrix meets a small buffer)
+    // segments of at most cap pairs (one segment unless a tie-heavy matrix meets a small buffer)
     int p0 = 0;
     while (p0 < rows) {
-        // last row of the segment
         if (t == 0) sh.p_end = rows;
         __syncthreads();
         const int off0 = s.cnt[p0];
-        for (int p = p0 + t; p < rows; p += MM_THREADS) {
+        for (int p = p0 + t; p < rows; p += TH) {
             const int endp = (p + 1 < rows) ? s.cnt[p + 1] : total;
             if (endp - off0 > s.cap && s.cnt[p] - off0 <= s.cap) sh.p_end = max(p, p0 + 1);
         }
@@ -290,19 +348,13 @@ __device__ void meet_pairs(const MMState &s, MMShared &sh, bool has_cf, bool ini
         const int seg_total = ((p1 < rows) ? s.cnt[p1] : total) - off0;
         __syncthreads();
         if (seg_total > 0) {
-            for (int p = p0 + warp; p < p1; p += MM_WARPS) {
-                int kind;
-                if (init) kind = ROW_ABOVE;
-                else if (p == n_act) kind = ROW_LIST + 100;
-                else {
-                    const int k = s.act[p];
-                    kind = (k == ci || k == cj) ? ROW_SKIP : ((s.flag[k] & 4) ? ROW_BELOW : ROW_LIST);
-                }
+            for (int p = p0 + warp; p < p1; p += (TH / 32)) {
+                const int kind = row_kind(s, init, n_act, p, ci, cj);
                 if (kind == ROW_SKIP || kind == ROW_LIST) continue;
                 row_pairs_warp<true>(s, has_cf, n_act, p, kind, ci, cj, s.cnt[p] - off0);
             }
             if (!init && n_u)
-                for (int p = p0 + t; p < min(p1, n_act); p += MM_THREADS) {
+                for (int p = p0 + t; p < min(p1, n_act); p += TH) {
                     const int k = s.act[p];
                     if (k == ci || k == cj || (s.flag[k] & 4)) continue;
                     row_pairs_list<true>(s, has_cf, p, n_u, s.cnt[p] - off0);
@@ -310,44 +362,38 @@ __device__ void meet_pairs(const MMState &s, MMShared &sh, bool has_cf, bool ini
             // draws, in rank order
             int cur = 0;
             while (cur < seg_total) {
-                if (rng_pos == 312) { mt_twist(sh); rng_pos = 0; }
+                if (rng_pos == 312) { mt_twist<TH>(sh); rng_pos = 0; }
                 const int n = min(312 - rng_pos, seg_total - cur);
-                for (int r = t; r < n; r += MM_THREADS) {
-                    const unsigned g1 = temper(sh.mt[2 * (rng_pos + r)]), g2 = temper(sh.mt[2 * (rng_pos + r) + 1]);
-                    double u = __dmul_rn(__dadd_rn(__uint2double_rn(g1), __dmul_rn(__uint2double_rn(g2), 4294967296.0)),
-                                         5.42101086242752217003726400434970855712890625e-20);
-                    unsigned long long ub = (unsigned long long)__double_as_longlong(u);
-                    if (u >= 1.0) ub = 0x3fefffffffffffffull;
-                    s.ptie[cur + r] = ub;
-                }
+                for (int r = t; r < n; r += TH)
+                    s.ptie[cur + r] = canonical(temper(sh.mt[2 * (rng_pos + r)]), temper(sh.mt[2 * (rng_pos + r) + 1]));
                 rng_pos += n;
                 cur += n;
                 __syncthreads();
             }
             draws += seg_total;
             // apply: both members keep the smallest (weight, draw) among their candidate and the new pairs
-            for (int p = t; p < n_act; p += MM_THREADS) { const int k = s.act[p]; __stcg(&s.key1[k], s.cand_dist[k]); }
+            for (int p = t; p < n_act; p += TH) { const int k = s.act[p]; __stcg(&s.key1[k], s.cand_dist[k]); }
             __syncthreads();
-            for (int r = t; r < seg_total; r += MM_THREADS) {
-                const unsigned wb = __float_as_uint(s.pw[r]);
+            for (int r = t; r < seg_total; r += TH) {
+                const unsigned wb = s.pw[r];
                 atomicMin(&s.key1[s.pa[r]], wb);
                 atomicMin(&s.key1[s.pb[r]], wb);
             }
             __syncthreads();
-            for (int p = t; p < n_act; p += MM_THREADS) {
+            for (int p = t; p < n_act; p += TH) {
                 const int k = s.act[p];
                 __stcg(&s.key2[k], s.cand_dist[k] == __ldcg(&s.key1[k]) ? s.cand_tie[k] : ~0ull);
             }
             __syncthreads();
-            for (int r = t; r < seg_total; r += MM_THREADS) {
-                const unsigned wb = __float_as_uint(s.pw[r]);
+            for (int r = t; r < seg_total; r += TH) {
+                const unsigned wb = s.pw[r];
                 const int a = s.pa[r], b = s.pb[r];
                 if (wb == __ldcg(&s.key1[a])) atomicMin(&s.key2[a], s.ptie[r]);
                 if (wb == __ldcg(&s.key1[b])) atomicMin(&s.key2[b], s.ptie[r]);
             }
             __syncthreads();
-            for (int r = t; r < seg_total; r += MM_THREADS) {
-                const unsigned wb = __float_as_uint(s.pw[r]);
+            for (int r = t; r < seg_total; r += TH) {
+                const unsigned wb = s.pw[r];
                 const unsigned long long tb = s.ptie[r];
                 const int a = s.pa[r], b = s.pb[r];
                 for (int e = 0; e < 2; e++) {
@@ -364,35 +410,206 @@ __device__ void meet_pairs(const MMState &s, MMShared &sh, bool has_cf, bool ini
     }
 }
 
-// first position of `what` in act[0..n_act)
-__device__ void remove_active(const MMState &s, MMShared &sh, int n_act, int what)
+// Small-case path of phases D + E: at most U_MAX members of U and at most PAIR_MAX pairs.  Every pair with a member of U is
+// tested by the thread of the OTHER cluster's position (both in U: the later one), row j by every thread; the pairs found
+// are ranked by (row position, partner position) — the order the reference meets them in — in shared memory.
+// Returns false (nothing changed) if there are more than PAIR_MAX pairs.
+template <int TH, int NU>
+__device__ bool meet_pairs_small(const MMState &s, MMShared &sh, bool has_cf, int n_act, int ci, int cj, int n_u, int &rng_pos,
+                                 long long &draws)
 {
+    const size_t N = s.N;
     const int t = threadIdx.x;
-    if (t == 0) sh.bi = n_act;
+    const float *dj = s.d + cj * N, *dTj = s.dT + cj * N;
+    const float mj = s.minv[cj];
+    // E positions per thread and round: their loads are issued together (a CTA of a few warps cannot hide an L2 round trip
+    // per position otherwise)
+    constexpr int E = TH > 512 ? 1 : (TH > 256 ? (NU <= 2 ? 2 : 1) : (NU <= 2 ? 4 : (NU <= 4 ? 2 : 1))), NA = NU ? NU : 1;
+    for (int q0 = t; q0 < n_act; q0 += TH * E) {
+        int k[E], onm[E];
+        float mk[E], a[E][NA], b[E][NA], ja[E], jb[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const int q = q0 + e * TH;
+            k[e] = q < n_act ? s.act[q] : -1;
+            if (k[e] == ci || k[e] == cj) k[e] = -1;
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            onm[e] = 0;
+            if (k[e] < 0) continue;
+            const int q = q0 + e * TH;
+            const bool in_u = (s.flag[k[e]] & 4) != 0;
+            mk[e] = s.minv[k[e]];
+#pragma unroll
+            for (int ui = 0; ui < NU; ui++) {
+                const bool on = ui < n_u && q != sh.u_pos[ui] && !(in_u && q < sh.u_pos[ui]);
+                onm[e] |= on ? (1 << ui) : 0;
+                a[e][ui] = on ? s.d[sh.u_cl[ui] * N + k[e]] : 0.f;
+                b[e][ui] = on ? s.dT[sh.u_cl[ui] * N + k[e]] : 0.f;
+            }
+            ja[e] = dj[k[e]];
+            jb[e] = dTj[k[e]];
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            if (k[e] < 0) continue;
+            const int q = q0 + e * TH;
+#pragma unroll
+            for (int ui = 0; ui < NU; ui++)
+                if (((onm[e] >> ui) & 1) && b[e][ui] <= mk[e] && a[e][ui] <= sh.u_minv[ui]) {
+                    const int idx = atomicAdd(&sh.total, 1);
+                    if (idx < PAIR_MAX) {
+                        const int pu = sh.u_pos[ui], u = sh.u_cl[ui];
+                        const bool k_is_row = q > pu;
+                        sh.pk[idx] = ((unsigned long long)max(q, pu) << 32) | (unsigned)min(q, pu);
+                        sh.pa[idx] = k_is_row ? k[e] : u;
+                        sh.pb[idx] = k_is_row ? u : k[e];
+                        sh.pw[idx] = fkey(pair_weight(s, has_cf, k[e], u));
+                    }
+                }
+            if (ja[e] <= mj && jb[e] <= mk[e]) {
+                const int idx = atomicAdd(&sh.total, 1);
+                if (idx < PAIR_MAX) {
+                    sh.pk[idx] = ((unsigned long long)n_act << 32) | (unsigned)q;
+                    sh.pa[idx] = k[e]; // (:565-573)
+                    sh.pb[idx] = cj;
+                    sh.pw[idx] = fkey(pair_weight(s, has_cf, cj, k[e]));
+                }
+            }
+        }
+    }
     __syncthreads();
-    for (int p = t; p < n_act; p += MM_THREADS)
-        if (s.act[p] == what) sh.bi = p;
+    const int total = sh.total;
+    if (total == 0) return true;
+    if (total > PAIR_MAX) return false;
+    if (t < total) {
+        int rank = 0;
+        const unsigned long long mine = sh.pk[t];
+        for (int r = 0; r < total; r++) rank += sh.pk[r] < mine;
+        sh.prank[t] = rank;
+    }
+    int base = 0;
+    while (base < total) {
+        if (rng_pos == 312) { mt_twist<TH>(sh); rng_pos = 0; }
+        const int n = min(312 - rng_pos, total - base);
+        if (t < total) {
+            const int r = sh.prank[t] - base;
+            if (r >= 0 && r < n) sh.pt[t] = canonical(temper(sh.mt[2 * (rng_pos + r)]), temper(sh.mt[2 * (rng_pos + r) + 1]));
+        }
+        rng_pos += n;
+        base += n;
+        __syncthreads();
+    }
+    draws += total;
+    bool win[2] = {false, false};
+    if (t < total) {
+        for (int e = 0; e < 2; e++) {
+            const int x = e ? sh.pb[t] : sh.pa[t];
+            unsigned bw = s.cand_dist[x];
+            unsigned long long bt = s.cand_tie[x];
+            int w = -1;
+            for (int r = 0; r < total; r++)
+                if ((sh.pa[r] == x || sh.pb[r] == x) && (sh.pw[r] < bw || (sh.pw[r] == bw && sh.pt[r] < bt))) { bw = sh.pw[r]; bt = sh.pt[r]; w = r; }
+            win[e] = w == t;
+        }
+    }
     __syncthreads();
-    const int at = sh.bi;
-    // shift left by one behind `at` (chunks of MM_THREADS, front to back)
-    for (int b = at; b < n_act - 1; b += MM_THREADS) {
-        const int p = b + t;
-        int v = 0;
-        if (p < n_act - 1) v = s.act[p + 1];
-        __syncthreads();
-        if (p < n_act - 1) s.act[p] = v;
-        __syncthreads();
+    if (t < total)
+        for (int e = 0; e < 2; e++)
+            if (win[e]) {
+                const int x = e ? sh.pb[t] : sh.pa[t];
+                s.cand_a[x] = sh.pa[t]; s.cand_b[x] = sh.pb[t]; s.cand_dist[x] = sh.pw[t]; s.cand_tie[x] = sh.pt[t];
+            }
+    return true;
+}
+
+// Phase B, small case: the rows that look for a new minimum, all in one block-wide pass (thread q holds column act[q] of each).
+template <int TH, int NR>
+__device__ __forceinline__ void rescan_rows(const MMState &s, MMShared &sh, int n_act, int ci, int n_rescan)
+{
+    const size_t N = s.N;
+    const int t = threadIdx.x, lane = t & 31;
+    constexpr int E = TH > 512 ? 1 : (TH > 256 ? (NR <= 2 ? 2 : 1) : (NR <= 2 ? 4 : (NR <= 4 ? 2 : 1)));
+    for (int qb = 0; qb < n_act; qb += TH * E) {
+        int l[E];
+        float v[E][NR];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const int q = qb + e * TH + t;
+            l[e] = q < n_act ? s.act[q] : -1;
+            if (l[e] == ci) l[e] = -1;
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++)
+#pragma unroll
+            for (int r = 0; r < NR; r++) v[e][r] = (r < n_rescan && l[e] >= 0 && l[e] != sh.rs_cl[r]) ? s.d[sh.rs_cl[r] * N + l[e]] : 0.f;
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            if (r >= n_rescan) break;
+            const float old = sh.rs_old[r];
+            unsigned m = ~0u;
+            int pe = IMAX, pl = IMAX;
+#pragma unroll
+            for (int e = E - 1; e >= 0; e--) { // (descending, so that the smallest position wins)
+                const int q = qb + e * TH + t;
+                if (l[e] >= 0 && l[e] != sh.rs_cl[r]) {
+                    m = min(m, fkey(v[e][r]));
+                    if (v[e][r] == old) pe = q;
+                    if (v[e][r] < old) pl = q;
+                }
+            }
+            m = __reduce_min_sync(~0u, m);
+            pe = __reduce_min_sync(~0u, pe);
+            pl = __reduce_min_sync(~0u, pl);
+            if (lane == 0) {
+                if (m != ~0u) atomicMin(&sh.rs_m[r], m);
+                if (pe != IMAX) atomicMin(&sh.rs_pe[r], pe);
+                if (pl != IMAX) atomicMin(&sh.rs_pl[r], pl);
+            }
+        }
     }
 }
 
-__global__ void __launch_bounds__(MM_THREADS, 1) mm_quickbuild_kernel(MMState s, int has_cf_i)
+#ifdef MM_PROF
+#define MM_MARK(i) do { if (threadIdx.x == 0) { long long now_ = clock64(); prof[i] += now_ - last_; last_ = now_; } } while (0)
+#else
+#define MM_MARK(i) do { } while (0)
+#endif
+
+template <int TH>
+__global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has_cf_i)
 {
     __shared__ MMShared sh;
+#ifdef MM_PROF
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last_ = clock64();
+#endif
     const bool has_cf = has_cf_i != 0;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const size_t N = s.N;
     const float thr = s.thr, thr_cf = s.thr_cf;
-    const float finf = __uint_as_float(FINF);
+    const float finf = __int_as_float(0x7f800000);
+
+    // The per-cluster arrays are rewritten in every step, and a global store drops the line from L1: kept in global memory
+    // every phase starts with a chain of L2 round trips (measured: 12 us per merge step, independent of N).  They live in
+    // shared memory whenever they fit (N <= ~5000); what outlives the tree is loaded here and written back at the end.
+    float *const g_minv_cf = s.minv_cf;
+    int *const g_cand_a = s.cand_a, *const g_cand_b = s.cand_b;
+    if (s.use_smem) {
+        extern __shared__ __align__(16) unsigned char dyn[];
+        const size_t n4 = ((size_t)s.N + 3) & ~(size_t)3;
+        s.cand_tie = (unsigned long long *)dyn;
+        unsigned *w = (unsigned *)(dyn + 8 * n4);
+        s.cand_dist = w;             w += n4;
+        s.cand_a = (int *)w;         w += n4;
+        s.cand_b = (int *)w;         w += n4;
+        s.act = (int *)w;            w += n4;
+        s.flag = (int *)w;           w += n4;
+        s.minv = (float *)w;         w += n4;
+        s.minv_cf = (float *)w;      w += n4;
+        s.cnt = (int *)w;            // n4 + 4 entries
+        for (int k = t; k < s.N; k += TH) { s.minv_cf[k] = g_minv_cf[k]; s.cand_a[k] = g_cand_a[k]; s.cand_b[k] = g_cand_b[k]; }
+    }
 
     // rng.seed(1)
     if (t == 0) {
@@ -401,21 +618,28 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_quickbuild_kernel(MMState s,
         for (int q = 1; q < 624; q++) { v = 1812433253u * (v ^ (v >> 30)) + (unsigned)q; sh.mt[q] = v; }
     }
     int rng_pos = 312;
-    long long draws = 0;
+    long long draws = 0, general_steps = 0;
     int n_act = s.N;
-    for (int k = t; k < s.N; k += MM_THREADS) {
+    for (int k = t; k < s.N; k += TH) {
         s.act[k] = k; s.conv[k] = k; s.size[k] = 1.0f; s.minv_sym[k] = finf; s.flag[k] = 0;
-        s.cand_dist[k] = FINF; s.cand_tie[k] = DINF;
+        s.cand_dist[k] = KINF; s.cand_tie[k] = DINF;
     }
     __syncthreads();
     // Initialize: row minima (+ the prior's, which start from what the previous tree left)
-    for (int k = warp; k < s.N; k += MM_WARPS) {
+    for (int k = warp; k < s.N; k += (TH / 32)) {
         float m = finf, mc = finf;
-        for (int l = lane; l < s.N; l += 32)
-            if (l != k) {
-                m = fminf(m, s.d[k * N + l]);
-                if (has_cf) mc = fminf(mc, s.cf[k * N + l]);
+        for (int lb = 0; lb < s.N; lb += 128) {
+            float v[4], c[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int l = lb + 32 * e + lane;
+                const bool ok = l < s.N && l != k;
+                v[e] = ok ? s.d[k * N + l] : finf;
+                c[e] = (ok && has_cf) ? s.cf[k * N + l] : finf;
             }
+#pragma unroll
+            for (int e = 0; e < 4; e++) { m = fminf(m, v[e]); mc = fminf(mc, c[e]); }
+        }
         for (int o = 16; o; o >>= 1) { m = fminf(m, __shfl_xor_sync(~0u, m, o)); mc = fminf(mc, __shfl_xor_sync(~0u, mc, o)); }
         if (lane == 0) {
             s.minv[k] = __fadd_rn(m, thr);
@@ -423,69 +647,71 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_quickbuild_kernel(MMState s,
         }
     }
     __syncthreads();
-    meet_pairs(s, sh, has_cf, true, n_act, -1, -1, 0, rng_pos, draws);
+    meet_pairs<TH>(s, sh, has_cf, true, n_act, -1, -1, 0, rng_pos, draws);
     __syncthreads();
 
+    MM_MARK(0);
     bool use_sym = false;
     long long first_sym = -1, sym_steps = 0;
-    unsigned sbest_d = FINF; // best_sym_candidate
+    unsigned sbest_d = KINF; // best_sym_candidate
     int sbest_a = -1, sbest_b = -1;
 
     for (int node = s.N; node < 2 * s.N - 1; node++) {
         // F (of the previous step): the best candidate over the active clusters
-        unsigned ba = FINF;
+        unsigned ba = KINF;
         unsigned long long bb = DINF;
-        int bp = 0x7fffffff;
-        for (int p = t; p < n_act; p += MM_THREADS) {
+        int bp = IMAX;
+        for (int p = t; p < n_act; p += TH) {
             const int k = s.act[p];
             const unsigned da = s.cand_dist[k];
             const unsigned long long db = s.cand_tie[k];
             if (da < ba || (da == ba && (db < bb || (db == bb && p < bp)))) { ba = da; bb = db; bp = p; }
         }
-        block_lexmin(ba, bb, bp, sh);
+        block_lexmin<TH>(ba, bb, bp, sh);
         int ci, cj;
-        if (ba == FINF) { // no mutually minimal pair: symmetric fallback (:1244-1256)
+        if (ba == KINF) { // no mutually minimal pair: symmetric fallback (:1244-1256)
             if (!use_sym) {
                 use_sym = true;
                 first_sym = node - s.N;
                 // InitializeSym
-                for (size_t e = t; e < (size_t)n_act * n_act; e += MM_THREADS) {
+                for (size_t e = t; e < (size_t)n_act * n_act; e += TH) {
                     const int x = s.act[e / n_act], y = s.act[e % n_act];
                     if (x < y) {
-                        const float v = __fadd_rn(s.d[x * N + y], s.d[y * N + x]);
+                        const float v = __fadd_rn(s.d[x * N + y], s.dT[x * N + y]);
                         s.sym[x * N + y] = v;
                         s.sym[y * N + x] = v;
                     }
                 }
                 __syncthreads();
-                for (int p = warp; p < n_act; p += MM_WARPS) {
+                for (int p = warp; p < n_act; p += (TH / 32)) {
                     const int x = s.act[p];
-                    float m = finf;
-                    int mq = 0x7fffffff;
+                    unsigned m = ~0u;
+                    int mq = IMAX;
                     for (int q = lane; q < n_act; q += 32) {
                         const int l = s.act[q];
                         if (l == x) continue;
-                        const float v = s.sym[x * N + l];
+                        const unsigned v = fkey(s.sym[x * N + l]);
                         if (v < m) { m = v; mq = q; }
                     }
                     for (int o = 16; o; o >>= 1) {
-                        const float om = __shfl_xor_sync(~0u, m, o);
+                        const unsigned om = __shfl_xor_sync(~0u, m, o);
                         const int oq = __shfl_xor_sync(~0u, mq, o);
                         if (om < m || (om == m && oq < mq)) { m = om; mq = oq; }
                     }
                     if (lane == 0) {
-                        s.minv_sym[x] = m; // min_values_sym starts at +inf for every cluster
-                        s.csym_dist[x] = m;
-                        if (m < finf) { s.csym_a[x] = x; s.csym_b[x] = s.act[mq]; }
+                        const float mv = (mq == IMAX || m >= KINF) ? finf : funkey(m); // min_values_sym starts at +inf for every cluster
+                        s.minv_sym[x] = mv;
+                        s.csym_dist[x] = mv;
+                        if (mv < finf) { s.csym_a[x] = x; s.csym_b[x] = s.act[mq]; }
                     }
                 }
                 __syncthreads();
-                unsigned a = FINF; unsigned long long b = 0; int c = 0x7fffffff;
-                for (int p = t; p < n_act; p += MM_THREADS) {
-                    const unsigned v = __float_as_uint(s.csym_dist[s.act[p]]);
+                unsigned a = KINF; unsigned long long b = 0; int c = IMAX;
+                for (int p = t; p < n_act; p += TH) {
+                    const unsigned v = fkey(s.csym_dist[s.act[p]]);
                     if (v < a || (v == a && p < c)) { a = v; c = p; }
                 }
-                block_lexmin(a, b, c, sh);
+                block_lexmin<TH>(a, b, c, sh);
                 if (a < sbest_d) { sbest_d = a; sbest_a = s.csym_a[s.act[c]]; sbest_b = s.csym_b[s.act[c]]; }
             }
             ci = sbest_a;
@@ -497,111 +723,180 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_quickbuild_kernel(MMState s,
         }
         if (use_sym) sym_steps++;
         __syncthreads();
+        MM_MARK(1);
         const float si = s.size[ci], sj = s.size[cj], sum = __fadd_rn(si, sj);
         if (t == 0) {
             s.merges[2 * (node - s.N)] = s.conv[ci];
             s.merges[2 * (node - s.N) + 1] = s.conv[cj];
             sh.n_rescan = 0;
+            sh.total = 0;
         }
         __syncthreads();
 
         // A: rows / columns j
-        float *di = s.d + ci * N, *dj = s.d + cj * N;
+        float *di = s.d + ci * N, *dj = s.d + cj * N, *dTi = s.dT + ci * N, *dTj = s.dT + cj * N;
         float min_j = finf, min_cf = finf;
-        for (int p = t; p < n_act; p += MM_THREADS) {
-            const int k = s.act[p];
-            if (k == ci || k == cj) continue;
-            if (has_cf) {
-                float *ck = s.cf + k * N;
-                const float ckj = ck[cj], cki = ck[ci], cik = s.cf[ci * N + k], cjk = s.cf[cj * N + k];
-                float njk = cjk;
-                if (cik != cjk) { njk = mix(si, cik, sj, cjk, sum); s.cf[cj * N + k] = njk; }
-                if (cki != ckj) ck[cj] = mix(si, cki, sj, ckj, sum);
-                min_cf = fminf(min_cf, njk);
+        constexpr int EA = TH > 512 ? 1 : (TH > 256 ? 2 : 4); // positions per thread and round, loads issued together
+        for (int p0 = t; p0 < n_act; p0 += TH * EA) {
+            int k[EA];
+            float dkj[EA], dki[EA], dik[EA], djk[EA], ckj[EA], cki[EA], cik[EA], cjk[EA];
+#pragma unroll
+            for (int e = 0; e < EA; e++) {
+                const int p = p0 + e * TH;
+                k[e] = p < n_act ? s.act[p] : -1;
+                if (k[e] == ci) sh.pos_i = p;
+                if (k[e] == ci || k[e] == cj) k[e] = -1;
             }
-            float *dk = s.d + k * N;
-            const float dkj = dk[cj], dki = dk[ci], dik = di[k], djk = dj[k];
-            float njk = djk;
-            if (dik != djk) { njk = mix(si, dik, sj, djk, sum); dj[k] = njk; }
-            if (dki != dkj) dk[cj] = mix(si, dki, sj, dkj, sum);
-            min_j = fminf(min_j, njk);
-            const float mk = s.minv[k];
-            int f = 0;
-            const int ca = s.cand_a[k], cb = s.cand_b[k];
-            if (ca == cj || cb == cj || ca == ci || cb == ci) f = 1;
-            if (dkj != dki) {
-                const float base = __fsub_rn(mk, thr);
-                if ((double)fabsf(__fsub_rn(base, dkj)) < 1e-4 || (double)fabsf(__fsub_rn(base, dki)) < 1e-4)
-                    s.rescan[atomicAdd(&sh.n_rescan, 1)] = p;
+#pragma unroll
+            for (int e = 0; e < EA; e++) {
+                if (k[e] < 0) continue;
+                dkj[e] = dTj[k[e]]; dki[e] = dTi[k[e]]; dik[e] = di[k[e]]; djk[e] = dj[k[e]];
+                if (has_cf) { ckj[e] = s.cfT[cj * N + k[e]]; cki[e] = s.cfT[ci * N + k[e]]; cik[e] = s.cf[ci * N + k[e]]; cjk[e] = s.cf[cj * N + k[e]]; }
             }
-            s.flag[k] = f;
+#pragma unroll
+            for (int e = 0; e < EA; e++) {
+                if (k[e] < 0) continue;
+                const int kk = k[e], p = p0 + e * TH;
+                if (has_cf) {
+                    float njk = cjk[e];
+                    if (cik[e] != cjk[e]) { njk = mix(si, cik[e], sj, cjk[e], sum); s.cf[cj * N + kk] = njk; s.cfT[kk * N + cj] = njk; }
+                    if (cki[e] != ckj[e]) { const float nkj = mix(si, cki[e], sj, ckj[e], sum); s.cf[kk * N + cj] = nkj; s.cfT[cj * N + kk] = nkj; }
+                    min_cf = fminf(min_cf, njk);
+                }
+                float njk = djk[e];
+                if (dik[e] != djk[e]) { njk = mix(si, dik[e], sj, djk[e], sum); dj[kk] = njk; s.dT[kk * N + cj] = njk; }
+                if (dki[e] != dkj[e]) { const float nkj = mix(si, dki[e], sj, dkj[e], sum); s.d[kk * N + cj] = nkj; dTj[kk] = nkj; }
+                min_j = fminf(min_j, njk);
+                const float mk = s.minv[kk];
+                int f = 0;
+                const int ca = s.cand_a[kk], cb = s.cand_b[kk];
+                if (ca == cj || cb == cj || ca == ci || cb == ci) f = 1;
+                if (dkj[e] != dki[e]) {
+                    const float base = __fsub_rn(mk, thr);
+                    if ((double)fabsf(__fsub_rn(base, dkj[e])) < 1e-4 || (double)fabsf(__fsub_rn(base, dki[e])) < 1e-4) {
+                        const int idx = atomicAdd(&sh.n_rescan, 1);
+                        s.rescan[idx] = p;
+                        if (idx < RS_MAX) { sh.rs_pos[idx] = p; sh.rs_cl[idx] = kk; sh.rs_old[idx] = base; sh.rs_m[idx] = ~0u; sh.rs_pe[idx] = IMAX; sh.rs_pl[idx] = IMAX; }
+                    }
+                }
+                s.flag[kk] = f;
+            }
         }
-        min_j = block_min(min_j, sh);
-        if (has_cf) min_cf = block_min(min_cf, sh);
+        block_min2<TH>(min_j, min_cf, sh);
         if (t == 0) {
             s.minv[cj] = __fadd_rn(min_j, thr);
             if (has_cf) s.minv_cf[cj] = __fadd_rn(min_cf, thr_cf);
             s.flag[cj] = 0;
-            s.cand_dist[cj] = FINF; // mcandidates[j] starts over (:541-542)
+            s.cand_dist[cj] = KINF; // mcandidates[j] starts over (:541-542)
             s.cand_tie[cj] = DINF;
         }
         __syncthreads();
 
+        MM_MARK(2);
         // B: new row minima
         const int n_rescan = sh.n_rescan;
-        for (int it = warp; it < n_rescan; it += MM_WARPS) {
-            const int k = s.act[s.rescan[it]];
-            const float *dk = s.d + k * N;
-            const float old = __fsub_rn(s.minv[k], thr);
-            float m = finf;
-            int pe = 0x7fffffff, pl = 0x7fffffff;
-            for (int q = lane; q < n_act; q += 32) {
-                const int l = s.act[q];
-                if (l == ci || l == k) continue;
-                const float v = dk[l];
-                m = fminf(m, v);
-                if (v == old) pe = min(pe, q);
-                if (v < old) pl = min(pl, q);
-            }
-            for (int o = 16; o; o >>= 1) {
-                m = fminf(m, __shfl_xor_sync(~0u, m, o));
-                pe = min(pe, __shfl_xor_sync(~0u, pe, o));
-                pl = min(pl, __shfl_xor_sync(~0u, pl, o));
-            }
-            if (lane == 0) {
-                const float mk = (pe != 0x7fffffff && pe < pl) ? old : m; // the scan stops at the old minimum (:337-339)
+        if (n_rescan > 0 && n_rescan <= RS_MAX && !s.force_general) {
+            // all rows in one block-wide pass: thread q holds column act[q] of each of them
+            if (n_rescan == 1) rescan_rows<TH, 1>(s, sh, n_act, ci, n_rescan);
+            else if (n_rescan == 2) rescan_rows<TH, 2>(s, sh, n_act, ci, n_rescan);
+            else if (n_rescan <= 4) rescan_rows<TH, 4>(s, sh, n_act, ci, n_rescan);
+            else rescan_rows<TH, RS_MAX>(s, sh, n_act, ci, n_rescan);
+            __syncthreads();
+            if (t < n_rescan) {
+                const int k = sh.rs_cl[t];
+                const float m = sh.rs_m[t] == ~0u ? finf : funkey(sh.rs_m[t]);
+                const float mk = (sh.rs_pe[t] != IMAX && sh.rs_pe[t] < sh.rs_pl[t]) ? sh.rs_old[t] : m; // the scan stops at the old minimum (:337-339)
                 s.minv[k] = __fadd_rn(mk, thr);
                 s.flag[k] |= 2;
             }
+        } else {
+            for (int it = warp; it < n_rescan; it += (TH / 32)) {
+                const int k = s.act[s.rescan[it]];
+                const float *dk = s.d + k * N;
+                const float old = __fsub_rn(s.minv[k], thr);
+                unsigned m = ~0u;
+                int pe = IMAX, pl = IMAX;
+                for (int qb = 0; qb < n_act; qb += 128) {
+                    float v[4];
+                    bool on[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int q = qb + 32 * e + lane;
+                        const int l = q < n_act ? s.act[q] : -1;
+                        on[e] = l >= 0 && l != ci && l != k;
+                        v[e] = on[e] ? dk[l] : 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (on[e]) {
+                            const int q = qb + 32 * e + lane;
+                            m = min(m, fkey(v[e]));
+                            if (v[e] == old) pe = min(pe, q);
+                            if (v[e] < old) pl = min(pl, q);
+                        }
+                }
+                m = __reduce_min_sync(~0u, m);
+                pe = __reduce_min_sync(~0u, pe);
+                pl = __reduce_min_sync(~0u, pl);
+                if (lane == 0) {
+                    const float mv = m == ~0u ? finf : funkey(m);
+                    const float mk = (pe != IMAX && pe < pl) ? old : mv;
+                    s.minv[k] = __fadd_rn(mk, thr);
+                    s.flag[k] |= 2;
+                }
+            }
         }
         __syncthreads();
 
+        MM_MARK(3);
         // C: U in order; its members' candidates start over
-        for (int p = t; p < n_act; p += MM_THREADS) {
-            const int k = s.act[p];
-            const bool in = k != ci && k != cj && s.flag[k] != 0;
-            s.cnt[p] = in ? 1 : 0;
-            if (in) { s.flag[k] |= 4; s.cand_dist[k] = FINF; s.cand_tie[k] = DINF; }
+        int n_u = 0;
+        for (int pb = 0; pb < n_act; pb += TH) {
+            const int p = pb + t;
+            const int k = p < n_act ? s.act[p] : -1;
+            const bool in = k >= 0 && k != ci && k != cj && s.flag[k] != 0;
+            const unsigned m = __ballot_sync(~0u, in);
+            if (lane == 0) sh.scan[warp] = __popc(m);
+            __syncthreads();
+            const int wc = lane < TH / 32 ? sh.scan[lane] : 0;
+            const int off = n_u + __reduce_add_sync(~0u, lane < warp ? wc : 0), tot = __reduce_add_sync(~0u, wc);
+            if (in) {
+                const int idx = off + __popc(m & ((1u << lane) - 1));
+                s.ulist[idx] = p;
+                if (idx < U_MAX) { sh.u_pos[idx] = p; sh.u_cl[idx] = k; sh.u_minv[idx] = s.minv[k]; }
+                s.flag[k] |= 4;
+                s.cand_dist[k] = KINF;
+                s.cand_tie[k] = DINF;
+            }
+            n_u += tot;
+            __syncthreads();
         }
-        __syncthreads();
-        const int n_u = block_exscan(s.cnt, n_act, sh);
-        for (int p = t; p < n_act; p += MM_THREADS) {
-            const int k = s.act[p];
-            if (k != ci && k != cj && (s.flag[k] & 4)) s.ulist[s.cnt[p]] = p;
-        }
-        __syncthreads();
 
+        MM_MARK(4);
         // D, E
-        meet_pairs(s, sh, has_cf, false, n_act, ci, cj, n_u, rng_pos, draws);
+        bool done = false;
+        if (n_u <= U_MAX && !s.force_general) {
+            if (n_u == 0) done = meet_pairs_small<TH, 0>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
+            else if (n_u == 1) done = meet_pairs_small<TH, 1>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
+            else if (n_u == 2) done = meet_pairs_small<TH, 2>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
+            else if (n_u <= 4) done = meet_pairs_small<TH, 4>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
+            else done = meet_pairs_small<TH, U_MAX>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
+        }
+        if (!done) {
+            general_steps++;
+            __syncthreads();
+            meet_pairs<TH>(s, sh, has_cf, false, n_act, ci, cj, n_u, rng_pos, draws);
+        }
         __syncthreads();
 
+        MM_MARK(5);
         // the symmetric matrix follows once it is in use (CoalesceSym)
         if (use_sym) {
             if (t == 0) sh.n_rescan = 0;
             __syncthreads();
             float *yi = s.sym + ci * N, *yj = s.sym + cj * N;
-            unsigned ja = FINF; unsigned long long jb = 0; int jp = 0x7fffffff;
-            for (int p = t; p < n_act; p += MM_THREADS) {
+            unsigned ja = KINF; unsigned long long jb = 0; int jp = IMAX;
+            for (int p = t; p < n_act; p += TH) {
                 const int k = s.act[p];
                 if (k == ci || k == cj) continue;
                 float *yk = s.sym + k * N;
@@ -609,7 +904,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_quickbuild_kernel(MMState s,
                 float njk = djk;
                 if (dik != djk) { njk = mix(si, dik, sj, djk, sum); yj[k] = njk; }
                 if (dki != dkj) yk[cj] = mix(si, dki, sj, dkj, sum);
-                const unsigned nb = __float_as_uint(njk);
+                const unsigned nb = fkey(njk);
                 if (nb < ja || (nb == ja && p < jp)) { ja = nb; jp = p; }
                 if (dkj != dki) {
                     const float mk = s.minv_sym[k];
@@ -620,55 +915,58 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_quickbuild_kernel(MMState s,
                     if (s.csym_b[k] == ci) s.csym_b[k] = cj;
                 }
             }
-            block_lexmin(ja, jb, jp, sh);
+            block_lexmin<TH>(ja, jb, jp, sh);
             __syncthreads();
             if (t == 0) {
-                s.minv_sym[cj] = __uint_as_float(ja);
-                s.csym_dist[cj] = __uint_as_float(ja);
-                if (ja != FINF) { s.csym_a[cj] = s.act[jp]; s.csym_b[cj] = cj; }
+                const float mv = (jp == IMAX || ja >= KINF) ? finf : funkey(ja);
+                s.minv_sym[cj] = mv;
+                s.csym_dist[cj] = mv;
+                if (mv < finf) { s.csym_a[cj] = s.act[jp]; s.csym_b[cj] = cj; }
             }
             const int n_rs = sh.n_rescan;
-            for (int it = warp; it < n_rs; it += MM_WARPS) {
+            for (int it = warp; it < n_rs; it += (TH / 32)) {
                 const int k = s.act[s.rescan[it]];
                 const float *yk = s.sym + k * N;
                 const float old = s.minv_sym[k];
-                float m = finf;
-                int mq = 0x7fffffff, pe = 0x7fffffff, pl = 0x7fffffff;
+                unsigned m = ~0u;
+                int mq = IMAX, pe = IMAX, pl = IMAX;
                 for (int q = lane; q < n_act; q += 32) {
                     const int l = s.act[q];
                     if (l == ci || l == k) continue;
                     const float v = yk[l];
-                    if (v < m) { m = v; mq = q; }
+                    const unsigned vk = fkey(v);
+                    if (vk < m) { m = vk; mq = q; }
                     if (v == old) pe = min(pe, q);
                     if (v < old) pl = min(pl, q);
                 }
                 for (int o = 16; o; o >>= 1) {
-                    const float om = __shfl_xor_sync(~0u, m, o);
+                    const unsigned om = __shfl_xor_sync(~0u, m, o);
                     const int oq = __shfl_xor_sync(~0u, mq, o);
                     if (om < m || (om == m && oq < mq)) { m = om; mq = oq; }
-                    pe = min(pe, __shfl_xor_sync(~0u, pe, o));
-                    pl = min(pl, __shfl_xor_sync(~0u, pl, o));
                 }
+                pe = __reduce_min_sync(~0u, pe);
+                pl = __reduce_min_sync(~0u, pl);
                 if (lane == 0) {
-                    if (pe != 0x7fffffff && pe < pl) { m = old; mq = pe; }
-                    s.minv_sym[k] = m;
-                    s.csym_dist[k] = m;
-                    if (m < finf) { s.csym_a[k] = k; s.csym_b[k] = s.act[mq]; }
+                    float mv = (mq == IMAX || m >= KINF) ? finf : funkey(m);
+                    if (pe != IMAX && pe < pl) { mv = old; mq = pe; }
+                    s.minv_sym[k] = mv;
+                    s.csym_dist[k] = mv;
+                    if (mv < finf) { s.csym_a[k] = k; s.csym_b[k] = s.act[mq]; }
                 }
             }
             __syncthreads();
             // best_sym_candidate: first cluster in order with the smallest candidate, the new cluster last
-            unsigned a = FINF; unsigned long long b = 0; int c = 0x7fffffff;
-            for (int p = t; p < n_act; p += MM_THREADS) {
+            unsigned a = KINF; unsigned long long b = 0; int c = IMAX;
+            for (int p = t; p < n_act; p += TH) {
                 const int k = s.act[p];
                 if (k == ci) continue;
-                const unsigned v = __float_as_uint(s.csym_dist[k]);
+                const unsigned v = fkey(s.csym_dist[k]);
                 const int ord = (k == cj) ? n_act : p;
                 if (v < a || (v == a && ord < c)) { a = v; c = ord; }
             }
-            block_lexmin(a, b, c, sh);
+            block_lexmin<TH>(a, b, c, sh);
             sbest_d = a;
-            if (a != FINF) {
+            if (a != KINF) {
                 const int k = (c == n_act) ? cj : s.act[c];
                 sbest_a = s.csym_a[k];
                 sbest_b = s.csym_b[k];
@@ -676,19 +974,51 @@ __global__ void __launch_bounds__(MM_THREADS, 1) mm_quickbuild_kernel(MMState s,
             __syncthreads();
         }
 
-        // bookkeeping
+        // bookkeeping: the new cluster's size and name, cluster i leaves the list
         if (t == 0) {
             s.size[cj] = sum;
             s.conv[cj] = node;
         }
-        remove_active(s, sh, n_act, ci);
+        const int at = sh.pos_i;
+        for (int b = at; b < n_act - 1; b += TH) {
+            const int p = b + t;
+            int v = 0;
+            if (p < n_act - 1) v = s.act[p + 1];
+            __syncthreads();
+            if (p < n_act - 1) s.act[p] = v;
+        }
         n_act--;
         __syncthreads();
+        MM_MARK(6);
     }
+    if (s.use_smem)
+        for (int k = t; k < s.N; k += TH) { g_minv_cf[k] = s.minv_cf[k]; g_cand_a[k] = s.cand_a[k]; g_cand_b[k] = s.cand_b[k]; }
     if (t == 0) {
+#ifdef MM_PROF
+        for (int q = 0; q < 7; q++) s.info[4 + q] = prof[q];
+#endif
         s.info[0] = draws;
         s.info[1] = first_sym;
         s.info[2] = sym_steps;
+        s.info[3] = general_steps;
+    }
+}
+
+// dT = d^T (z = 0) and cfT = cf^T (z = 1), 32 x 32 tiles through shared memory
+__global__ void mm_transpose_kernel(const float *d, float *dT, const float *cf, float *cfT, int N)
+{
+    __shared__ float tile[32][33];
+    const float *src = blockIdx.z ? cf : d;
+    float *dst = blockIdx.z ? cfT : dT;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int x = x0 + threadIdx.x, y = y0 + r;
+        if (x < N && y < N) tile[r][threadIdx.x] = src[(size_t)y * N + x];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int x = y0 + threadIdx.x, y = x0 + r;
+        if (x < N && y < N) dst[(size_t)y * N + x] = tile[threadIdx.x][r];
     }
 }
 
@@ -699,6 +1029,8 @@ struct rp_minmatch {
     int device = 0, N = 0;
     MMState s{};
     void *block = nullptr; // one allocation behind every array
+    size_t dyn_smem = 0;
+    int threads = 256;
     int *h_merges = nullptr; // pinned
     long long *h_info = nullptr;
     cudaStream_t stream = nullptr;
@@ -742,8 +1074,8 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
     // layout of the single block (8-byte items first)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_tie = take(8 * (size_t)N), o_key2 = take(8 * (size_t)N), o_ptie = take(8 * (size_t)s.cap), o_info = take(64);
-    const size_t o_d = take(4 * nn), o_cf = take(4 * nn), o_sym = take(4 * nn);
+    const size_t o_tie = take(8 * (size_t)N), o_key2 = take(8 * (size_t)N), o_ptie = take(8 * (size_t)s.cap), o_info = take(128);
+    const size_t o_d = take(4 * nn), o_cf = take(4 * nn), o_sym = take(4 * nn), o_dT = take(4 * nn), o_cfT = take(4 * nn);
     const size_t o_f[5] = {take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N)};
     const size_t o_i[12] = {take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N),
                             take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N),
@@ -760,14 +1092,14 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
     s.key2 = (unsigned long long *)(b + o_key2);
     s.ptie = (unsigned long long *)(b + o_ptie);
     s.info = (long long *)(b + o_info);
-    s.d = (float *)(b + o_d); s.cf = (float *)(b + o_cf); s.sym = (float *)(b + o_sym);
+    s.d = (float *)(b + o_d); s.cf = (float *)(b + o_cf); s.sym = (float *)(b + o_sym); s.dT = (float *)(b + o_dT); s.cfT = (float *)(b + o_cfT);
     s.minv_cf = (float *)(b + o_f[0]); s.csym_dist = (float *)(b + o_f[1]); s.minv = (float *)(b + o_f[2]);
     s.minv_sym = (float *)(b + o_f[3]); s.size = (float *)(b + o_f[4]);
     s.cand_a = (int *)(b + o_i[0]); s.cand_b = (int *)(b + o_i[1]); s.cand_dist = (unsigned *)(b + o_i[2]);
     s.csym_a = (int *)(b + o_i[3]); s.csym_b = (int *)(b + o_i[4]); s.conv = (int *)(b + o_i[5]); s.act = (int *)(b + o_i[6]);
     s.flag = (int *)(b + o_i[7]); s.rescan = (int *)(b + o_i[8]); s.cnt = (int *)(b + o_i[9]); s.ulist = (int *)(b + o_i[10]);
     s.key1 = (unsigned *)(b + o_i[11]);
-    s.pa = (int *)(b + o_pa); s.pb = (int *)(b + o_pb); s.pw = (float *)(b + o_pw);
+    s.pa = (int *)(b + o_pa); s.pb = (int *)(b + o_pb); s.pw = (unsigned *)(b + o_pw);
     s.merges = (int *)(b + o_merges);
     // a fresh MinMatch object: min_values_CF = 0 (vector::resize), candidates name nobody (lin1 = lin2 = -1)
     MM_CUDA(cudaMemset(s.minv_cf, 0, 4 * (size_t)N));
@@ -776,11 +1108,33 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
     MM_CUDA(cudaMemset(s.csym_a, 0xff, 4 * (size_t)N));
     MM_CUDA(cudaMemset(s.csym_b, 0xff, 4 * (size_t)N));
     MM_CUDA(cudaMemset(s.csym_dist, 0x7f, 4 * (size_t)N));
+    s.force_general = getenv("RP_MINMATCH_GENERAL") ? atoi(getenv("RP_MINMATCH_GENERAL")) : 0;
+    {
+        const size_t n4 = ((size_t)N + 3) & ~(size_t)3, want = 40 * n4 + 16;
+        int max_optin = 0;
+        MM_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        // one CTA per tree; the merge loop is bound by instruction issue on its SM, and everything every warp does per phase
+        // (reductions, barriers) counts once per warp: few warps for small N (measured: N=200 1.24 / 1.30 / 1.67 ms per tree with
+        // 256 / 512 / 1024 threads, N=1000 10.4 / 9.7 / 11.0 ms)
+        h->threads = getenv("RP_MINMATCH_THREADS") ? atoi(getenv("RP_MINMATCH_THREADS")) : (N < 512 ? 256 : (N <= 2048 ? 512 : 1024));
+        if (h->threads != 256 && h->threads != 512) h->threads = 1024;
+        cudaFuncAttributes fa;
+        if (h->threads == 256) MM_CUDA(cudaFuncGetAttributes(&fa, mm_quickbuild_kernel<256>));
+        else if (h->threads == 512) MM_CUDA(cudaFuncGetAttributes(&fa, mm_quickbuild_kernel<512>));
+        else MM_CUDA(cudaFuncGetAttributes(&fa, mm_quickbuild_kernel<1024>));
+        if (!getenv("RP_MINMATCH_NO_SMEM") && want + fa.sharedSizeBytes <= (size_t)max_optin) {
+            if (h->threads == 256) MM_CUDA(cudaFuncSetAttribute(mm_quickbuild_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+            else if (h->threads == 512) MM_CUDA(cudaFuncSetAttribute(mm_quickbuild_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+            else MM_CUDA(cudaFuncSetAttribute(mm_quickbuild_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+            h->dyn_smem = want;
+            s.use_smem = 1;
+        }
+    }
     MM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     MM_CUDA(cudaEventCreate(&h->e0));
     MM_CUDA(cudaEventCreate(&h->e1));
     MM_CUDA(cudaMallocHost(&h->h_merges, 8 * (size_t)N));
-    MM_CUDA(cudaMallocHost(&h->h_info, 64));
+    MM_CUDA(cudaMallocHost(&h->h_info, 128));
     *out = h;
     return RP_OK;
 }
@@ -801,11 +1155,17 @@ extern "C" void rp_minmatch_destroy(rp_minmatch *h)
 static int mm_run(rp_minmatch *h, bool has_prior, int *merges, rp_minmatch_stats *st)
 {
     MM_CUDA(cudaEventRecord(h->e0, h->stream));
-    mm_quickbuild_kernel<<<1, MM_THREADS, 0, h->stream>>>(h->s, has_prior ? 1 : 0);
+    {
+        const dim3 grid((h->N + 31) / 32, (h->N + 31) / 32, has_prior ? 2 : 1);
+        mm_transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(h->s.d, h->s.dT, h->s.cf, h->s.cfT, h->N);
+    }
+    if (h->threads == 256) mm_quickbuild_kernel<256><<<1, 256, h->dyn_smem, h->stream>>>(h->s, has_prior ? 1 : 0);
+    else if (h->threads == 512) mm_quickbuild_kernel<512><<<1, 512, h->dyn_smem, h->stream>>>(h->s, has_prior ? 1 : 0);
+    else mm_quickbuild_kernel<1024><<<1, 1024, h->dyn_smem, h->stream>>>(h->s, has_prior ? 1 : 0);
     MM_CUDA(cudaGetLastError());
     MM_CUDA(cudaEventRecord(h->e1, h->stream));
     MM_CUDA(cudaMemcpyAsync(h->h_merges, h->s.merges, 8 * (size_t)(h->N - 1), cudaMemcpyDeviceToHost, h->stream));
-    MM_CUDA(cudaMemcpyAsync(h->h_info, h->s.info, 24, cudaMemcpyDeviceToHost, h->stream));
+    MM_CUDA(cudaMemcpyAsync(h->h_info, h->s.info, 128, cudaMemcpyDeviceToHost, h->stream));
     MM_CUDA(cudaStreamSynchronize(h->stream));
     memcpy(merges, h->h_merges, 8 * (size_t)(h->N - 1));
     MM_CUDA(cudaEventElapsedTime(&h->last_ms, h->e0, h->e1));
@@ -814,8 +1174,13 @@ static int mm_run(rp_minmatch *h, bool has_prior, int *merges, rp_minmatch_stats
         st->draws = h->h_info[0];
         st->first_fallback_step = (int)h->h_info[1];
         st->fallback_steps = (int)h->h_info[2];
-        st->launches = 1;
+        st->general_steps = (int)h->h_info[3];
+        st->launches = 2;
     }
+#ifdef MM_PROF
+    fprintf(stderr, "mm_prof cycles: init %lld | F %lld A %lld B %lld C %lld DE %lld sym %lld book %lld\n", h->h_info[4], h->h_info[5], h->h_info[6],
+            h->h_info[7], h->h_info[8], h->h_info[9], h->h_info[10], h->h_info[11] - 0);
+#endif
     return RP_OK;
 }
 

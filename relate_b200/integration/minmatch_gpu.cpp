@@ -12,6 +12,8 @@
 // code runs, as it does for every stage this repo leaves to the reference) and for the built-in cross-check.
 //
 //   RELATE_GPU_MINMATCH=0          trees by the reference's CPU code (A/B timing)
+//   RELATE_GPU_MINMATCH_MIN_N=<n>  smallest N built on the GPU (default 512: one CTA per tree pays ~10 us per merge whatever N
+//                                  is, the CPU 0.6 ms per tree at N=200 and 16 ms at N=1000, 0.8 s at N=5000; measured on B200)
 //   RELATE_GPU_MINMATCH_VERIFY=1   build every tree both ways and abort on the first differing merge
 //   RELATE_GPU_MINMATCH_STATS=1    one line on stderr at exit: trees, seconds in QuickBuild, kernel seconds
 //   RELATE_GPU_DEVICE=<i>          CUDA device (default 0)
@@ -48,6 +50,7 @@ Builders g;
 
 const bool use_gpu = !(getenv("RELATE_GPU_MINMATCH") && atoi(getenv("RELATE_GPU_MINMATCH")) == 0);
 const bool verify = getenv("RELATE_GPU_MINMATCH_VERIFY") != nullptr;
+const int min_n = getenv("RELATE_GPU_MINMATCH_MIN_N") ? atoi(getenv("RELATE_GPU_MINMATCH_MIN_N")) : 512;
 
 void store_tree(Tree &tree, const int *merges, int N)
 {
@@ -115,7 +118,7 @@ static void gpu_quickbuild(MinMatch *self, int &slot, int N, float threshold, fl
 void MinMatch::QuickBuild(CollapsedMatrix<float> &d, Tree &tree, std::vector<double> &sample_ages, Tree *tmpl_tree)
 {
     const auto t0 = std::chrono::steady_clock::now();
-    if (!use_gpu || tmpl_tree != NULL || (int)sample_ages.size() == N) {
+    if (!use_gpu || N < min_n || tmpl_tree != NULL || (int)sample_ages.size() == N) {
         rp_ref_minmatch_quickbuild(this, d, tree, sample_ages, tmpl_tree);
         g.trees_ref++;
     } else
@@ -126,7 +129,7 @@ void MinMatch::QuickBuild(CollapsedMatrix<float> &d, Tree &tree, std::vector<dou
 void MinMatch::QuickBuild(CollapsedMatrix<float> &d, Tree &tree, std::vector<double> &sample_ages, const CollapsedMatrix<float> &d_prior)
 {
     const auto t0 = std::chrono::steady_clock::now();
-    if (!use_gpu || (int)sample_ages.size() == N) {
+    if (!use_gpu || N < min_n || (int)sample_ages.size() == N) {
         rp_ref_minmatch_quickbuild_prior(this, d, tree, sample_ages, d_prior);
         g.trees_ref++;
     } else

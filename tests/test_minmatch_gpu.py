@@ -91,7 +91,8 @@ def _bt(cwd, W, out="o", painting="0.001,1", seed="1", **env):
     t0 = time.perf_counter()
     p = subprocess.run([oracle.REF_RELATE_GPU, "--mode", "BuildTopology", "--chunk_index", "0", "--first_section", "0",
                         "--last_section", str(W - 1), "-o", out, "--painting", painting, "--seed", seed],
-                       cwd=cwd, capture_output=True, text=True, env=dict(os.environ, RELATE_GPU_MINMATCH_STATS="1", **env))
+                       cwd=cwd, capture_output=True, text=True,
+                       env=dict(os.environ, RELATE_GPU_MINMATCH_STATS="1", RELATE_GPU_MINMATCH_MIN_N="0", **env))
     assert p.returncode == 0, p.stderr[-2000:]
     m = re.search(r"QuickBuild: (\d+) trees on the GPU \((\d+) by the reference's code\), ([0-9.]+) s in the call, ([0-9.]+) s in the kernel",
                   p.stderr)
