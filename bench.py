@@ -411,6 +411,54 @@ def sharded_leg(name, devices, peaks, reps=3):
 
 
 # --------------------------------------------------------------------------------------------------
+def tree_builder_leg(device, sizes=((1000, 3), (5000, 2))):
+    """Row f4: rp_minmatch_quickbuild (one CTA per tree) on seeded GetMatrix-shaped matrix sequences (tests/mm_cases.py: the
+    first tree without a prior, the next with the prior BuildTopology derives from the previous tree) against the reference's
+    own MinMatch::QuickBuild timed on one host core (oracle/_ref/qblens; the oracle port if the lens did not travel).  Checks
+    that the GPU merge lists are identical to the CPU ones."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mm_cases
+    from oracle import oracle
+    from relate_b200 import capi
+    out = []
+    for N, T in sizes:
+        res = []
+        with capi.MinMatch(N, mm_cases.THETA, device=device) as g:
+            def build(d, prior):
+                t0 = time.perf_counter()
+                m, st = g.quickbuild(d, prior)
+                res.append((m, st, time.perf_counter() - t0))
+                return m
+            trees = mm_cases.tree_sequence(1, N, "tree", T, oracle.prior_from_merges, build)
+            # warm second pass over the same inputs on a fresh handle (the first launch of a process loads the module)
+        warm = []
+        with capi.MinMatch(N, mm_cases.THETA, device=device) as g:
+            for d, prior in trees:
+                t0 = time.perf_counter()
+                m, st = g.quickbuild(d, prior)
+                warm.append((m, st, time.perf_counter() - t0))
+        tmpd = tempfile.mkdtemp(prefix="relate_qb_")
+        try:
+            if os.access(oracle.REF_QBLENS, os.X_OK):
+                ref, secs = oracle.reference_quickbuild(N, mm_cases.THETA, trees, tmpd)
+                kind = "reference"
+            else:
+                o = oracle.MinMatchOracle(N, mm_cases.THETA)
+                t0 = time.perf_counter()
+                ref = [o.quickbuild(d, prior)[0] for d, prior in trees]
+                secs, kind = time.perf_counter() - t0, "port"
+        finally:
+            shutil.rmtree(tmpd, ignore_errors=True)
+        same = all(np.array_equal(ref[t], warm[t][0]) and np.array_equal(ref[t], res[t][0]) for t in range(T))
+        out.append({"N": N, "trees": T, "gpu_ms_per_tree_kernel": sum(w[1]["ms_kernel"] for w in warm) / T,
+                    "gpu_ms_per_tree_call": 1e3 * sum(w[2] for w in warm) / T, "cpu_ms_per_tree": 1e3 * secs / T, "cpu_kind": kind,
+                    "cpu_cores": 1, "draws_per_tree": sum(w[1]["draws"] for w in warm) / T,
+                    "general_steps": sum(w[1]["general_steps"] for w in warm), "merge_lists_identical": bool(same)})
+    return {"what": "MinMatch::QuickBuild (src/tree_builder.cpp:1060-1303, 2357-2646) per tree, host matrices in (H2D inside the call), "
+                    "merge list out; one CTA per tree", "sizes": out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -584,6 +632,11 @@ def main():
                     line["e2e_resident"] = dict(resident_leg(out_dir, local_rank, N_HAP), workload=WORKLOAD)
                 except Exception as e:
                     line["e2e_resident"] = {"error": f"{type(e).__name__}: {e}"}
+            if world == 1:
+                try:
+                    line["tree_builder"] = tree_builder_leg(local_rank)
+                except Exception as e:
+                    line["tree_builder"] = {"error": f"{type(e).__name__}: {e}"}
             if world == 1 and not args.no_cpu_baseline:
                 cb = cpu_baseline_sample()
                 line["cpu_baseline"] = cb
