@@ -223,7 +223,8 @@ typedef struct rp_minmatch_stats {
     long long draws;          /* random numbers drawn = feasible pairs met                          */
     int first_fallback_step;  /* first merge without a mutually minimal pair (-1: none)              */
     int fallback_steps;       /* merges taken while the symmetric fallback matrix was in use         */
-    int general_steps;        /* merges whose pairs went through the any-size path (many ties)       */
+    int general_steps;        /* merges whose pairs went through the any-size path (> 63 rows to rescan) */
+    int medium_steps;         /* merges with more than 128 feasible pairs (ties): ballot-ranked path   */
     int launches;
 } rp_minmatch_stats;
 int rp_minmatch_create(int device, int N, double theta, rp_minmatch **out);

@@ -46,7 +46,7 @@ class RpStats(C.Structure):
 
 class RpMinMatchStats(C.Structure):
     _fields_ = [("ms_kernel", C.c_float), ("draws", C.c_longlong), ("first_fallback_step", C.c_int),
-                ("fallback_steps", C.c_int), ("general_steps", C.c_int), ("launches", C.c_int)]
+                ("fallback_steps", C.c_int), ("general_steps", C.c_int), ("medium_steps", C.c_int), ("launches", C.c_int)]
 
 
 class RpTune(C.Structure):

@@ -72,6 +72,7 @@ struct MMState {
     int *rescan;   // positions whose row needs a new minimum
     int *ulist;    // positions of U, ascending
     int *cnt;      // pairs per row (n_act + 1 entries), then exclusive offsets
+    int *wcnt;     // medium path: pairs per U row and warp of positions, 64 x (N / 32 + 1)
     unsigned *key1;
     unsigned long long *key2;
     // pair buffer of the general path
@@ -81,7 +82,8 @@ struct MMState {
     unsigned long long *ptie;
     // output
     int *merges;
-    long long *info; // [0] draws, [1] first step without a candidate (-1), [2] steps on the fallback, [3] steps on the general path
+    long long *info; // [0] draws, [1] first step without a candidate (-1), [2] steps on the fallback, [3] steps on the general path,
+                     // [12] steps on the medium path ([4..11]: per-phase cycles with -DMM_PROF)
 };
 
 struct MMShared {
@@ -222,12 +224,13 @@ __device__ int block_exscan(int *arr, int n, MMShared &sh)
     return total;
 }
 
-// weight of a feasible pair (x, y): with a prior matrix 0 if the pair is mutually minimal there too, else d + d^T
+// weight of a feasible pair (x, y): with a prior matrix 0 if the pair is mutually minimal there too, else d + d^T.  Symmetric in
+// (x, y); everything is read from row x of a matrix or of its transpose, so callers pass the cluster their warp shares as x.
 __device__ __forceinline__ float pair_weight(const MMState &s, bool has_cf, int x, int y)
 {
     const size_t N = s.N;
-    if (has_cf && s.cf[x * N + y] <= s.minv_cf[x] && s.cf[y * N + x] <= s.minv_cf[y]) return 0.0f;
-    return __fadd_rn(s.d[x * N + y], s.d[y * N + x]);
+    if (has_cf && s.cf[x * N + y] <= s.minv_cf[x] && s.cfT[x * N + y] <= s.minv_cf[y]) return 0.0f;
+    return __fadd_rn(s.d[x * N + y], s.dT[x * N + y]);
 }
 
 enum { ROW_SKIP = 0, ROW_BELOW = 1, ROW_LIST = 2, ROW_ABOVE = 3, ROW_J = 4 };
@@ -277,27 +280,39 @@ __device__ int row_pairs_warp(const MMState &s, bool has_cf, int n_act, int p, i
     return count;
 }
 
-// a row outside U meets the earlier members of U only
+// a row outside U meets the earlier members of U only.  One thread per row: d[x][y] is read as dT[y][x] and d[y][x] as such, so
+// that the threads of a warp (neighbouring x, the same y) share cache lines
 template <bool EMIT>
 __device__ int row_pairs_list(const MMState &s, bool has_cf, int p, int n_u, int base)
 {
     const size_t N = s.N;
     const int x = s.act[p];
     const float mx = s.minv[x];
-    const float *dx = s.d + x * N;
     int count = 0;
-    for (int u = 0; u < n_u; u++) {
-        const int pu = s.ulist[u];
-        if (pu >= p) break;
-        const int y = s.act[pu];
-        if (dx[y] <= mx && s.dT[x * N + y] <= s.minv[y]) {
-            if (EMIT) {
-                s.pa[base + count] = x;
-                s.pb[base + count] = y;
-                s.pw[base + count] = fkey(pair_weight(s, has_cf, x, y));
-            }
-            count++;
+    for (int u0 = 0; u0 < n_u; u0 += 4) {
+        int y[4];
+        float a[4], b[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int pu = u0 + e < n_u ? s.ulist[u0 + e] : 0x7fffffff;
+            y[e] = pu < p ? s.act[pu] : -1;
         }
+        if (y[0] < 0) break;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            a[e] = y[e] >= 0 ? s.dT[y[e] * N + x] : 0.f; // d[x][y]
+            b[e] = y[e] >= 0 ? s.d[y[e] * N + x] : 0.f;  // d[y][x]
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (y[e] >= 0 && a[e] <= mx && b[e] <= s.minv[y[e]]) {
+                if (EMIT) {
+                    s.pa[base + count] = x;
+                    s.pb[base + count] = y[e];
+                    s.pw[base + count] = fkey(pair_weight(s, has_cf, y[e], x));
+                }
+                count++;
+            }
     }
     return count;
 }
@@ -308,6 +323,78 @@ __device__ __forceinline__ int row_kind(const MMState &s, bool init, int n_act, 
     if (p == n_act) return ROW_J;
     const int k = s.act[p];
     return (k == ci || k == cj) ? ROW_SKIP : ((s.flag[k] & 4) ? ROW_BELOW : ROW_LIST);
+}
+
+// Pairs 0..total-1 of the pair buffer, in the order the reference meets them: pair r takes the r-th next draw; both members keep
+// the lexicographically smallest (weight, draw) among their candidate and the new pairs (three rounds of atomicMin on keys
+// that are initialised from the members' current candidates).
+template <int TH>
+__device__ void draw_and_apply(const MMState &s, MMShared &sh, int total, int &rng_pos, long long &draws)
+{
+    const int t = threadIdx.x;
+    int cur = 0;
+    while (cur < total) {
+        if (rng_pos == 312) { mt_twist<TH>(sh); rng_pos = 0; }
+        const int n = min(312 - rng_pos, total - cur);
+        for (int r = t; r < n; r += TH)
+            s.ptie[cur + r] = canonical(temper(sh.mt[2 * (rng_pos + r)]), temper(sh.mt[2 * (rng_pos + r) + 1]));
+        rng_pos += n;
+        cur += n;
+        __syncthreads();
+    }
+    draws += total;
+    for (int r = t; r < total; r += TH) {
+        const int a = s.pa[r], b = s.pb[r];
+        __stcg(&s.key1[a], s.cand_dist[a]);
+        __stcg(&s.key1[b], s.cand_dist[b]);
+    }
+    __syncthreads();
+    // (pairs of one row are neighbours in the buffer and share a member: one atomic per warp and member, not one per pair)
+    for (int r0 = 0; r0 < total; r0 += TH) {
+        const int r = r0 + t;
+        const bool in = r < total;
+        const unsigned wb = in ? s.pw[r] : ~0u;
+        for (int e = 0; e < 2; e++) {
+            const int x = in ? (e ? s.pb[r] : s.pa[r]) : -1;
+            const unsigned grp = __match_any_sync(~0u, x);
+            const unsigned m = __reduce_min_sync(grp, wb);
+            if (in && (threadIdx.x & 31) == __ffs(grp) - 1) atomicMin(&s.key1[x], m);
+        }
+    }
+    __syncthreads();
+    for (int r = t; r < total; r += TH) {
+        const int a = s.pa[r], b = s.pb[r];
+        __stcg(&s.key2[a], s.cand_dist[a] == __ldcg(&s.key1[a]) ? s.cand_tie[a] : ~0ull);
+        __stcg(&s.key2[b], s.cand_dist[b] == __ldcg(&s.key1[b]) ? s.cand_tie[b] : ~0ull);
+    }
+    __syncthreads();
+    for (int r0 = 0; r0 < total; r0 += TH) {
+        const int r = r0 + t;
+        const bool in = r < total;
+        const unsigned wb = in ? s.pw[r] : ~0u;
+        const unsigned long long tb = in ? s.ptie[r] : ~0ull;
+        for (int e = 0; e < 2; e++) {
+            const int x = in ? (e ? s.pb[r] : s.pa[r]) : -1;
+            const bool cand = in && wb == __ldcg(&s.key1[x]);
+            const unsigned grp = __match_any_sync(~0u, x);
+            const unsigned hi = __reduce_min_sync(grp, cand ? (unsigned)(tb >> 32) : ~0u);
+            const unsigned lo = __reduce_min_sync(grp, (cand && (unsigned)(tb >> 32) == hi) ? (unsigned)tb : ~0u);
+            if (in && (threadIdx.x & 31) == __ffs(grp) - 1 && !(hi == ~0u && lo == ~0u)) atomicMin(&s.key2[x], ((unsigned long long)hi << 32) | lo);
+        }
+    }
+    __syncthreads();
+    for (int r = t; r < total; r += TH) {
+        const unsigned wb = s.pw[r];
+        const unsigned long long tb = s.ptie[r];
+        const int a = s.pa[r], b = s.pb[r];
+        for (int e = 0; e < 2; e++) {
+            const int x = e ? b : a;
+            if (wb == __ldcg(&s.key1[x]) && tb == __ldcg(&s.key2[x]) && !(s.cand_dist[x] == wb && s.cand_tie[x] <= tb)) {
+                s.cand_a[x] = a; s.cand_b[x] = b; s.cand_dist[x] = wb; s.cand_tie[x] = tb;
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // General path of phases D + E (init: every row looks above itself): count, rank, draw, apply.  Any number of pairs.
@@ -359,52 +446,7 @@ __device__ void meet_pairs(const MMState &s, MMShared &sh, bool has_cf, bool ini
                     if (k == ci || k == cj || (s.flag[k] & 4)) continue;
                     row_pairs_list<true>(s, has_cf, p, n_u, s.cnt[p] - off0);
                 }
-            // draws, in rank order
-            int cur = 0;
-            while (cur < seg_total) {
-                if (rng_pos == 312) { mt_twist<TH>(sh); rng_pos = 0; }
-                const int n = min(312 - rng_pos, seg_total - cur);
-                for (int r = t; r < n; r += TH)
-                    s.ptie[cur + r] = canonical(temper(sh.mt[2 * (rng_pos + r)]), temper(sh.mt[2 * (rng_pos + r) + 1]));
-                rng_pos += n;
-                cur += n;
-                __syncthreads();
-            }
-            draws += seg_total;
-            // apply: both members keep the smallest (weight, draw) among their candidate and the new pairs
-            for (int p = t; p < n_act; p += TH) { const int k = s.act[p]; __stcg(&s.key1[k], s.cand_dist[k]); }
-            __syncthreads();
-            for (int r = t; r < seg_total; r += TH) {
-                const unsigned wb = s.pw[r];
-                atomicMin(&s.key1[s.pa[r]], wb);
-                atomicMin(&s.key1[s.pb[r]], wb);
-            }
-            __syncthreads();
-            for (int p = t; p < n_act; p += TH) {
-                const int k = s.act[p];
-                __stcg(&s.key2[k], s.cand_dist[k] == __ldcg(&s.key1[k]) ? s.cand_tie[k] : ~0ull);
-            }
-            __syncthreads();
-            for (int r = t; r < seg_total; r += TH) {
-                const unsigned wb = s.pw[r];
-                const int a = s.pa[r], b = s.pb[r];
-                if (wb == __ldcg(&s.key1[a])) atomicMin(&s.key2[a], s.ptie[r]);
-                if (wb == __ldcg(&s.key1[b])) atomicMin(&s.key2[b], s.ptie[r]);
-            }
-            __syncthreads();
-            for (int r = t; r < seg_total; r += TH) {
-                const unsigned wb = s.pw[r];
-                const unsigned long long tb = s.ptie[r];
-                const int a = s.pa[r], b = s.pb[r];
-                for (int e = 0; e < 2; e++) {
-                    const int x = e ? b : a;
-                    if (wb == __ldcg(&s.key1[x]) && tb == __ldcg(&s.key2[x]) &&
-                        !(s.cand_dist[x] == wb && s.cand_tie[x] <= tb)) {
-                        s.cand_a[x] = a; s.cand_b[x] = b; s.cand_dist[x] = wb; s.cand_tie[x] = tb;
-                    }
-                }
-            }
-            __syncthreads();
+            draw_and_apply<TH>(s, sh, seg_total, rng_pos, draws);
         }
         p0 = p1;
     }
@@ -465,7 +507,7 @@ __device__ bool meet_pairs_small(const MMState &s, MMShared &sh, bool has_cf, in
                         sh.pk[idx] = ((unsigned long long)max(q, pu) << 32) | (unsigned)min(q, pu);
                         sh.pa[idx] = k_is_row ? k[e] : u;
                         sh.pb[idx] = k_is_row ? u : k[e];
-                        sh.pw[idx] = fkey(pair_weight(s, has_cf, k[e], u));
+                        sh.pw[idx] = fkey(pair_weight(s, has_cf, u, k[e]));
                     }
                 }
             if (ja[e] <= mj && jb[e] <= mk[e]) {
@@ -521,6 +563,125 @@ __device__ bool meet_pairs_small(const MMState &s, MMShared &sh, bool has_cf, in
                 const int x = e ? sh.pb[t] : sh.pa[t];
                 s.cand_a[x] = sh.pa[t]; s.cand_b[x] = sh.pb[t]; s.cand_dist[x] = sh.pw[t]; s.cand_tie[x] = sh.pt[t];
             }
+    return true;
+}
+
+// Medium path of phases D + E: up to 63 members of U, any number of pairs that fits the pair buffer, up to MED_E positions per
+// thread.  Thread q tests position q against every member of U it is responsible for (the pair {q, u} belongs to q if q comes
+// before u, or if q is outside U) and against row j, once, and keeps the outcomes as a bit mask; ballots and per-warp counts
+// turn the masks into the pairs' ranks in the reference's order (row position, then partner position).  Tie-rich data (many
+// identical haplotypes) has hundreds of feasible pairs in most steps — they pass through here.
+constexpr int MED_E = 20;
+template <int TH>
+__device__ bool meet_pairs_medium(const MMState &s, MMShared &sh, bool has_cf, int n_act, int ci, int cj, int n_u, int &rng_pos,
+                                  long long &draws)
+{
+    if (n_u > 63 || n_act > TH * MED_E) return false;
+    const size_t N = s.N;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int npw = (n_act + 31) >> 5; // warps of positions
+    int *wcnt = s.wcnt;                // [n_u + 1][npw]: pairs of U row ui (row j: index n_u) found in that warp of positions
+    const float mj = s.minv[cj];
+    const float *dj = s.d + cj * N, *dTj = s.dT + cj * N;
+    unsigned long long bits[MED_E];
+#pragma unroll
+    for (int e = 0; e < MED_E; e++) {
+        bits[e] = 0;
+        if (e * TH >= n_act) break;
+        const int q = e * TH + t;
+        const int k = q < n_act ? s.act[q] : -1;
+        const bool live = k >= 0 && k != ci && k != cj;
+        unsigned long long b = 0;
+        int nb = 0; // members of U before position q
+        if (live) {
+            const bool in_u = (s.flag[k] & 4) != 0;
+            const float mk = s.minv[k];
+            for (int u0 = 0; u0 < n_u; u0 += 4) {
+                float a[4], c[4], mu[4];
+                bool on[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int ui = u0 + j;
+                    const int pu = ui < n_u ? s.ulist[ui] : -1;
+                    on[j] = pu >= 0 && pu != q && (q < pu || !in_u);
+                    nb += pu >= 0 && pu < q;
+                    const int u = on[j] ? s.act[pu] : 0;
+                    a[j] = on[j] ? s.d[u * N + k] : 0.f;  // d[u][k]
+                    c[j] = on[j] ? s.dT[u * N + k] : 0.f; // d[k][u]
+                    mu[j] = on[j] ? s.minv[u] : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (on[j] && c[j] <= mk && a[j] <= mu[j]) b |= 1ull << (u0 + j);
+            }
+            if (dj[k] <= mj && dTj[k] <= mk) b |= 1ull << 63;
+            // the pairs of this position's own row (outside U: the members of U before it)
+            s.cnt[q] = in_u ? 0 : __popcll(b & ((1ull << nb) - 1));
+        } else if (q < n_act)
+            s.cnt[q] = 0;
+        bits[e] = b;
+        const int pw = q >> 5;
+        for (int ui = 0; ui < n_u; ui++) {
+            const unsigned m = __ballot_sync(~0u, ((b >> ui) & 1) && q < s.ulist[ui]);
+            if (lane == 0 && pw < npw) wcnt[ui * npw + pw] = __popc(m);
+        }
+        const unsigned m = __ballot_sync(~0u, (b >> 63) != 0);
+        if (lane == 0 && pw < npw) wcnt[n_u * npw + pw] = __popc(m);
+    }
+    __syncthreads();
+    // per U row (and row j): exclusive prefix over the warps of positions, total into the row's count
+    for (int ui = warp; ui <= n_u; ui += TH / 32) {
+        int run = 0;
+        for (int w0 = 0; w0 < npw; w0 += 32) {
+            const int w = w0 + lane;
+            const int v = w < npw ? wcnt[ui * npw + w] : 0;
+            int inc = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(~0u, inc, o);
+                if (lane >= o) inc += up;
+            }
+            if (w < npw) wcnt[ui * npw + w] = run + inc - v;
+            run += __shfl_sync(~0u, inc, 31);
+        }
+        if (lane == 0) s.cnt[ui < n_u ? s.ulist[ui] : n_act] = run;
+    }
+    __syncthreads();
+    const int total = block_exscan<TH>(s.cnt, n_act + 1, sh);
+    if (total == 0) return true;
+    if (total > s.cap) return false;
+    // the pairs, at their ranks
+#pragma unroll
+    for (int e = 0; e < MED_E; e++) {
+        if (e * TH >= n_act) break;
+        const int q = e * TH + t;
+        const unsigned long long b = bits[e];
+        const int k = q < n_act ? s.act[q] : -1;
+        const int pw = q >> 5;
+        int own = 0;
+        for (int ui = 0; ui < n_u; ui++) {
+            const int pu = s.ulist[ui];
+            const bool hit = (b >> ui) & 1;
+            const unsigned m = __ballot_sync(~0u, hit && q < pu);
+            if (!hit) continue;
+            const int u = s.act[pu];
+            int r, row, partner;
+            if (q < pu) { r = s.cnt[pu] + wcnt[ui * npw + pw] + __popc(m & ((1u << lane) - 1)); row = u; partner = k; }
+            else { r = s.cnt[q] + own++; row = k; partner = u; }
+            s.pa[r] = row;
+            s.pb[r] = partner;
+            s.pw[r] = fkey(pair_weight(s, has_cf, u, k));
+        }
+        const bool hj = (b >> 63) != 0;
+        const unsigned m = __ballot_sync(~0u, hj);
+        if (hj) {
+            const int r = s.cnt[n_act] + wcnt[n_u * npw + pw] + __popc(m & ((1u << lane) - 1));
+            s.pa[r] = k; // (:565-573)
+            s.pb[r] = cj;
+            s.pw[r] = fkey(pair_weight(s, has_cf, cj, k));
+        }
+    }
+    __syncthreads();
+    draw_and_apply<TH>(s, sh, total, rng_pos, draws);
     return true;
 }
 
@@ -618,7 +779,7 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
         for (int q = 1; q < 624; q++) { v = 1812433253u * (v ^ (v >> 30)) + (unsigned)q; sh.mt[q] = v; }
     }
     int rng_pos = 312;
-    long long draws = 0, general_steps = 0;
+    long long draws = 0, general_steps = 0, medium_steps = 0;
     int n_act = s.N;
     for (int k = t; k < s.N; k += TH) {
         s.act[k] = k; s.conv[k] = k; s.size[k] = 1.0f; s.minv_sym[k] = finf; s.flag[k] = 0;
@@ -882,6 +1043,11 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
             else if (n_u <= 4) done = meet_pairs_small<TH, 4>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
             else done = meet_pairs_small<TH, U_MAX>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
         }
+        if (!done && !(s.force_general & 1)) {
+            __syncthreads();
+            done = meet_pairs_medium<TH>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
+            medium_steps += done;
+        }
         if (!done) {
             general_steps++;
             __syncthreads();
@@ -1001,6 +1167,7 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
         s.info[1] = first_sym;
         s.info[2] = sym_steps;
         s.info[3] = general_steps;
+        s.info[12] = medium_steps;
     }
 }
 
@@ -1081,7 +1248,7 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
                             take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N),
                             take(4 * (size_t)N), take(4 * (size_t)(N + 2)), take(4 * (size_t)N), take(4 * (size_t)N)};
     const size_t o_pa = take(4 * (size_t)s.cap), o_pb = take(4 * (size_t)s.cap), o_pw = take(4 * (size_t)s.cap);
-    const size_t o_merges = take(8 * (size_t)N);
+    const size_t o_merges = take(8 * (size_t)N), o_wcnt = take(4 * 64 * ((size_t)N / 32 + 2));
     cudaError_t e = cudaMalloc(&h->block, off);
     if (e != cudaSuccess) {
         delete h;
@@ -1101,6 +1268,7 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
     s.key1 = (unsigned *)(b + o_i[11]);
     s.pa = (int *)(b + o_pa); s.pb = (int *)(b + o_pb); s.pw = (unsigned *)(b + o_pw);
     s.merges = (int *)(b + o_merges);
+    s.wcnt = (int *)(b + o_wcnt);
     // a fresh MinMatch object: min_values_CF = 0 (vector::resize), candidates name nobody (lin1 = lin2 = -1)
     MM_CUDA(cudaMemset(s.minv_cf, 0, 4 * (size_t)N));
     MM_CUDA(cudaMemset(s.cand_a, 0xff, 4 * (size_t)N));
@@ -1175,6 +1343,7 @@ static int mm_run(rp_minmatch *h, bool has_prior, int *merges, rp_minmatch_stats
         st->first_fallback_step = (int)h->h_info[1];
         st->fallback_steps = (int)h->h_info[2];
         st->general_steps = (int)h->h_info[3];
+        st->medium_steps = (int)h->h_info[12];
         st->launches = 2;
     }
 #ifdef MM_PROF

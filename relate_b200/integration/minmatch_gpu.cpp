@@ -36,14 +36,15 @@ namespace {
 
 struct Builders {
     std::vector<rp_minmatch *> handle;
-    long trees = 0, trees_ref = 0;
+    long trees = 0, trees_ref = 0, draws = 0, general_steps = 0, medium_steps = 0, fallback_steps = 0;
     double seconds = 0, kernel_seconds = 0;
     ~Builders()
     {
         for (rp_minmatch *h : handle) rp_minmatch_destroy(h);
         if (getenv("RELATE_GPU_MINMATCH_STATS"))
-            fprintf(stderr, "Relate_gpu: QuickBuild: %ld trees on the GPU (%ld by the reference's code), %.3f s in the call, %.3f s in the kernel\n",
-                    trees, trees_ref, seconds, kernel_seconds);
+            fprintf(stderr, "Relate_gpu: QuickBuild: %ld trees on the GPU (%ld by the reference's code), %.3f s in the call, %.3f s in the kernel; "
+                            "%ld draws, %ld merge steps with more than 128 pairs, %ld on the any-size pair path, %ld on the symmetric fallback\n",
+                    trees, trees_ref, seconds, kernel_seconds, draws, medium_steps, general_steps, fallback_steps);
     }
 };
 Builders g;
@@ -98,6 +99,10 @@ static void gpu_quickbuild(MinMatch *self, int &slot, int N, float threshold, fl
         exit(1);
     }
     g.kernel_seconds += 1e-3 * st.ms_kernel;
+    g.draws += st.draws;
+    g.general_steps += st.general_steps;
+    g.medium_steps += st.medium_steps;
+    g.fallback_steps += st.fallback_steps;
     store_tree(tree, merges.data(), N);
     if (verify) {
         Tree ref;
