@@ -228,9 +228,13 @@ __device__ int block_exscan(int *arr, int n, MMShared &sh)
 // (x, y); everything is read from row x of a matrix or of its transpose, so callers pass the cluster their warp shares as x.
 __device__ __forceinline__ float pair_weight(const MMState &s, bool has_cf, int x, int y)
 {
-    const size_t N = s.N;
-    if (has_cf && s.cf[x * N + y] <= s.minv_cf[x] && s.cfT[x * N + y] <= s.minv_cf[y]) return 0.0f;
-    return __fadd_rn(s.d[x * N + y], s.dT[x * N + y]);
+    const size_t o = (size_t)x * s.N + y;
+    const float dxy = s.d[o], dyx = s.dT[o]; // (all four loads before the first use: one round trip, not three)
+    if (has_cf) {
+        const float cxy = s.cf[o], cyx = s.cfT[o];
+        if (cxy <= s.minv_cf[x] && cyx <= s.minv_cf[y]) return 0.0f;
+    }
+    return __fadd_rn(dxy, dyx);
 }
 
 enum { ROW_SKIP = 0, ROW_BELOW = 1, ROW_LIST = 2, ROW_ABOVE = 3, ROW_J = 4 };
