@@ -60,6 +60,19 @@ def test_small_pair_buffer_segments(monkeypatch):
     run_sequence(6, 130, "blocks", n_trees=3)
 
 
+@pytest.mark.parametrize("env", [{"RP_MINMATCH_GENERAL": "1"}, {"RP_MINMATCH_GENERAL": "2"}, {"RP_MINMATCH_NO_SMEM": "1"},
+                                 {"RP_MINMATCH_THREADS": "256"}, {"RP_MINMATCH_THREADS": "1024"},
+                                 {"RP_MINMATCH_NO_SMEM": "1", "RP_MINMATCH_GENERAL": "2", "RP_MINMATCH_THREADS": "1024"}])
+def test_every_code_path_gives_the_same_trees(monkeypatch, env):
+    """The kernel picks a path per merge step by size (small / medium / any-size pair handling, block-wide or warp-per-row
+    rescans), keeps the per-cluster arrays in shared or in global memory by N, and runs with 256, 512 or 1024 threads: each
+    choice forced in turn on inputs that normally take another one."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for seed, N, kind in [(41, 130, "tree"), (42, 257, "blocks"), (43, 100, "ties"), (44, 64, "uniform"), (45, 600, "tree")]:
+        run_sequence(seed, N, kind, n_trees=3)
+
+
 def test_handle_state_is_per_handle():
     """Two handles fed the same sequence give the same trees; a fresh handle fed only the last (d, prior) need not."""
     N = 64
