@@ -42,6 +42,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the tree_builder leg runs many one-CTA kernels side by side: streams share 8 hardware queues by default and kernels of streams
+# that share one serialise (measured: 850 trees/s with 8, 2 900 with 32); must be set before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 N_HAP, N_SNP, MEMORY_GB, PAINTING = 1000, 50000, 5.0, "0.001,1"
 WORKLOAD = f"synthetic block-Kingman N={N_HAP} x L={N_SNP}, single chunk, --memory {MEMORY_GB:g}, --painting {PAINTING}"
@@ -451,10 +454,34 @@ def tree_builder_leg(device, sizes=((1000, 3), (5000, 2))):
         finally:
             shutil.rmtree(tmpd, ignore_errors=True)
         same = all(np.array_equal(ref[t], warm[t][0]) and np.array_equal(ref[t], res[t][0]) for t in range(T))
+        # a tree occupies one SM: K handles (K windows in BuildTopology's terms) driven from K host threads side by side, the
+        # matrices already on the device (rp_minmatch_quickbuild_device: what a consumer that keeps GetMatrix's output in HBM calls)
+        conc = None
+        if N <= 1000:
+            import torch
+            dev_trees = [(torch.from_numpy(d).cuda(device), None if prior is None else torch.from_numpy(prior).cuda(device)) for d, prior in trees]
+            torch.cuda.synchronize(device)
+            K = 64
+            handles = [capi.MinMatch(N, mm_cases.THETA, device=device) for _ in range(K)]
+            outs = [None] * K
+
+            def work(i):
+                outs[i] = [handles[i].quickbuild_device(d.data_ptr(), None if prior is None else prior.data_ptr())[0] for d, prior in dev_trees]
+            for rep in range(2):   # (the second round is the warm one)
+                ts = [threading.Thread(target=work, args=(i,)) for i in range(K)]
+                t0 = time.perf_counter()
+                [x.start() for x in ts]
+                [x.join() for x in ts]
+                wall = time.perf_counter() - t0
+            for h in handles:
+                h.close()
+            conc = {"handles": K, "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "trees_per_s": K * T / wall, "one_handle_trees_per_s": T / sum(w[2] for w in warm),
+                    "identical": bool(all(np.array_equal(outs[i][t], ref[t]) for i in range(K) for t in range(T)))}
         out.append({"N": N, "trees": T, "gpu_ms_per_tree_kernel": sum(w[1]["ms_kernel"] for w in warm) / T,
                     "gpu_ms_per_tree_call": 1e3 * sum(w[2] for w in warm) / T, "cpu_ms_per_tree": 1e3 * secs / T, "cpu_kind": kind,
                     "cpu_cores": 1, "draws_per_tree": sum(w[1]["draws"] for w in warm) / T,
-                    "general_steps": sum(w[1]["general_steps"] for w in warm), "merge_lists_identical": bool(same)})
+                    "general_steps": sum(w[1]["general_steps"] for w in warm), "medium_steps": sum(w[1]["medium_steps"] for w in warm),
+                    "merge_lists_identical": bool(same), "concurrent": conc})
     return {"what": "MinMatch::QuickBuild (src/tree_builder.cpp:1060-1303, 2357-2646) per tree, host matrices in (H2D inside the call), "
                     "merge list out; one CTA per tree", "sizes": out}
 

@@ -216,7 +216,10 @@ void rp_window_close(rp_window *win);
  * (t = 0..N-2), i.e. exactly what QuickBuild stores into tree.nodes (:1268-1274).  The lists are IDENTICAL to the
  * reference's for identical input matrices (same float arithmetic, same order of std::mt19937 draws).
  * d (and d_prior) are N x N row-major floats; neither is modified (the reference modifies d in place and its caller
- * does not read it again). */
+ * does not read it again).  A handle is not re-entrant; distinct handles may be used from distinct threads, and each tree
+ * occupies one SM, so trees of different windows (different handles) run side by side on one device: measured at N=1000,
+ * 64 handles on 64 host threads, 2 900 trees/s against 109 for one handle (CUDA_DEVICE_MAX_CONNECTIONS=32 in the environment
+ * before the first CUDA call: with the default 8 hardware queues kernels of streams that share a queue serialise, 850/s). */
 typedef struct rp_minmatch rp_minmatch;
 typedef struct rp_minmatch_stats {
     float ms_kernel;          /* device time of the tree kernel (CUDA events on the handle's stream) */

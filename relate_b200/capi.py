@@ -306,6 +306,13 @@ class MinMatch:
         check(lib().rp_minmatch_quickbuild(self._h, _ptr(d), _ptr(prior), _ptr(merges), C.byref(st)))
         return merges, {n: getattr(st, n) for n, _ in st._fields_}
 
+    def quickbuild_device(self, dev_d: int, dev_prior: int | None = None):
+        """Same with the matrices already in the handle's device memory (raw device pointers, N x N float32 each)."""
+        merges = np.empty((self.N - 1, 2), np.int32)
+        st = RpMinMatchStats()
+        check(lib().rp_minmatch_quickbuild_device(self._h, _P(dev_d), _P(dev_prior) if dev_prior else None, _ptr(merges), C.byref(st)))
+        return merges, {n: getattr(st, n) for n, _ in st._fields_}
+
     def close(self):
         if self._h:
             lib().rp_minmatch_destroy(self._h)

@@ -1206,7 +1206,7 @@ struct rp_minmatch {
     long long *h_info = nullptr;
     cudaStream_t stream = nullptr;
     float last_ms = 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr; // e2: end of the call's work; waited for without spinning
 };
 
 #define MM_CUDA(call)                                                                                         \
@@ -1305,6 +1305,7 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
     MM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     MM_CUDA(cudaEventCreate(&h->e0));
     MM_CUDA(cudaEventCreate(&h->e1));
+    MM_CUDA(cudaEventCreateWithFlags(&h->e2, cudaEventBlockingSync | cudaEventDisableTiming));
     MM_CUDA(cudaMallocHost(&h->h_merges, 8 * (size_t)N));
     MM_CUDA(cudaMallocHost(&h->h_info, 128));
     *out = h;
@@ -1318,6 +1319,7 @@ extern "C" void rp_minmatch_destroy(rp_minmatch *h)
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->e0) cudaEventDestroy(h->e0);
     if (h->e1) cudaEventDestroy(h->e1);
+    if (h->e2) cudaEventDestroy(h->e2);
     if (h->h_merges) cudaFreeHost(h->h_merges);
     if (h->h_info) cudaFreeHost(h->h_info);
     if (h->block) cudaFree(h->block);
@@ -1338,7 +1340,9 @@ static int mm_run(rp_minmatch *h, bool has_prior, int *merges, rp_minmatch_stats
     MM_CUDA(cudaEventRecord(h->e1, h->stream));
     MM_CUDA(cudaMemcpyAsync(h->h_merges, h->s.merges, 8 * (size_t)(h->N - 1), cudaMemcpyDeviceToHost, h->stream));
     MM_CUDA(cudaMemcpyAsync(h->h_info, h->s.info, 128, cudaMemcpyDeviceToHost, h->stream));
-    MM_CUDA(cudaStreamSynchronize(h->stream));
+    // a tree takes milliseconds and a consumer may drive many handles from as many host threads (one tree per SM): block, do not spin
+    MM_CUDA(cudaEventRecord(h->e2, h->stream));
+    MM_CUDA(cudaEventSynchronize(h->e2));
     memcpy(merges, h->h_merges, 8 * (size_t)(h->N - 1));
     MM_CUDA(cudaEventElapsedTime(&h->last_ms, h->e0, h->e1));
     if (st) {

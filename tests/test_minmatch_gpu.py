@@ -73,6 +73,24 @@ def test_every_code_path_gives_the_same_trees(monkeypatch, env):
         run_sequence(seed, N, kind, n_trees=3)
 
 
+def test_matrices_already_on_the_device():
+    """rp_minmatch_quickbuild_device: the matrices are taken from device memory (as the distance kernel leaves them) and are
+    not modified; same trees as from the host."""
+    import torch
+    N = 200
+    o = oracle.MinMatchOracle(N, mm_cases.THETA)
+    res = []
+    trees = mm_cases.tree_sequence(9, N, "tree", 3, oracle.prior_from_merges, lambda d, p: res.append(o.quickbuild(d, p)[0]) or res[-1])
+    with capi.MinMatch(N, mm_cases.THETA) as g:
+        for t, (d, prior) in enumerate(trees):
+            dd = torch.from_numpy(d).cuda()
+            pp = torch.from_numpy(prior).cuda() if prior is not None else None
+            torch.cuda.synchronize()
+            m, _ = g.quickbuild_device(dd.data_ptr(), pp.data_ptr() if pp is not None else None)
+            assert np.array_equal(m, res[t])
+            assert np.array_equal(dd.cpu().numpy(), d) and (pp is None or np.array_equal(pp.cpu().numpy(), prior))
+
+
 def test_handle_state_is_per_handle():
     """Two handles fed the same sequence give the same trees; a fresh handle fed only the last (d, prior) need not."""
     N = 64
