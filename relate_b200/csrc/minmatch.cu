@@ -8,15 +8,18 @@
 //
 //   A  update row/column j of d (and of the prior matrix) from rows/columns i and j; row j's new minimum; which rows
 //      have to look for a new minimum (their old one was d[k][i] or d[k][j]); which candidates name i or j
-//   B  one warp per such row: the new minimum, with the reference's early `break` decided from three reductions
-//      (smallest value, first position equal to the old minimum, first position below it)
+//   B  the new minimum of each such row (up to eight rows in one block-wide pass, else a warp per row), with the reference's
+//      early `break` decided from three reductions (smallest value, first position equal to the old minimum, first position
+//      below it)
 //   C  U = rows whose minimum moved or whose candidate named i or j (the reference's `updated_cluster`), in order
-//   D  count feasible pairs per row — rows of U against every earlier row, the other rows against the earlier members
-//      of U, and row j against everybody, which is exactly the set and the order the reference meets them in —,
-//      prefix-sum the counts: a pair's rank is the index of its random draw
-//   E  write the pairs, give pair r the r-th next output of a device-side std::mt19937 (seeded with 1 per tree, two
-//      32-bit outputs per double as libstdc++'s generate_canonical does), and let both members keep the
-//      lexicographically smallest (weight, draw) among their old candidate and their new pairs: three rounds of atomicMin
+//   D  find the feasible pairs — rows of U against every earlier row, the other rows against the earlier members of U, and row j
+//      against everybody, which is exactly the set and the order the reference meets them in — and rank them in that order:
+//      a pair's rank is the index of its random draw.  Three sizes: a handful of pairs are ranked by counting in shared memory;
+//      hundreds (blocks of identical haplotypes) keep one bit mask per position and rank through ballots and per-warp counts;
+//      anything (Initialize, more than 63 members of U) is counted row by row, prefix-summed and cut into segments
+//   E  give pair r the r-th next output of a device-side std::mt19937 (seeded with 1 per tree, two 32-bit outputs per double as
+//      libstdc++'s generate_canonical does), and let both members keep the lexicographically smallest (weight, draw) among their
+//      old candidate and their new pairs (in shared memory, or three rounds of atomicMin over the pair buffer)
 //   F  the best candidate over all clusters = the next (i, j)
 // plus the same for the symmetric fallback matrix once no mutually-minimal pair is left.  All float arithmetic uses
 // explicit round-to-nearest intrinsics (no FMA contraction), so the values equal the reference's x86-64 SSE results and
