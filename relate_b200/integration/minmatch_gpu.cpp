@@ -12,7 +12,7 @@
 // code runs, as it does for every stage this repo leaves to the reference) and for the built-in cross-check.
 //
 //   RELATE_GPU_MINMATCH=0          trees by the reference's CPU code (A/B timing)
-//   RELATE_GPU_MINMATCH_MIN_N=<n>  smallest N built on the GPU (default 512: one CTA per tree pays ~10 us per merge whatever N
+//   RELATE_GPU_MINMATCH_MIN_N=<n>  smallest N built on the GPU (default 600: one CTA per tree pays ~10 us per merge whatever N
 //                                  is, the CPU 0.6 ms per tree at N=200 and 16 ms at N=1000, 0.8 s at N=5000; measured on B200)
 //   RELATE_GPU_MINMATCH_VERIFY=1   build every tree both ways and abort on the first differing merge
 //   RELATE_GPU_MINMATCH_STATS=1    one line on stderr at exit: trees, seconds in QuickBuild, kernel seconds
@@ -51,7 +51,7 @@ Builders g;
 
 const bool use_gpu = !(getenv("RELATE_GPU_MINMATCH") && atoi(getenv("RELATE_GPU_MINMATCH")) == 0);
 const bool verify = getenv("RELATE_GPU_MINMATCH_VERIFY") != nullptr;
-const int min_n = getenv("RELATE_GPU_MINMATCH_MIN_N") ? atoi(getenv("RELATE_GPU_MINMATCH_MIN_N")) : 512;
+const int min_n = getenv("RELATE_GPU_MINMATCH_MIN_N") ? atoi(getenv("RELATE_GPU_MINMATCH_MIN_N")) : 600;
 
 void store_tree(Tree &tree, const int *merges, int N)
 {
