@@ -26,6 +26,11 @@ Keys beyond the base contract:
                multi-warp kernel, md5 of the paint files (must equal the 1-device files) and a d_ij check through
                the oracle's one-row lens.  `sharded_config4` (N=10000 x L=100000, --memory 100) is added at 8 GPUs
                (or RELATE_BENCH_CONFIG4=1) when the box has the disk and RAM for its 40 GB of paint files.
+  window_repaint / e2e_resident   the consumer side (row f1): RePaintSection + GetMatrix of one window on the device, and the
+               file-less path chunk files -> first distance matrix.
+  tree_builder the consumer side (row f4), N=1 only: rp_minmatch_quickbuild per tree at N=1000 and N=5000 against the
+               reference's own MinMatch::QuickBuild on one host core (oracle/_ref/qblens), merge lists checked identical,
+               and the rate of 64 handles building N=1000 trees side by side (one tree per SM).
 """
 from __future__ import annotations
 
