@@ -745,7 +745,7 @@ __device__ __forceinline__ void rescan_rows(const MMState &s, MMShared &sh, int 
 #define MM_MARK(i) do { } while (0)
 #endif
 
-template <int TH>
+template <int TH, bool SMEM>
 __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has_cf_i)
 {
     __shared__ MMShared sh;
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
     // shared memory whenever they fit (N <= ~5000); what outlives the tree is loaded here and written back at the end.
     float *const g_minv_cf = s.minv_cf;
     int *const g_cand_a = s.cand_a, *const g_cand_b = s.cand_b;
-    if (s.use_smem) {
+    if (SMEM) { // (a template parameter, not s.use_smem: the compiler then knows these pointers are shared memory and emits LDS / STS)
         extern __shared__ __align__(16) unsigned char dyn[];
         const size_t n4 = ((size_t)s.N + 3) & ~(size_t)3;
         s.cand_tie = (unsigned long long *)dyn;
@@ -1164,7 +1164,7 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
         __syncthreads();
         MM_MARK(6);
     }
-    if (s.use_smem)
+    if (SMEM)
         for (int k = t; k < s.N; k += TH) { g_minv_cf[k] = s.minv_cf[k]; g_cand_a[k] = s.cand_a[k]; g_cand_b[k] = s.cand_b[k]; }
     if (t == 0) {
 #ifdef MM_PROF
@@ -1294,13 +1294,11 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
         h->threads = getenv("RP_MINMATCH_THREADS") ? atoi(getenv("RP_MINMATCH_THREADS")) : (N < 512 ? 256 : 512);
         if (h->threads != 256 && h->threads != 512) h->threads = 1024;
         cudaFuncAttributes fa;
-        if (h->threads == 256) MM_CUDA(cudaFuncGetAttributes(&fa, mm_quickbuild_kernel<256>));
-        else if (h->threads == 512) MM_CUDA(cudaFuncGetAttributes(&fa, mm_quickbuild_kernel<512>));
-        else MM_CUDA(cudaFuncGetAttributes(&fa, mm_quickbuild_kernel<1024>));
+        const void *fn = h->threads == 256 ? (const void *)mm_quickbuild_kernel<256, true>
+                         : h->threads == 512 ? (const void *)mm_quickbuild_kernel<512, true> : (const void *)mm_quickbuild_kernel<1024, true>;
+        MM_CUDA(cudaFuncGetAttributes(&fa, fn));
         if (!getenv("RP_MINMATCH_NO_SMEM") && want + fa.sharedSizeBytes <= (size_t)max_optin) {
-            if (h->threads == 256) MM_CUDA(cudaFuncSetAttribute(mm_quickbuild_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
-            else if (h->threads == 512) MM_CUDA(cudaFuncSetAttribute(mm_quickbuild_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
-            else MM_CUDA(cudaFuncSetAttribute(mm_quickbuild_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+            MM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
             h->dyn_smem = want;
             s.use_smem = 1;
         }
@@ -1336,9 +1334,16 @@ static int mm_run(rp_minmatch *h, bool has_prior, int *merges, rp_minmatch_stats
         const dim3 grid((h->N + 31) / 32, (h->N + 31) / 32, has_prior ? 2 : 1);
         mm_transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(h->s.d, h->s.dT, h->s.cf, h->s.cfT, h->N);
     }
-    if (h->threads == 256) mm_quickbuild_kernel<256><<<1, 256, h->dyn_smem, h->stream>>>(h->s, has_prior ? 1 : 0);
-    else if (h->threads == 512) mm_quickbuild_kernel<512><<<1, 512, h->dyn_smem, h->stream>>>(h->s, has_prior ? 1 : 0);
-    else mm_quickbuild_kernel<1024><<<1, 1024, h->dyn_smem, h->stream>>>(h->s, has_prior ? 1 : 0);
+    const int hc = has_prior ? 1 : 0;
+#define MM_LAUNCH(TH_)                                                                                             \
+    do {                                                                                                           \
+        if (h->s.use_smem) mm_quickbuild_kernel<TH_, true><<<1, TH_, h->dyn_smem, h->stream>>>(h->s, hc);          \
+        else mm_quickbuild_kernel<TH_, false><<<1, TH_, 0, h->stream>>>(h->s, hc);                                 \
+    } while (0)
+    if (h->threads == 256) MM_LAUNCH(256);
+    else if (h->threads == 512) MM_LAUNCH(512);
+    else MM_LAUNCH(1024);
+#undef MM_LAUNCH
     MM_CUDA(cudaGetLastError());
     MM_CUDA(cudaEventRecord(h->e1, h->stream));
     MM_CUDA(cudaMemcpyAsync(h->h_merges, h->s.merges, 8 * (size_t)(h->N - 1), cudaMemcpyDeviceToHost, h->stream));
