@@ -332,11 +332,9 @@ __device__ __forceinline__ int row_kind(const MMState &s, bool init, int n_act, 
     return (k == ci || k == cj) ? ROW_SKIP : ((s.flag[k] & 4) ? ROW_BELOW : ROW_LIST);
 }
 
-// Pairs 0..total-1 of the pair buffer, in the order the reference meets them: pair r takes the r-th next draw; both members keep
-// the lexicographically smallest (weight, draw) among their candidate and the new pairs (three rounds of atomicMin on keys
-// that are initialised from the members' current candidates).
+// the next `total` draws of the tree's mt19937 as ptie[0..total)
 template <int TH>
-__device__ void draw_and_apply(const MMState &s, MMShared &sh, int total, int &rng_pos, long long &draws)
+__device__ void draw_ties(const MMState &s, MMShared &sh, int total, int &rng_pos, long long &draws)
 {
     const int t = threadIdx.x;
     int cur = 0;
@@ -350,6 +348,16 @@ __device__ void draw_and_apply(const MMState &s, MMShared &sh, int total, int &r
         __syncthreads();
     }
     draws += total;
+}
+
+// Pairs 0..total-1 of the pair buffer, in the order the reference meets them: pair r takes the r-th next draw; both members keep
+// the lexicographically smallest (weight, draw) among their candidate and the new pairs (three rounds of atomicMin on keys
+// that are initialised from the members' current candidates).
+template <int TH>
+__device__ void draw_and_apply(const MMState &s, MMShared &sh, int total, int &rng_pos, long long &draws)
+{
+    const int t = threadIdx.x;
+    draw_ties<TH>(s, sh, total, rng_pos, draws);
     for (int r = t; r < total; r += TH) {
         const int a = s.pa[r], b = s.pb[r];
         __stcg(&s.key1[a], s.cand_dist[a]);
@@ -656,39 +664,84 @@ __device__ bool meet_pairs_medium(const MMState &s, MMShared &sh, bool has_cf, i
     const int total = block_exscan<TH>(s.cnt, n_act + 1, sh);
     if (total == 0) return true;
     if (total > s.cap) return false;
-    // the pairs, at their ranks
+    if (n_u > U_MAX) { // many members of U: one block-wide minimum each would cost more than the pair buffer with its three rounds of atomicMin
+        // the pairs, at their ranks
 #pragma unroll
-    for (int e = 0; e < MED_E; e++) {
-        if (e * TH >= n_act) break;
-        const int q = e * TH + t;
-        const unsigned long long b = bits[e];
-        const int k = q < n_act ? s.act[q] : -1;
-        const int pw = q >> 5;
-        int own = 0;
-        for (int ui = 0; ui < n_u; ui++) {
-            const int pu = s.ulist[ui];
-            const bool hit = (b >> ui) & 1;
-            const unsigned m = __ballot_sync(~0u, hit && q < pu);
-            if (!hit) continue;
-            const int u = s.act[pu];
-            int r, row, partner;
-            if (q < pu) { r = s.cnt[pu] + wcnt[ui * npw + pw] + __popc(m & ((1u << lane) - 1)); row = u; partner = k; }
-            else { r = s.cnt[q] + own++; row = k; partner = u; }
-            s.pa[r] = row;
-            s.pb[r] = partner;
-            s.pw[r] = fkey(pair_weight(s, has_cf, u, k));
+        for (int e = 0; e < MED_E; e++) {
+            if (e * TH >= n_act) break;
+            const int q = e * TH + t;
+            const unsigned long long b = bits[e];
+            const int k = q < n_act ? s.act[q] : -1;
+            const int pw = q >> 5;
+            int own = 0;
+            for (int ui = 0; ui < n_u; ui++) {
+                const int pu = s.ulist[ui];
+                const bool hit = (b >> ui) & 1;
+                const unsigned m = __ballot_sync(~0u, hit && q < pu);
+                if (!hit) continue;
+                const int u = s.act[pu];
+                int r, row, partner;
+                if (q < pu) { r = s.cnt[pu] + wcnt[ui * npw + pw] + __popc(m & ((1u << lane) - 1)); row = u; partner = k; }
+                else { r = s.cnt[q] + own++; row = k; partner = u; }
+                s.pa[r] = row;
+                s.pb[r] = partner;
+                s.pw[r] = fkey(pair_weight(s, has_cf, u, k));
+            }
+            const bool hj = (b >> 63) != 0;
+            const unsigned m = __ballot_sync(~0u, hj);
+            if (hj) {
+                const int r = s.cnt[n_act] + wcnt[n_u * npw + pw] + __popc(m & ((1u << lane) - 1));
+                s.pa[r] = k; // (:565-573)
+                s.pb[r] = cj;
+                s.pw[r] = fkey(pair_weight(s, has_cf, cj, k));
+            }
         }
-        const bool hj = (b >> 63) != 0;
-        const unsigned m = __ballot_sync(~0u, hj);
-        if (hj) {
-            const int r = s.cnt[n_act] + wcnt[n_u * npw + pw] + __popc(m & ((1u << lane) - 1));
-            s.pa[r] = k; // (:565-573)
-            s.pb[r] = cj;
-            s.pw[r] = fkey(pair_weight(s, has_cf, cj, k));
-        }
+        __syncthreads();
+        draw_and_apply<TH>(s, sh, total, rng_pos, draws);
+        return true;
     }
-    __syncthreads();
-    draw_and_apply<TH>(s, sh, total, rng_pos, draws);
+    draw_ties<TH>(s, sh, total, rng_pos, draws);
+    // Every pair has a member in U or is (k, j).  That member's candidate is a block-wide minimum over the positions; the other
+    // member's candidate belongs to the thread of its position, which updates it on the spot.  No pair buffer, no atomics.
+    for (int ui = 0; ui <= n_u; ui++) {
+        const bool jrow = ui == n_u;
+        const int pu = jrow ? n_act : s.ulist[ui]; // (row j comes after every position)
+        const int u = jrow ? cj : s.act[pu];
+        unsigned bw = ~0u;
+        unsigned long long bt = ~0ull;
+        int bq = IMAX; // this thread's best pair with u
+#pragma unroll
+        for (int e = 0; e < MED_E; e++) {
+            if (e * TH >= n_act) break;
+            const int q = e * TH + t;
+            const unsigned long long b = bits[e];
+            const bool hit = jrow ? (b >> 63) != 0 : ((b >> ui) & 1) != 0;
+            const bool urow = q < pu; // the pair is met in u's row (else in q's own row, after the earlier members of U)
+            const unsigned m = __ballot_sync(~0u, hit && urow);
+            if (!hit) continue;
+            const int k = s.act[q];
+            const int r = urow ? s.cnt[pu] + wcnt[ui * npw + (q >> 5)] + __popc(m & ((1u << lane) - 1))
+                               : s.cnt[q] + __popcll(b & ((1ull << ui) - 1));
+            const unsigned wk = fkey(pair_weight(s, has_cf, u, k));
+            const unsigned long long tie = s.ptie[r];
+            if (wk < s.cand_dist[k] || (wk == s.cand_dist[k] && tie < s.cand_tie[k])) {
+                s.cand_dist[k] = wk;
+                s.cand_tie[k] = tie;
+                s.cand_a[k] = (urow && !jrow) ? u : k; // (row, partner); the new cluster's row: (partner, j)   (:565-573)
+                s.cand_b[k] = (urow && !jrow) ? k : u;
+            }
+            if (wk < bw || (wk == bw && tie < bt)) { bw = wk; bt = tie; bq = q; }
+        }
+        block_lexmin<TH>(bw, bt, bq, sh);
+        if (t == 0 && bq != IMAX && (bw < s.cand_dist[u] || (bw == s.cand_dist[u] && bt < s.cand_tie[u]))) {
+            const int k = s.act[bq];
+            s.cand_dist[u] = bw;
+            s.cand_tie[u] = bt;
+            s.cand_a[u] = (bq < pu && !jrow) ? u : k;
+            s.cand_b[u] = (bq < pu && !jrow) ? k : u;
+        }
+        __syncthreads();
+    }
     return true;
 }
 
