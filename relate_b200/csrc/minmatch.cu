@@ -840,6 +840,7 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
     }
     int rng_pos = 312;
     long long draws = 0, general_steps = 0, medium_steps = 0;
+    bool last_was_big = false;
     int n_act = s.N;
     for (int k = t; k < s.N; k += TH) {
         s.act[k] = k; s.conv[k] = k; s.size[k] = 1.0f; s.minv_sym[k] = finf; s.flag[k] = 0;
@@ -1096,7 +1097,8 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
         MM_MARK(4);
         // D, E
         bool done = false;
-        if (n_u <= U_MAX && !s.force_general) {
+        // (a step that follows one with hundreds of pairs usually has hundreds too: blocks of identical haplotypes; skip the attempt)
+        if (n_u <= U_MAX && !s.force_general && !last_was_big) {
             if (n_u == 0) done = meet_pairs_small<TH, 0>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
             else if (n_u == 1) done = meet_pairs_small<TH, 1>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
             else if (n_u == 2) done = meet_pairs_small<TH, 2>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
@@ -1105,8 +1107,10 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
         }
         if (!done && !(s.force_general & 1)) {
             __syncthreads();
+            const long long before = draws;
             done = meet_pairs_medium<TH>(s, sh, has_cf, n_act, ci, cj, n_u, rng_pos, draws);
             medium_steps += done;
+            last_was_big = done && draws - before > PAIR_MAX;
         }
         if (!done) {
             general_steps++;
