@@ -33,6 +33,8 @@ try:
         p = subprocess.run([exe] + bt, cwd=os.path.join(tmp, tag), capture_output=True, text=True, env=env)
         wall = time.perf_counter() - t0
         assert p.returncode == 0, p.stderr[-2000:]
+        if os.environ.get("RELATE_BT_STDERR"):
+            print("\n".join(l for l in p.stderr.splitlines() if l.startswith("mm_prof"))[-1500:])
         m = re.search(r"QuickBuild: (\d+) trees on the GPU \((\d+) by the reference's code\), ([0-9.]+) s in the call, ([0-9.]+) s in the kernel", p.stderr)
         res[tag] = (wall, m.groups() if m else None)
         print(f"  {tag:5s}: BuildTopology wall {wall:8.2f} s" + (f"; QuickBuild {m.group(3)} s for {int(m.group(1)) + int(m.group(2))} trees "
