@@ -58,6 +58,8 @@ struct MMState {
     float thr, thr_cf;
     int force_general; // tests: skip the small-case paths
     int use_smem;      // the per-cluster arrays fit into shared memory (40 bytes per cluster)
+    int pre_init;      // Initialize's O(N^2) passes were done by the grid-wide kernels in front (minima in minv / minv_cf, pairs in the buffer)
+    int *init_cnt;     // their per-row counts / offsets (N + 1) and, behind them, the total
     // matrices (row-major N x N)
     float *d, *cf, *sym;
     float *dT, *cfT; // transposes, kept in step: a column of d is a row of dT (a warp reading a column touches 32 lines)
@@ -814,7 +816,7 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
     // The per-cluster arrays are rewritten in every step, and a global store drops the line from L1: kept in global memory
     // every phase starts with a chain of L2 round trips (measured: 12 us per merge step, independent of N).  They live in
     // shared memory whenever they fit (N <= ~5000); what outlives the tree is loaded here and written back at the end.
-    float *const g_minv_cf = s.minv_cf;
+    float *const g_minv_cf = s.minv_cf, *const g_minv = s.minv;
     int *const g_cand_a = s.cand_a, *const g_cand_b = s.cand_b;
     if (SMEM) { // (a template parameter, not s.use_smem: the compiler then knows these pointers are shared memory and emits LDS / STS)
         extern __shared__ __align__(16) unsigned char dyn[];
@@ -847,29 +849,37 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
         s.cand_dist[k] = KINF; s.cand_tie[k] = DINF;
     }
     __syncthreads();
-    // Initialize: row minima (+ the prior's, which start from what the previous tree left)
-    for (int k = warp; k < s.N; k += (TH / 32)) {
-        float m = finf, mc = finf;
-        for (int lb = 0; lb < s.N; lb += 128) {
-            float v[4], c[4];
+    if (s.pre_init) {
+        // Initialize's O(N^2) passes were done across the whole GPU (mm_init_* kernels): row minima in g_minv / g_minv_cf (the latter
+        // copied above), the feasible pairs in the pair buffer in the reference's order
+        if (SMEM)
+            for (int k = t; k < s.N; k += TH) s.minv[k] = g_minv[k];
+    } else {
+        // Initialize: row minima (+ the prior's, which start from what the previous tree left)
+        for (int k = warp; k < s.N; k += (TH / 32)) {
+            float m = finf, mc = finf;
+            for (int lb = 0; lb < s.N; lb += 128) {
+                float v[4], c[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int l = lb + 32 * e + lane;
-                const bool ok = l < s.N && l != k;
-                v[e] = ok ? s.d[k * N + l] : finf;
-                c[e] = (ok && has_cf) ? s.cf[k * N + l] : finf;
+                for (int e = 0; e < 4; e++) {
+                    const int l = lb + 32 * e + lane;
+                    const bool ok = l < s.N && l != k;
+                    v[e] = ok ? s.d[k * N + l] : finf;
+                    c[e] = (ok && has_cf) ? s.cf[k * N + l] : finf;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) { m = fminf(m, v[e]); mc = fminf(mc, c[e]); }
             }
-#pragma unroll
-            for (int e = 0; e < 4; e++) { m = fminf(m, v[e]); mc = fminf(mc, c[e]); }
-        }
-        for (int o = 16; o; o >>= 1) { m = fminf(m, __shfl_xor_sync(~0u, m, o)); mc = fminf(mc, __shfl_xor_sync(~0u, mc, o)); }
-        if (lane == 0) {
-            s.minv[k] = __fadd_rn(m, thr);
-            if (has_cf) s.minv_cf[k] = __fadd_rn(fminf(s.minv_cf[k], mc), thr_cf);
+            for (int o = 16; o; o >>= 1) { m = fminf(m, __shfl_xor_sync(~0u, m, o)); mc = fminf(mc, __shfl_xor_sync(~0u, mc, o)); }
+            if (lane == 0) {
+                s.minv[k] = __fadd_rn(m, thr);
+                if (has_cf) s.minv_cf[k] = __fadd_rn(fminf(s.minv_cf[k], mc), thr_cf);
+            }
         }
     }
     __syncthreads();
-    meet_pairs<TH>(s, sh, has_cf, true, n_act, -1, -1, 0, rng_pos, draws);
+    if (s.pre_init && s.init_cnt[s.N + 1] <= s.cap) draw_and_apply<TH>(s, sh, s.init_cnt[s.N + 1], rng_pos, draws);
+    else meet_pairs<TH>(s, sh, has_cf, true, n_act, -1, -1, 0, rng_pos, draws); // (more pairs than the buffer holds: in segments)
     __syncthreads();
 
     MM_MARK(0);
@@ -1235,6 +1245,96 @@ __global__ void __launch_bounds__(TH, 1) mm_quickbuild_kernel(MMState s, int has
     }
 }
 
+// ---- Initialize across the whole GPU --------------------------------------------------------------------------------------
+// The tree's CTA spent 5-7 % of a tree in the three O(N^2) passes of Initialize (row minima, count, emit).  They have no order
+// dependence beyond a prefix sum, so a warp per row on all SMs does them in front of the tree kernel.
+__global__ void mm_init_rowmin_kernel(MMState s, int has_cf)
+{
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= s.N) return;
+    const size_t N = s.N;
+    const float finf = __int_as_float(0x7f800000);
+    float m = finf, mc = finf;
+    for (int lb = 0; lb < s.N; lb += 128) {
+        float v[4], c[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int l = lb + 32 * e + lane;
+            const bool ok = l < s.N && l != k;
+            v[e] = ok ? s.d[k * N + l] : finf;
+            c[e] = (ok && has_cf) ? s.cf[k * N + l] : finf;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) { m = fminf(m, v[e]); mc = fminf(mc, c[e]); }
+    }
+    for (int o = 16; o; o >>= 1) { m = fminf(m, __shfl_xor_sync(~0u, m, o)); mc = fminf(mc, __shfl_xor_sync(~0u, mc, o)); }
+    if (lane == 0) {
+        s.minv[k] = __fadd_rn(m, s.thr);
+        if (has_cf) s.minv_cf[k] = __fadd_rn(fminf(s.minv_cf[k], mc), s.thr_cf); // (starts from what the previous tree left)
+    }
+}
+
+// row p against the rows above it (Initialize's order: :87-143); EMIT = false counts, EMIT = true writes at the row's offset
+template <bool EMIT>
+__global__ void mm_init_pairs_kernel(MMState s, int has_cf)
+{
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= s.N) return;
+    if (EMIT && s.init_cnt[s.N + 1] > s.cap) return; // (the tree kernel does it itself, in segments)
+    const size_t N = s.N;
+    const int x = p;
+    const float mx = s.minv[x];
+    int count = 0;
+    const int base = EMIT ? s.init_cnt[p] : 0;
+    for (int qb = p + 1; qb < s.N; qb += 128) {
+        float v[4], vt[4];
+        bool ok[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int y = qb + 32 * c + lane;
+            ok[c] = y < s.N;
+            v[c] = ok[c] ? s.d[x * N + y] : 0.f;
+            vt[c] = ok[c] ? s.dT[x * N + y] : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int y = qb + 32 * c + lane;
+            ok[c] = ok[c] && v[c] <= mx && vt[c] <= s.minv[y];
+            const unsigned m = __ballot_sync(~0u, ok[c]);
+            if (EMIT && ok[c]) {
+                const int r = base + count + __popc(m & ((1u << lane) - 1));
+                s.pa[r] = x;
+                s.pb[r] = y;
+                s.pw[r] = fkey(pair_weight(s, has_cf != 0, x, y));
+            }
+            count += __popc(m);
+        }
+    }
+    if (!EMIT && lane == 0) s.init_cnt[p] = count;
+}
+
+// exclusive prefix sum of init_cnt[0..N) in place, the total into init_cnt[N] and init_cnt[N + 1]
+__global__ void mm_init_scan_kernel(MMState s)
+{
+    __shared__ int part[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, n = s.N, per = (n + 1023) / 1024;
+    const int b = min(t * per, n), e = min(b + per, n);
+    int sum = 0;
+    for (int q = b; q < e; q++) sum += s.init_cnt[q];
+    int inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(~0u, inc, o);
+        if (lane >= o) inc += up;
+    }
+    if (lane == 31) part[warp] = inc;
+    __syncthreads();
+    const int wc = part[lane];
+    const int wbase = __reduce_add_sync(~0u, lane < warp ? wc : 0), total = __reduce_add_sync(~0u, wc);
+    int run = wbase + inc - sum;
+    for (int q = b; q < e; q++) { const int v = s.init_cnt[q]; s.init_cnt[q] = run; run += v; }
+    if (t == 0) { s.init_cnt[n] = total; s.init_cnt[n + 1] = total; }
+}
+
 // dT = d^T (z = 0) and cfT = cf^T (z = 1), 32 x 32 tiles through shared memory
 __global__ void mm_transpose_kernel(const float *d, float *dT, const float *cf, float *cfT, int N)
 {
@@ -1312,6 +1412,7 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
                             take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N), take(4 * (size_t)N),
                             take(4 * (size_t)N), take(4 * (size_t)(N + 2)), take(4 * (size_t)N), take(4 * (size_t)N)};
     const size_t o_pa = take(4 * (size_t)s.cap), o_pb = take(4 * (size_t)s.cap), o_pw = take(4 * (size_t)s.cap);
+    const size_t o_icnt = take(4 * ((size_t)N + 4));
     const size_t o_merges = take(8 * (size_t)N), o_wcnt = take(4 * 64 * ((size_t)N / 32 + 2));
     cudaError_t e = cudaMalloc(&h->block, off);
     if (e != cudaSuccess) {
@@ -1333,6 +1434,8 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
     s.pa = (int *)(b + o_pa); s.pb = (int *)(b + o_pb); s.pw = (unsigned *)(b + o_pw);
     s.merges = (int *)(b + o_merges);
     s.wcnt = (int *)(b + o_wcnt);
+    s.init_cnt = (int *)(b + o_icnt);
+    s.pre_init = getenv("RP_MINMATCH_PRE_INIT") ? atoi(getenv("RP_MINMATCH_PRE_INIT")) : 1;
     // a fresh MinMatch object: min_values_CF = 0 (vector::resize), candidates name nobody (lin1 = lin2 = -1)
     MM_CUDA(cudaMemset(s.minv_cf, 0, 4 * (size_t)N));
     MM_CUDA(cudaMemset(s.cand_a, 0xff, 4 * (size_t)N));
@@ -1391,6 +1494,13 @@ static int mm_run(rp_minmatch *h, bool has_prior, int *merges, rp_minmatch_stats
         const dim3 grid((h->N + 31) / 32, (h->N + 31) / 32, has_prior ? 2 : 1);
         mm_transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(h->s.d, h->s.dT, h->s.cf, h->s.cfT, h->N);
     }
+    if (h->s.pre_init) {
+        const int rows = (h->N + 7) / 8, hc0 = has_prior ? 1 : 0;
+        mm_init_rowmin_kernel<<<rows, 256, 0, h->stream>>>(h->s, hc0);
+        mm_init_pairs_kernel<false><<<rows, 256, 0, h->stream>>>(h->s, hc0);
+        mm_init_scan_kernel<<<1, 1024, 0, h->stream>>>(h->s);
+        mm_init_pairs_kernel<true><<<rows, 256, 0, h->stream>>>(h->s, hc0);
+    }
     const int hc = has_prior ? 1 : 0;
 #define MM_LAUNCH(TH_)                                                                                             \
     do {                                                                                                           \
@@ -1417,7 +1527,7 @@ static int mm_run(rp_minmatch *h, bool has_prior, int *merges, rp_minmatch_stats
         st->fallback_steps = (int)h->h_info[2];
         st->general_steps = (int)h->h_info[3];
         st->medium_steps = (int)h->h_info[12];
-        st->launches = 2;
+        st->launches = h->s.pre_init ? 6 : 2;
     }
 #ifdef MM_PROF
     fprintf(stderr, "mm_prof cycles: init %lld | F %lld A %lld B %lld C %lld DE %lld sym %lld book %lld\n", h->h_info[4], h->h_info[5], h->h_info[6],
