@@ -1450,8 +1450,9 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
         MM_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         // one CTA per tree; the merge loop is bound by instruction issue on its SM, and everything every warp does per phase
         // (reductions, barriers) counts once per warp: few warps for small N (measured: N=200 1.24 / 1.30 / 1.67 ms per tree with
-        // 256 / 512 / 1024 threads, N=1000 10.4 / 9.7 / 11.0 ms, N=5000 134 / 101 / 100 ms)
-        h->threads = getenv("RP_MINMATCH_THREADS") ? atoi(getenv("RP_MINMATCH_THREADS")) : (N < 512 ? 256 : 512);
+        // 256 / 512 / 1024 threads, N=1000 10.4 / 9.7 / 11.0 ms, N=5000 134 / 101 / 100 ms on synthetic input and 160 / 146 ms
+        // with 512 / 1024 threads on real, tie-rich matrices)
+        h->threads = getenv("RP_MINMATCH_THREADS") ? atoi(getenv("RP_MINMATCH_THREADS")) : (N < 512 ? 256 : (N <= 2560 ? 512 : 1024));
         if (h->threads != 256 && h->threads != 512) h->threads = 1024;
         cudaFuncAttributes fa;
         const void *fn = h->threads == 256 ? (const void *)mm_quickbuild_kernel<256, true>
