@@ -588,11 +588,11 @@ __device__ bool meet_pairs_small(const MMState &s, MMShared &sh, bool has_cf, in
 // before u, or if q is outside U) and against row j, once, and keeps the outcomes as a bit mask; ballots and per-warp counts
 // turn the masks into the pairs' ranks in the reference's order (row position, then partner position).  Tie-rich data (many
 // identical haplotypes) has hundreds of feasible pairs in most steps — they pass through here.
-constexpr int MED_E = 20;
 template <int TH>
 __device__ bool meet_pairs_medium(const MMState &s, MMShared &sh, bool has_cf, int n_act, int ci, int cj, int n_u, int &rng_pos,
                                   long long &draws)
 {
+    constexpr int MED_E = TH <= 256 ? 4 : (TH <= 512 ? 20 : 10); // positions per thread: 256 threads serve N < 512, the others N <= 10 240
     if (n_u > 63 || n_act > TH * MED_E) return false;
     const size_t N = s.N;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
