@@ -1385,9 +1385,12 @@ extern "C" int rp_minmatch_create(int device, int N, double theta, rp_minmatch *
                                          (float)(-0.001 * std::log(theta / (1.0 - theta))), out);        // :44
 }
 
+static int mm_create(int device, int N, float threshold, float threshold_cf, rp_minmatch *h);
+
 extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold, float threshold_cf, rp_minmatch **out)
 {
     if (!out || N < 2) return rp::api_fail(RP_EINVAL, "rp_minmatch_create: bad argument");
+    *out = nullptr;
     int ndev = 0;
     MM_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return rp::api_fail(RP_ENODEVICE, "rp_minmatch_create: no such device");
@@ -1395,6 +1398,17 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
     auto *h = new rp_minmatch;
     h->device = device;
     h->N = N;
+    const int rc = mm_create(device, N, threshold, threshold_cf, h);
+    if (rc != RP_OK) {
+        rp_minmatch_destroy(h); // (keeps the error message: destroy does not touch it)
+        return rc;
+    }
+    *out = h;
+    return RP_OK;
+}
+
+static int mm_create(int device, int N, float threshold, float threshold_cf, rp_minmatch *h)
+{
     MMState &s = h->s;
     s.N = N;
     s.thr = threshold;
@@ -1416,7 +1430,7 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
     const size_t o_merges = take(8 * (size_t)N), o_wcnt = take(4 * 64 * ((size_t)N / 32 + 2));
     cudaError_t e = cudaMalloc(&h->block, off);
     if (e != cudaSuccess) {
-        delete h;
+        h->block = nullptr;
         return rp::api_fail(RP_ENOMEM, std::string("rp_minmatch_create: cudaMalloc: ") + cudaGetErrorString(e));
     }
     char *b = (char *)h->block;
@@ -1459,7 +1473,8 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
                          : h->threads == 512 ? (const void *)mm_quickbuild_kernel<512, true> : (const void *)mm_quickbuild_kernel<1024, true>;
         MM_CUDA(cudaFuncGetAttributes(&fa, fn));
         if (!getenv("RP_MINMATCH_NO_SMEM") && want + fa.sharedSizeBytes <= (size_t)max_optin) {
-            MM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+            // (a per-function setting shared by every handle of the process, whatever its N: the device's maximum, once and for all)
+            MM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - (int)fa.sharedSizeBytes));
             h->dyn_smem = want;
             s.use_smem = 1;
         }
@@ -1470,7 +1485,6 @@ extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold,
     MM_CUDA(cudaEventCreateWithFlags(&h->e2, cudaEventBlockingSync | cudaEventDisableTiming));
     MM_CUDA(cudaMallocHost(&h->h_merges, 8 * (size_t)N));
     MM_CUDA(cudaMallocHost(&h->h_info, 128));
-    *out = h;
     return RP_OK;
 }
 

@@ -91,6 +91,23 @@ def test_matrices_already_on_the_device():
             assert np.array_equal(dd.cpu().numpy(), d) and (pp is None or np.array_equal(pp.cpu().numpy(), prior))
 
 
+def test_handles_of_different_sizes_coexist():
+    """The opt-in shared-memory limit is a per-kernel setting shared by all handles: a small handle created after a large one
+    must not take the large one's shared memory away."""
+    big, small = 700, 520   # both run the 512-thread instance; 28 KB vs 21 KB of per-cluster state
+    rng = np.random.default_rng(3)
+    db, ds = mm_cases.matrix(rng, big, "tree"), mm_cases.matrix(rng, small, "tree")
+    want_b, _ = oracle.MinMatchOracle(big, mm_cases.THETA).quickbuild(db)
+    want_s, _ = oracle.MinMatchOracle(small, mm_cases.THETA).quickbuild(ds)
+    with capi.MinMatch(big, mm_cases.THETA) as gb:
+        with capi.MinMatch(small, mm_cases.THETA) as gs:
+            assert np.array_equal(gs.quickbuild(ds)[0], want_s)
+            assert np.array_equal(gb.quickbuild(db)[0], want_b)
+        gb2 = capi.MinMatch(big, mm_cases.THETA)
+        assert np.array_equal(gb2.quickbuild(db)[0], want_b)
+        gb2.close()
+
+
 def test_handle_state_is_per_handle():
     """Two handles fed the same sequence give the same trees; a fresh handle fed only the last (d, prior) need not."""
     N = 64
