@@ -234,6 +234,9 @@ int rp_minmatch_create(int device, int N, double theta, rp_minmatch **out);
 /* same from the two thresholds a MinMatch object holds (threshold, threshold_CF; tree_builder.cpp:43-44) */
 int rp_minmatch_create_thresholds(int device, int N, float threshold, float threshold_cf, rp_minmatch **out);
 void rp_minmatch_destroy(rp_minmatch *mm);
+/* back to the state of a freshly constructed MinMatch object (what a new `MinMatch tb(data)` is in the reference): lets a
+ * consumer that meets one object after the other (one per window) keep one handle and its N x N buffers */
+int rp_minmatch_reset(rp_minmatch *mm);
 /* d, d_prior on the host (d_prior NULL: the three-argument QuickBuild); merges: int [2*(N-1)] on the host */
 int rp_minmatch_quickbuild(rp_minmatch *mm, const float *d, const float *d_prior, int *merges, rp_minmatch_stats *stats);
 /* same with the matrices already in this device's memory (e.g. left there by the distance kernel) */

@@ -91,6 +91,7 @@ SYMBOLS = {
     "rp_minmatch_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.POINTER(_P)]),
     "rp_minmatch_create_thresholds": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(_P)]),
     "rp_minmatch_destroy": (None, [_P]),
+    "rp_minmatch_reset": (C.c_int, [_P]),
     "rp_minmatch_quickbuild": (C.c_int, [_P, _P, _P, _P, C.POINTER(RpMinMatchStats)]),
     "rp_minmatch_quickbuild_device": (C.c_int, [_P, _P, _P, _P, C.POINTER(RpMinMatchStats)]),
     "rp_rle_encode": (C.c_int, [_P, C.c_int, _P, _P]),
@@ -312,6 +313,10 @@ class MinMatch:
         st = RpMinMatchStats()
         check(lib().rp_minmatch_quickbuild_device(self._h, _P(dev_d), _P(dev_prior) if dev_prior else None, _ptr(merges), C.byref(st)))
         return merges, {n: getattr(st, n) for n, _ in st._fields_}
+
+    def reset(self):
+        """Back to the state of a freshly constructed MinMatch object."""
+        check(lib().rp_minmatch_reset(self._h))
 
     def close(self):
         if self._h:

@@ -1387,6 +1387,34 @@ extern "C" int rp_minmatch_create(int device, int N, double theta, rp_minmatch *
 
 static int mm_create(int device, int N, float threshold, float threshold_cf, rp_minmatch *h);
 
+#define RP_TRY_MM(expr)               \
+    do {                              \
+        int rc_ = (expr);             \
+        if (rc_ != RP_OK) return rc_; \
+    } while (0)
+
+// the state of a freshly constructed MinMatch object: min_values_CF = 0 (vector::resize), candidates name nobody (lin1 = lin2 = -1)
+static int mm_reset_state(rp_minmatch *h)
+{
+    const MMState &s = h->s;
+    const size_t n = 4 * (size_t)h->N;
+    MM_CUDA(cudaMemset(s.minv_cf, 0, n));
+    MM_CUDA(cudaMemset(s.cand_a, 0xff, n));
+    MM_CUDA(cudaMemset(s.cand_b, 0xff, n));
+    MM_CUDA(cudaMemset(s.csym_a, 0xff, n));
+    MM_CUDA(cudaMemset(s.csym_b, 0xff, n));
+    MM_CUDA(cudaMemset(s.csym_dist, 0x7f, n));
+    return RP_OK;
+}
+
+extern "C" int rp_minmatch_reset(rp_minmatch *h)
+{
+    if (!h) return rp::api_fail(RP_EINVAL, "rp_minmatch_reset: null argument");
+    MM_CUDA(cudaSetDevice(h->device));
+    MM_CUDA(cudaStreamSynchronize(h->stream));
+    return mm_reset_state(h);
+}
+
 extern "C" int rp_minmatch_create_thresholds(int device, int N, float threshold, float threshold_cf, rp_minmatch **out)
 {
     if (!out || N < 2) return rp::api_fail(RP_EINVAL, "rp_minmatch_create: bad argument");
@@ -1450,13 +1478,7 @@ static int mm_create(int device, int N, float threshold, float threshold_cf, rp_
     s.wcnt = (int *)(b + o_wcnt);
     s.init_cnt = (int *)(b + o_icnt);
     s.pre_init = getenv("RP_MINMATCH_PRE_INIT") ? atoi(getenv("RP_MINMATCH_PRE_INIT")) : 1;
-    // a fresh MinMatch object: min_values_CF = 0 (vector::resize), candidates name nobody (lin1 = lin2 = -1)
-    MM_CUDA(cudaMemset(s.minv_cf, 0, 4 * (size_t)N));
-    MM_CUDA(cudaMemset(s.cand_a, 0xff, 4 * (size_t)N));
-    MM_CUDA(cudaMemset(s.cand_b, 0xff, 4 * (size_t)N));
-    MM_CUDA(cudaMemset(s.csym_a, 0xff, 4 * (size_t)N));
-    MM_CUDA(cudaMemset(s.csym_b, 0xff, 4 * (size_t)N));
-    MM_CUDA(cudaMemset(s.csym_dist, 0x7f, 4 * (size_t)N));
+    RP_TRY_MM(mm_reset_state(h));
     s.force_general = getenv("RP_MINMATCH_GENERAL") ? atoi(getenv("RP_MINMATCH_GENERAL")) : 0;
     {
         const size_t n4 = ((size_t)N + 3) & ~(size_t)3, want = 40 * n4 + 16;

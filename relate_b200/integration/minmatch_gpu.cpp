@@ -16,7 +16,10 @@
 //                                  is, the CPU 0.6 ms per tree at N=200 and 16 ms at N=1000, 0.8 s at N=5000; measured on B200)
 //   RELATE_GPU_MINMATCH_VERIFY=1   build every tree both ways and abort on the first differing merge
 //   RELATE_GPU_MINMATCH_STATS=1    one line on stderr at exit: trees, seconds in QuickBuild, kernel seconds
+//   RELATE_GPU_MINMATCH_POOL=<n>   GPU handles kept (default 2): a new MinMatch object takes the least recently used one, reset;
+//                                  only objects that are in use at the same time need one each
 //   RELATE_GPU_DEVICE=<i>          CUDA device (default 0)
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -35,12 +38,17 @@ void rp_ref_minmatch_quickbuild_prior(MinMatch *self, CollapsedMatrix<float> &d,
 namespace {
 
 struct Builders {
-    std::vector<rp_minmatch *> handle;
+    // BuildTopology makes one MinMatch object per window, one after the other, and never tells when it is done with one: the
+    // handles (five N x N matrices each) are pooled and the least recently used one is reset for the next new object
+    struct Slot { rp_minmatch *h; int owner, N; long last_use; float thr, thr_cf; };
+    std::vector<Slot> pool;
+    int next_owner = 0;
+    long clock = 0;
     long trees = 0, trees_ref = 0, draws = 0, general_steps = 0, medium_steps = 0, fallback_steps = 0;
     double seconds = 0, kernel_seconds = 0;
     ~Builders()
     {
-        for (rp_minmatch *h : handle) rp_minmatch_destroy(h);
+        for (Slot &sl : pool) rp_minmatch_destroy(sl.h);
         if (getenv("RELATE_GPU_MINMATCH_STATS"))
             fprintf(stderr, "Relate_gpu: QuickBuild: %ld trees on the GPU (%ld by the reference's code), %.3f s in the call, %.3f s in the kernel; "
                             "%ld draws, %ld merge steps with more than 128 pairs, %ld on the any-size pair path, %ld on the symmetric fallback\n",
@@ -73,28 +81,51 @@ void store_tree(Tree &tree, const int *merges, int N)
 
 } // namespace
 
-// One GPU handle per MinMatch object.  A freshly constructed object has candidates_to_check_size == 0 (a member the
-// reference never touches after its in-class initialiser, tree_builder.hpp:56); the binding keeps "handle index + 1"
+// One GPU handle per MinMatch object in use.  A freshly constructed object has candidates_to_check_size == 0 (a member the
+// reference never touches after its in-class initialiser, tree_builder.hpp:56); the binding keeps the object's number
 // there, so that a new object — BuildTopology makes one per window — starts from fresh state as the reference's does.
 static void gpu_quickbuild(MinMatch *self, int &slot, int N, float threshold, float threshold_CF, CollapsedMatrix<float> &d,
                            const CollapsedMatrix<float> *prior, Tree &tree)
 {
-    if (slot == 0) {
-        rp_minmatch *h = nullptr;
-        const int device = getenv("RELATE_GPU_DEVICE") ? atoi(getenv("RELATE_GPU_DEVICE")) : 0;
-        if (rp_minmatch_create_thresholds(device, N, threshold, threshold_CF, &h) != RP_OK) {
-            fprintf(stderr, "Relate_gpu: rp_minmatch_create: %s\n", rp_last_error());
-            exit(1);
-        }
-        g.handle.push_back(h);
-        slot = (int)g.handle.size();
+    const size_t pool_max = getenv("RELATE_GPU_MINMATCH_POOL") ? (size_t)std::max(1, atoi(getenv("RELATE_GPU_MINMATCH_POOL"))) : 2;
+    Builders::Slot *mine = nullptr;
+    if (slot != 0)
+        for (Builders::Slot &sl : g.pool)
+            if (sl.owner == slot) mine = &sl;
+    if (slot != 0 && !mine) {
+        fprintf(stderr, "Relate_gpu: more than %zu MinMatch objects in use at once; raise RELATE_GPU_MINMATCH_POOL\n", pool_max);
+        exit(1);
     }
+    if (slot == 0) { // a new object: a new handle while the pool has room, else the least recently used one, reset
+        Builders::Slot *lru = nullptr;
+        for (Builders::Slot &sl : g.pool)
+            if (sl.N == N && sl.thr == threshold && sl.thr_cf == threshold_CF && (!lru || sl.last_use < lru->last_use)) lru = &sl;
+        if (g.pool.size() < pool_max || !lru) {
+            rp_minmatch *h = nullptr;
+            const int device = getenv("RELATE_GPU_DEVICE") ? atoi(getenv("RELATE_GPU_DEVICE")) : 0;
+            if (rp_minmatch_create_thresholds(device, N, threshold, threshold_CF, &h) != RP_OK) {
+                fprintf(stderr, "Relate_gpu: rp_minmatch_create: %s\n", rp_last_error());
+                exit(1);
+            }
+            g.pool.push_back({h, 0, N, 0, threshold, threshold_CF});
+            mine = &g.pool.back();
+        } else {
+            if (rp_minmatch_reset(lru->h) != RP_OK) {
+                fprintf(stderr, "Relate_gpu: rp_minmatch_reset: %s\n", rp_last_error());
+                exit(1);
+            }
+            mine = lru;
+        }
+        mine->owner = slot = ++g.next_owner;
+    }
+    mine->last_use = ++g.clock;
+    rp_minmatch *handle = mine->h;
     std::vector<int> merges(2 * (size_t)(N - 1));
     rp_minmatch_stats st;
     const CollapsedMatrix<float> *use_prior = (prior && prior->size() == d.size()) ? prior : nullptr;
     // d_CF = d_prior, or d itself when the prior has another size (:2365-2368)
     const float *prior_ptr = prior ? (use_prior ? &(*use_prior)[0][0] : &d[0][0]) : nullptr;
-    if (rp_minmatch_quickbuild(g.handle[slot - 1], &d[0][0], prior_ptr, merges.data(), &st) != RP_OK) {
+    if (rp_minmatch_quickbuild(handle, &d[0][0], prior_ptr, merges.data(), &st) != RP_OK) {
         fprintf(stderr, "Relate_gpu: rp_minmatch_quickbuild: %s\n", rp_last_error());
         exit(1);
     }

@@ -108,6 +108,20 @@ def test_handles_of_different_sizes_coexist():
         gb2.close()
 
 
+def test_reset_gives_a_fresh_object():
+    """rp_minmatch_reset: the same tree sequence before and after a reset gives the same trees (state carried from tree to tree
+    would change the second pass otherwise: the sequence is NOT idempotent without the reset)."""
+    N = 96
+    o = oracle.MinMatchOracle(N, mm_cases.THETA)
+    trees = mm_cases.tree_sequence(12, N, "blocks", 4, oracle.prior_from_merges, lambda d, p: o.quickbuild(d, p)[0])
+    with capi.MinMatch(N, mm_cases.THETA) as g:
+        first = [g.quickbuild(d, p)[0] for d, p in trees]
+        g.reset()
+        second = [g.quickbuild(d, p)[0] for d, p in trees]
+    for a, b in zip(first, second):
+        assert np.array_equal(a, b)
+
+
 def test_handle_state_is_per_handle():
     """Two handles fed the same sequence give the same trees; a fresh handle fed only the last (d, prior) need not."""
     N = 64
