@@ -9,7 +9,7 @@
 //     every other stage delegated to the reference binary;
 //   * every other mode is handed to the reference binary unchanged (exec).
 // The reference binary is found via $RELATE_REFERENCE_BIN, else "<dir of this exe>/Relate.ref".
-// Extra flags of this build (stripped before delegating): --gpus a,b,c   --fp64   --chunks a-b   --resident
+// Extra flags of this build (stripped before delegating): --gpus a,b,c   --fp64   --chunks a-b   --resident   --gpu_topology
 // `--resident` (modes BuildTopology and All) runs BuildTopology in `Relate_gpu` — the reference linked with this repo's
 // binding of DistanceMeasure::GetMatrix (relate_b200/integration/; found via $RELATE_GPU_BIN, else next to this
 // executable) — with the stepping stones kept in HBM: no paint files are written or read.
@@ -73,6 +73,7 @@ const Flag kFlags[] = {
     {"fp64", 0, false, "(relate_b200) fp64 state in the painting kernel (verification mode)."},
     {"chunks", 0, true, "(relate_b200) --mode Paint: paint chunks a-b (instead of --chunk_index), whole chunks per GPU."},
     {"resident", 0, false, "(relate_b200) BuildTopology / All: distance matrices from stepping stones resident in HBM (needs Relate_gpu); no paint files."},
+    {"gpu_topology", 0, false, "(relate_b200) BuildTopology / All: distance matrices and trees on the GPU from the paint files (needs Relate_gpu)."},
 };
 
 void print_help()
@@ -140,7 +141,8 @@ bool parse(int argc, char **argv, Args &a, std::string &err)
         }
         a.present.insert(f->name);
         a.val[f->name] = value;
-        const bool ours = !strcmp(f->name, "gpus") || !strcmp(f->name, "fp64") || !strcmp(f->name, "chunks") || !strcmp(f->name, "resident");
+        const bool ours = !strcmp(f->name, "gpus") || !strcmp(f->name, "fp64") || !strcmp(f->name, "chunks") || !strcmp(f->name, "resident") ||
+                          !strcmp(f->name, "gpu_topology");
         if (!ours) {
             a.passthrough.push_back(std::string("--") + f->name);
             if (f->has_value) a.passthrough.push_back(value);
@@ -350,11 +352,14 @@ int main(int argc, char **argv)
     }
 
     const bool resident = a.count("resident") != 0;
+    // --gpu_topology: BuildTopology in Relate_gpu as well (window repaint, distance matrices and trees on the GPU), but from the
+    // paint files a Paint stage wrote
+    const bool gpu_topology = a.count("gpu_topology") != 0;
     std::string gpu_bin;
-    if (resident) {
+    if (resident || gpu_topology) {
         gpu_bin = gpu_consumer_binary(argv[0]);
         if (gpu_bin.empty()) {
-            std::cerr << "relate: --resident needs Relate_gpu (make -C relate_b200/integration REF=<reference checkout>; or set RELATE_GPU_BIN)." << std::endl;
+            std::cerr << "relate: --resident / --gpu_topology need Relate_gpu (make -C relate_b200/integration REF=<reference checkout>; or set RELATE_GPU_BIN)." << std::endl;
             return 1;
         }
     }
@@ -366,6 +371,7 @@ int main(int argc, char **argv)
         }
         return run_reference(gpu_bin, a.passthrough, true);
     }
+    if (mode == "BuildTopology" && gpu_topology) return run_reference(gpu_bin, a.passthrough, false);
 
     if (mode == "All") { // Relate.cpp:190-296 with Paint native
         if (a.count("help") || !a.count("output") ||
@@ -423,7 +429,7 @@ int main(int argc, char **argv)
                 if (rc) return rc;
                 if (c < end_chunk) ahead = start_paint(c + 1);
                 // (an error return below waits for the background painter: a std::async future joins in its destructor)
-                if ((rc = run_reference(ref, with_mode(a, "BuildTopology", {"--chunk_index", cs, "--first_section", "0", "--last_section", ls})))) return rc;
+                if ((rc = run_reference(gpu_topology ? gpu_bin : ref, with_mode(a, "BuildTopology", {"--chunk_index", cs, "--first_section", "0", "--last_section", ls})))) return rc;
             }
             if ((rc = run_reference(ref, with_mode(a, "FindEquivalentBranches", {"--chunk_index", cs})))) return rc;
             if (a.count("postprocess")) {

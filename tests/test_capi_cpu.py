@@ -114,7 +114,8 @@ def test_cli_flag_surface(tmp_path):
     # every reference flag is accepted (scripts pass a fixed set)
     flags = ["--haps", "h", "--sample", "s", "--map", "m", "-m", "1.25e-8", "-N", "30000", "--memory", "5", "--seed", "1",
              "--dist", "d", "--annot", "a", "--sample_ages", "x", "--coal", "c", "--fb", "1", "--no_consistency",
-             "--transversion", "--first_section", "0", "--last_section", "1", "-i", "in", "--painting", "0.001,1"]
+             "--transversion", "--first_section", "0", "--last_section", "1", "-i", "in", "--painting", "0.001,1",
+             "--resident", "--gpu_topology", "--fp64"]
     p = subprocess.run([exe, "--mode", "Paint"] + flags, capture_output=True, text=True)
     assert p.returncode == 0 and "Needed: chunk_index, output." in p.stdout
 

@@ -197,3 +197,26 @@ def test_buildtopology_gpu_trees_byte_identical_to_cpu_trees(tmp_path, N, L, W):
     print(f"\nBuildTopology N={N} L={L}: {b['gpu_trees']} trees; QuickBuild on the CPU {a['call_s']:.3f} s "
           f"({1e3 * a['call_s'] / a['ref_trees']:.2f} ms/tree), on the GPU {b['call_s']:.3f} s in the call, {b['kernel_s']:.3f} s in the "
           f"kernel ({1e3 * b['kernel_s'] / b['gpu_trees']:.2f} ms/tree); BuildTopology wall {a['wall']:.2f} s -> {b['wall']:.2f} s")
+
+
+@need_relate_gpu
+def test_cli_gpu_topology_flag(tmp_path):
+    """`relate --mode BuildTopology --gpu_topology` = BuildTopology in Relate_gpu (GPU window repaint, distance matrices and trees)
+    on the paint files `relate --mode Paint` wrote: the same files as running Relate_gpu by hand."""
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "relate_b200", "bin", "relate")
+    N, L, W = 200, 2000, 2
+    for tag in ("cli", "direct"):
+        synth.make_chunk_dir(str(tmp_path / tag / "o"), N, L, seed=33, n_windows=W)
+    env = dict(os.environ, RELATE_REFERENCE_BIN=oracle.REF_RELATE, RELATE_GPU_BIN=oracle.REF_RELATE_GPU, RELATE_GPU_MINMATCH_MIN_N="0")
+    bt = ["--mode", "BuildTopology", "--chunk_index", "0", "--first_section", "0", "--last_section", str(W - 1), "-o", "o",
+          "--painting", "0.001,1", "--seed", "1"]
+    for tag, cmd in (("cli", [exe] + bt + ["--gpu_topology"]), ("direct", [oracle.REF_RELATE_GPU] + bt)):
+        p = subprocess.run([exe, "--mode", "Paint", "--chunk_index", "0", "-o", "o", "--painting", "0.001,1"], cwd=str(tmp_path / tag),
+                           capture_output=True, text=True, env=env)
+        assert p.returncode == 0, p.stderr[-1000:]
+        p = subprocess.run(cmd, cwd=str(tmp_path / tag), capture_output=True, text=True, env=env)
+        assert p.returncode == 0, p.stderr[-1000:]
+    for w in range(W):
+        for ext in ("anc", "mut"):
+            assert filecmp.cmp(str(tmp_path / "cli" / "o" / "chunk_0" / f"o_{w}.{ext}"),
+                               str(tmp_path / "direct" / "o" / "chunk_0" / f"o_{w}.{ext}"), shallow=False), (w, ext)
