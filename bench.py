@@ -419,7 +419,7 @@ def sharded_leg(name, devices, peaks, reps=3):
 
 
 # --------------------------------------------------------------------------------------------------
-def tree_builder_leg(device, sizes=((1000, 3), (5000, 2))):
+def tree_builder_leg(device, sizes=((1000, 3), (5000, 2), (10000, 2))):
     """Row f4: rp_minmatch_quickbuild (one CTA per tree) on seeded GetMatrix-shaped matrix sequences (tests/mm_cases.py: the
     first tree without a prior, the next with the prior BuildTopology derives from the previous tree) against the reference's
     own MinMatch::QuickBuild timed on one host core (oracle/_ref/qblens; the oracle port if the lens did not travel).  Checks
